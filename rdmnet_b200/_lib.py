@@ -1,0 +1,74 @@
+"""ctypes loader for librdm_sm100.so (the C ABI of include/rdm_sm100.h). Fails loudly: no fallback."""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librdm_sm100.so")
+_lib = None
+
+c_void_p, c_int, c_i64, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol of include/rdm_sm100.h (tests/test_abi_cpu.py checks it)
+SIGNATURES = {
+    "rdm_last_error": (ctypes.c_char_p, []),
+    "rdm_version": (c_int, []),
+    "rdm_grid_subsample_workspace": (c_size_t, [c_i64, c_int]),
+    "rdm_grid_subsample": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "rdm_selfcheck_bucket_table": (c_int, [c_i64]),
+    "rdm_radius_search_workspace": (c_size_t, [c_i64, c_int]),
+    "rdm_radius_search": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_float, c_int,
+                                  c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "rdm_kpconv_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_float, c_int, c_int, c_int,
+                                  c_int, c_void_p, c_void_p, c_void_p]),
+    "rdm_maxpool": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "rdm_upsample_concat": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "rdm_linear_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "rdm_linear": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                           c_void_p, c_size_t, c_void_p]),
+    "rdm_groupnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int,
+                              c_float, c_void_p, c_void_p]),
+    "rdm_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p]),
+    "rdm_activation": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_float, c_void_p]),
+}
+
+
+def lib():
+    """Returns the loaded library, raising RuntimeError if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(make -C rdmnet_b200/csrc). rdmnet_b200 has no CPU or PyTorch fallback.")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def ptr(t):
+    """Device pointer of a CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("rdmnet_b200: expected a CUDA tensor (there is no CPU path)")
+    if not t.is_contiguous():
+        raise RuntimeError("rdmnet_b200: expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def check(code, what):
+    if code != 0:
+        raise RuntimeError(f"{what} failed (code {code}): {lib().rdm_last_error().decode()}")
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args), name)

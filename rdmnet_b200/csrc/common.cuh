@@ -1,0 +1,124 @@
+// Shared helpers for librdm_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define RDM_OK 0
+#define RDM_ERR_ARG 1
+#define RDM_ERR_CUDA 2
+#define RDM_ERR_WORKSPACE 3
+
+void rdm_set_error(const char* fmt, ...);
+
+#define RDM_CHECK_ARG(cond, ...)  \
+  do {                            \
+    if (!(cond)) {                \
+      rdm_set_error(__VA_ARGS__); \
+      return RDM_ERR_ARG;         \
+    }                             \
+  } while (0)
+
+#define RDM_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      rdm_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return RDM_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+#define RDM_LAUNCH_CHECK() RDM_CUDA(cudaGetLastError())
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over a caller-provided workspace.
+struct Workspace {
+  char* base;
+  size_t size, off;
+  bool ok;
+  __host__ Workspace(void* p, size_t n) : base((char*)p), size(n), off(0), ok(true) {}
+  template <typename T>
+  __host__ T* get(size_t count) {
+    off = align_up(off, 256);
+    T* r = (T*)(base + off);
+    off += count * sizeof(T);
+    if (off > size) ok = false;
+    return r;
+  }
+};
+
+#ifdef __CUDACC__
+#define FULL_MASK 0xffffffffu
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+
+// Block-wide exclusive scan of one int per thread (blockDim.x <= 1024, multiple of 32).
+// `smem` must hold 33 ints. Returns exclusive prefix; *total gets the block sum.
+__device__ __forceinline__ int block_exclusive_scan(int v, int* smem, int* total) {
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(FULL_MASK, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();  // protect smem reuse across calls
+  if (lane == 31) smem[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < nw ? smem[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(FULL_MASK, winc, o);
+      if (lane >= o) winc += t;
+    }
+    smem[lane] = winc - w;  // exclusive warp offsets
+    if (lane == 31) smem[32] = winc;
+  }
+  __syncthreads();
+  *total = smem[32];
+  return smem[warp] + inc - v;
+}
+
+// In-warp bitonic sort (ascending) of n (power of two, >= 32... or any pow2) 64-bit keys held in shared memory.
+__device__ __forceinline__ void warp_bitonic_sort_u64(unsigned long long* a, int n, int lane) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < (n >> 1); t += 32) {
+        // element pair (i, i^j) with i having bit j clear
+        int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        int p = i | j;
+        unsigned long long x = a[i], y = a[p];
+        bool up = ((i & k) == 0);
+        if ((x > y) == up) {
+          a[i] = y;
+          a[p] = x;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+#endif

@@ -1,0 +1,364 @@
+// Dense building blocks of the backbone / transformer: fp32 GEMM (Linear, KPConv weight contraction),
+// GroupNorm(+residual)(+LeakyReLU) over stacked (N, C) features, LayerNorm(+residual)(+ReLU).
+//
+// Reference semantics: torch.nn.Linear; geotransformer/modules/kpconv/modules.py:33-50 (GroupNorm over (1,C,N), eps 1e-5,
+// statistics joint over both clouds), :78-83, :205-225 (residual + LeakyReLU(0.1)); torch.nn.LayerNorm (eps 1e-5).
+#include "common.cuh"
+#include "../../include/rdm_sm100.h"
+
+// ------------------------------------------------------------------------------------------------------- GEMM
+// C[M,N] = A[M,K] * B + bias.  B_NK: B is [N,K] row-major (nn.Linear weight), else [K,N] row-major (KPConv weights).
+// 256 threads, BK = 16, each thread owns a (TM x TN) micro-tile split in 4-wide halves to keep LDS.128 conflict-free.
+#define GEMM_BK 16
+
+template <int BM, int BN, bool B_NK>
+__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B,
+                                                    int ldb, const float* __restrict__ bias, float* __restrict__ C,
+                                                    int ldc, int M, int N, int K, int k_per_split, int vecA, int vecB,
+                                                    int vecC) {
+  constexpr int TM = BM / 16, TN = BN / 16;  // 8x8 (128 tile) or 4x4 (64 tile)
+  constexpr int PAD = 4;
+  __shared__ __align__(16) float As[2][GEMM_BK][BM + PAD];
+  __shared__ __align__(16) float Bs[2][GEMM_BK][BN + PAD];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kb = blockIdx.z * k_per_split, ke = min(K, kb + k_per_split);
+  if (gridDim.z > 1) C += (size_t)blockIdx.z * M * N;  // split-K partial buffers (ldc == N there)
+
+  // loader geometry for "row-major with K contiguous" operands (A always, B when B_NK): rows x 4 float4
+  constexpr int A_PASSES = BM / 64, BNK_PASSES = BN / 64;
+  // loader for B [K,N]: 16 rows x (BN/4) float4
+  constexpr int BKN_PER_THREAD = (GEMM_BK * BN / 4) / 256;
+  float4 ra[A_PASSES], rb[B_NK ? BNK_PASSES : BKN_PER_THREAD];
+
+  auto load_rowmajor_k = [&](const float* P, int ld, int row, int rows_total, int k, int vec) -> float4 {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < rows_total) {
+      const float* p = P + (size_t)row * ld + k;
+      if (vec && k + 3 < ke) {
+        v = *(const float4*)p;
+      } else {
+        if (k < ke) v.x = p[0];
+        if (k + 1 < ke) v.y = p[1];
+        if (k + 2 < ke) v.z = p[2];
+        if (k + 3 < ke) v.w = p[3];
+      }
+    }
+    return v;
+  };
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int p = 0; p < A_PASSES; p++) {
+      int row = (tid >> 2) + p * 64, kq = (tid & 3) * 4;
+      ra[p] = load_rowmajor_k(A, lda, m0 + row, M, k0 + kq, vecA);
+    }
+    if constexpr (B_NK) {
+#pragma unroll
+      for (int p = 0; p < BNK_PASSES; p++) {
+        int row = (tid >> 2) + p * 64, kq = (tid & 3) * 4;
+        rb[p] = load_rowmajor_k(B, ldb, n0 + row, N, k0 + kq, vecB);
+      }
+    } else {
+#pragma unroll
+      for (int p = 0; p < BKN_PER_THREAD; p++) {
+        int e = tid + p * 256;
+        int kr = e / (BN / 4), nq = (e % (BN / 4)) * 4;
+        int k = k0 + kr, n = n0 + nq;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < ke) {
+          const float* pB = B + (size_t)k * ldb + n;
+          if (vecB && n + 3 < N) {
+            v = *(const float4*)pB;
+          } else {
+            if (n < N) v.x = pB[0];
+            if (n + 1 < N) v.y = pB[1];
+            if (n + 2 < N) v.z = pB[2];
+            if (n + 3 < N) v.w = pB[3];
+          }
+        }
+        rb[p] = v;
+      }
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int p = 0; p < A_PASSES; p++) {
+      int row = (tid >> 2) + p * 64, kq = (tid & 3) * 4;
+      As[buf][kq + 0][row] = ra[p].x;
+      As[buf][kq + 1][row] = ra[p].y;
+      As[buf][kq + 2][row] = ra[p].z;
+      As[buf][kq + 3][row] = ra[p].w;
+    }
+    if constexpr (B_NK) {
+#pragma unroll
+      for (int p = 0; p < BNK_PASSES; p++) {
+        int row = (tid >> 2) + p * 64, kq = (tid & 3) * 4;
+        Bs[buf][kq + 0][row] = rb[p].x;
+        Bs[buf][kq + 1][row] = rb[p].y;
+        Bs[buf][kq + 2][row] = rb[p].z;
+        Bs[buf][kq + 3][row] = rb[p].w;
+      }
+    } else {
+#pragma unroll
+      for (int p = 0; p < BKN_PER_THREAD; p++) {
+        int e = tid + p * 256;
+        int kr = e / (BN / 4), nq = (e % (BN / 4)) * 4;
+        *(float4*)&Bs[buf][kr][nq] = rb[p];
+      }
+    }
+  };
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; i++)
+#pragma unroll
+    for (int j = 0; j < TN; j++) acc[i][j] = 0.f;
+
+  int nk = (ke - kb + GEMM_BK - 1) / GEMM_BK;
+  if (nk > 0) {
+    load_tiles(kb);
+    store_tiles(0);
+  }
+  __syncthreads();
+  for (int t = 0; t < nk; t++) {
+    int buf = t & 1;
+    if (t + 1 < nk) load_tiles(kb + (t + 1) * GEMM_BK);
+#pragma unroll
+    for (int k = 0; k < GEMM_BK; k++) {
+      float a[TM], b[TN];
+      if constexpr (TM == 8) {
+        float4 a0 = *(const float4*)&As[buf][k][ty * 4], a1 = *(const float4*)&As[buf][k][BM / 2 + ty * 4];
+        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      } else {
+        float4 a0 = *(const float4*)&As[buf][k][ty * 4];
+        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+      }
+      if constexpr (TN == 8) {
+        float4 b0 = *(const float4*)&Bs[buf][k][tx * 4], b1 = *(const float4*)&Bs[buf][k][BN / 2 + tx * 4];
+        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+      } else {
+        float4 b0 = *(const float4*)&Bs[buf][k][tx * 4];
+        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (t + 1 < nk) store_tiles(buf ^ 1);
+    __syncthreads();
+  }
+  // epilogue
+  const bool add_bias = (bias != nullptr) && gridDim.z == 1;
+#pragma unroll
+  for (int i = 0; i < TM; i++) {
+    int row = m0 + ((TM == 8 && i >= 4) ? BM / 2 + ty * 4 + (i - 4) : ty * 4 + i);
+    if (row >= M) continue;
+#pragma unroll
+    for (int jh = 0; jh < TN / 4; jh++) {
+      int col = n0 + (jh == 0 ? tx * 4 : BN / 2 + tx * 4);
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        v[j] = acc[i][jh * 4 + j];
+        if (add_bias && col + j < N) v[j] += bias[col + j];
+      }
+      float* cp = C + (size_t)row * ldc + col;
+      if (vecC && col + 3 < N) {
+        *(float4*)cp = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (col + j < N) cp[j] = v[j];
+      }
+    }
+  }
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, const float* __restrict__ bias,
+                                     float* __restrict__ C, int ldc, int M, int N) {
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= (long long)M * N) return;
+  int m = (int)(e / N), n = (int)(e - (long long)m * N);
+  float s = 0.f;
+  for (int z = 0; z < splits; z++) s += part[(size_t)z * M * N + e];
+  if (bias) s += bias[n];
+  C[(size_t)m * ldc + n] = s;
+}
+
+static inline int aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+extern "C" size_t rdm_linear_workspace(int M, int N, int K) {
+  // worst case: 16 split-K partial buffers
+  return (size_t)16 * M * N * sizeof(float) + 256;
+}
+
+extern "C" int rdm_linear(const float* A, int lda, const float* B, int ldb, int b_is_nk, const float* bias, float* C,
+                          int ldc, int M, int N, int K, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  RDM_CHECK_ARG(M >= 0 && N >= 1 && K >= 1, "rdm_linear: bad shape M=%d N=%d K=%d", M, N, K);
+  if (M == 0) return RDM_OK;
+  int vecA = (lda % 4 == 0) && aligned16(A), vecB = (ldb % 4 == 0) && aligned16(B), vecC = (ldc % 4 == 0) && aligned16(C);
+  long long t128 = (long long)cdiv(M, 128) * cdiv(N, 128), t64 = (long long)cdiv(M, 64) * cdiv(N, 64);
+  bool big = t128 >= 120;
+  int splits = 1;
+  if (!big && t64 < 120 && workspace != nullptr) {
+    splits = (int)min((long long)16, max((long long)1, (296 + t64 - 1) / t64));
+    splits = min(splits, max(1, K / 256));
+    while (splits > 1 && (size_t)splits * M * N * sizeof(float) > workspace_bytes) splits--;
+  }
+  int kps = cdiv(cdiv(K, splits), GEMM_BK) * GEMM_BK;
+  splits = cdiv(K, kps);
+  float* out = splits > 1 ? (float*)workspace : C;
+  int ldo = splits > 1 ? N : ldc;
+  int vecO = splits > 1 ? ((N % 4 == 0) && aligned16(workspace)) : vecC;
+  if (big) {
+    dim3 grid(cdiv(N, 128), cdiv(M, 128), 1);
+    if (b_is_nk)
+      sgemm_kernel<128, 128, true><<<grid, 256, 0, stream>>>(A, lda, B, ldb, bias, out, ldo, M, N, K, kps, vecA, vecB, vecO);
+    else
+      sgemm_kernel<128, 128, false><<<grid, 256, 0, stream>>>(A, lda, B, ldb, bias, out, ldo, M, N, K, kps, vecA, vecB, vecO);
+  } else {
+    dim3 grid(cdiv(N, 64), cdiv(M, 64), splits);
+    if (b_is_nk)
+      sgemm_kernel<64, 64, true><<<grid, 256, 0, stream>>>(A, lda, B, ldb, bias, out, ldo, M, N, K, kps, vecA, vecB, vecO);
+    else
+      sgemm_kernel<64, 64, false><<<grid, 256, 0, stream>>>(A, lda, B, ldb, bias, out, ldo, M, N, K, kps, vecA, vecB, vecO);
+  }
+  RDM_LAUNCH_CHECK();
+  if (splits > 1) {
+    splitk_reduce_kernel<<<cdiv((long long)M * N, 256), 256, 0, stream>>>((const float*)workspace, splits, bias, C, ldc, M, N);
+    RDM_LAUNCH_CHECK();
+  }
+  return RDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- GroupNorm
+// stats[g] = {sum, sumsq} (double) over rows x (C/G) channels of group g.
+__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const float* __restrict__ x, int N, int C, int G,
+                                                              int rows_per_cta, double* __restrict__ stats) {
+  extern __shared__ float s_part[];  // [2*C]
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
+  for (int c = tid; c < C; c += 256) {
+    float s = 0.f, ss = 0.f;
+    for (int r = r0; r < r1; r++) {
+      float v = x[(size_t)r * C + c];
+      s += v;
+      ss = fmaf(v, v, ss);
+    }
+    s_part[c] = s;
+    s_part[C + c] = ss;
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int g = tid; g < G; g += 256) {
+    double s = 0.0, ss = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; c++) {
+      s += (double)s_part[c];
+      ss += (double)s_part[C + c];
+    }
+    atomicAdd(&stats[2 * g], s);
+    atomicAdd(&stats[2 * g + 1], ss);
+  }
+}
+
+// y = act( (x - mean_g) * rstd_g * gamma_c + beta_c (+ res) ),  act: 0 none, 1 LeakyReLU(slope)
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float* __restrict__ x,
+                                                              const double* __restrict__ stats,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta,
+                                                              const float* __restrict__ res, float* __restrict__ y, int N,
+                                                              int C, int G, float eps, int act, float slope) {
+  extern __shared__ float s_ms[];  // mean[G], rstd[G]
+  const int tid = threadIdx.x;
+  const int cpg = C / G;
+  for (int g = tid; g < G; g += 256) {
+    double cnt = (double)N * cpg;
+    double mean = stats[2 * g] / cnt;
+    double var = stats[2 * g + 1] / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_ms[g] = (float)mean;
+    s_ms[G + g] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  long long total = (long long)N * C;
+  for (long long e = blockIdx.x * 256LL + tid; e < total; e += (long long)gridDim.x * 256) {
+    int c = (int)(e % C), g = c / cpg;
+    float v = (x[e] - s_ms[g]) * s_ms[G + g] * gamma[c] + beta[c];
+    if (res) v += res[e];
+    if (act == 1) v = v > 0.f ? v : v * slope;
+    y[e] = v;
+  }
+}
+
+extern "C" int rdm_groupnorm(const float* x, const float* gamma, const float* beta, const float* residual, float* y,
+                             int N, int C, int groups, float eps, int act, float slope, double* stats_scratch,
+                             cudaStream_t stream) {
+  RDM_CHECK_ARG(N >= 0 && C >= 1 && groups >= 1 && C % groups == 0, "rdm_groupnorm: C=%d not divisible by groups=%d", C, groups);
+  RDM_CHECK_ARG(groups <= 1024 && C <= 6144, "rdm_groupnorm: shape too large");
+  if (N == 0) return RDM_OK;
+  RDM_CUDA(cudaMemsetAsync(stats_scratch, 0, sizeof(double) * 2 * groups, stream));
+  int rows = 64;
+  while (rows > 4 && cdiv(N, rows) < 296) rows >>= 1;
+  groupnorm_stats_kernel<<<cdiv(N, rows), 256, 2 * C * sizeof(float), stream>>>(x, N, C, groups, rows, stats_scratch);
+  RDM_LAUNCH_CHECK();
+  long long total = (long long)N * C;
+  int grid = (int)min((long long)148 * 8, (total + 255) / 256);
+  groupnorm_apply_kernel<<<grid, 256, 2 * groups * sizeof(float), stream>>>(x, stats_scratch, gamma, beta, residual, y, N,
+                                                                           C, groups, eps, act, slope);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- LayerNorm
+// y[r] = act( LN(x[r] + res[r]) * gamma + beta ), one warp per row. act: 0 none, 2 ReLU.
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float* __restrict__ y, int N, int C, float eps, int act) {
+  int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float* xr = x + (size_t)row * C;
+  const float* rr = res ? res + (size_t)row * C : nullptr;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += xr[c] + (rr ? rr[c] : 0.f);
+  float mean = warp_sum(s) / (float)C;
+  float ss = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    float d = xr[c] + (rr ? rr[c] : 0.f) - mean;
+    ss = fmaf(d, d, ss);
+  }
+  float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
+  for (int c = lane; c < C; c += 32) {
+    float v = (xr[c] + (rr ? rr[c] : 0.f) - mean) * rstd * gamma[c] + beta[c];
+    if (act == 2) v = fmaxf(v, 0.f);
+    y[(size_t)row * C + c] = v;
+  }
+}
+
+extern "C" int rdm_layernorm(const float* x, const float* residual, const float* gamma, const float* beta, float* y,
+                             int N, int C, float eps, int act, cudaStream_t stream) {
+  RDM_CHECK_ARG(N >= 0 && C >= 1, "rdm_layernorm: bad shape");
+  if (N == 0) return RDM_OK;
+  layernorm_kernel<<<cdiv(N, 8), 256, 0, stream>>>(x, residual, gamma, beta, y, N, C, eps, act);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- small elementwise
+// y = act(x): 1 LeakyReLU(slope), 2 ReLU, 3 sigmoid clamped to [0,1]
+__global__ void activation_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, int act, float slope) {
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float v = x[e];
+  if (act == 1) v = v > 0.f ? v : v * slope;
+  else if (act == 2) v = fmaxf(v, 0.f);
+  else if (act == 3) v = fminf(fmaxf(1.f / (1.f + expf(-v)), 0.f), 1.f);
+  y[e] = v;
+}
+
+extern "C" int rdm_activation(const float* x, float* y, int64_t n, int act, float slope, cudaStream_t stream) {
+  if (n <= 0) return RDM_OK;
+  activation_kernel<<<cdiv(n, 256), 256, 0, stream>>>(x, y, n, act, slope);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}

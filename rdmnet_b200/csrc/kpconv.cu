@@ -1,0 +1,295 @@
+// KPConv neighbour-gather kernels (the HBM/L2-bound part of the backbone) + strided max-pool + nearest upsample.
+//
+// Reference semantics: geotransformer/modules/kpconv/kpconv.py:79-122 (KPConv.forward),
+// geotransformer/modules/kpconv/functional.py:6-22 (nearest_upsample), :54-67 (maxpool).
+//
+// KPConv is split in two: (1) kpconv_gather: A[m, k, c] = (1/cnt_m) * sum_h w[m,h,k] * F[idx[m,h], c]   (this file)
+//                         (2) a dense GEMM  out = A.view(M, 15*C_in) @ W.view(15*C_in, C_out) + bias      (dense.cu)
+// with w = max(0, 1 - |s[idx] - q - kp_k| / sigma) and cnt_m = max(1, #{h : sum_c F[idx[m,h], c] > 0}).
+// The (M,H,K,3) / (M,H,C) temporaries the reference materialises in HBM never exist; per CTA the 15 influences of
+// each neighbour are computed once into shared memory and re-used by all channel slices.
+#include "common.cuh"
+#include "../../include/rdm_sm100.h"
+
+#define KP_K 15
+
+// flag[n] = (sum_c F[n,c] > 0)   (kpconv.py:113-114)
+__global__ void row_positive_kernel(const float* __restrict__ f, int n, int c, unsigned char* __restrict__ flag) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  float s = 0.f;
+  for (int i = lane; i < c; i += 32) s += f[(size_t)row * c + i];
+  s = warp_sum(s);
+  if (lane == 0) flag[row] = s > 0.f ? 1 : 0;
+}
+
+// C_in == 1 (encoder1_1): one warp per query, lanes over neighbours.
+template <typename IdxT>
+__global__ void __launch_bounds__(256) kpconv_gather_c1_kernel(const float* __restrict__ feats,
+                                                               const float* __restrict__ q_pts,
+                                                               const float* __restrict__ s_pts,
+                                                               const IdxT* __restrict__ idx,
+                                                               const float* __restrict__ kpts, float sigma, int M, int N,
+                                                               int H, float* __restrict__ out) {
+  __shared__ float s_kp[KP_K * 3];
+  if (threadIdx.x < KP_K * 3) s_kp[threadIdx.x] = kpts[threadIdx.x];
+  __syncthreads();
+  int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= M) return;
+  float qx = q_pts[3 * m], qy = q_pts[3 * m + 1], qz = q_pts[3 * m + 2];
+  float acc[KP_K];
+#pragma unroll
+  for (int k = 0; k < KP_K; k++) acc[k] = 0.f;
+  int cnt = 0;
+  for (int h = lane; h < H; h += 32) {
+    long long j = (long long)idx[(size_t)m * H + h];
+    if (j >= N) continue;
+    float f = feats[j];
+    cnt += f > 0.f;
+    float dx = s_pts[3 * j] - qx, dy = s_pts[3 * j + 1] - qy, dz = s_pts[3 * j + 2] - qz;
+#pragma unroll
+    for (int k = 0; k < KP_K; k++) {
+      float ex = dx - s_kp[3 * k], ey = dy - s_kp[3 * k + 1], ez = dz - s_kp[3 * k + 2];
+      float w = fmaxf(0.f, 1.f - sqrtf(ex * ex + ey * ey + ez * ez) / sigma);
+      acc[k] += w * f;
+    }
+  }
+  cnt = warp_sum_i(cnt);
+  float inv = 1.f / (float)max(cnt, 1);
+#pragma unroll
+  for (int k = 0; k < KP_K; k++) {
+    float v = warp_sum(acc[k]);
+    if (lane == k) out[(size_t)m * KP_K + k] = v * inv;
+  }
+}
+
+// General case. CTA = 8 warps = QPC queries x NS channel slices (slice = 32*VEC channels).
+// smem: w[QPC][H][16] floats, sidx[QPC][H] ints, nvalid[QPC], npos[QPC]
+template <int VEC, typename IdxT>
+__global__ void __launch_bounds__(256) kpconv_gather_kernel(const float* __restrict__ feats,
+                                                            const unsigned char* __restrict__ rowpos,
+                                                            const float* __restrict__ q_pts,
+                                                            const float* __restrict__ s_pts,
+                                                            const IdxT* __restrict__ idx, const float* __restrict__ kpts,
+                                                            float sigma, int M, int N, int H, int C, int NS, int QPC,
+                                                            float* __restrict__ out) {
+  extern __shared__ __align__(16) float s_mem[];
+  __shared__ float s_kp[KP_K * 3];
+  float* s_w = s_mem;                             // QPC*H*16
+  int* s_idx = (int*)(s_mem + (size_t)QPC * H * 16);  // QPC*H
+  int* s_nvalid = s_idx + QPC * H;                // QPC
+  int* s_npos = s_nvalid + QPC;                   // QPC
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m0 = blockIdx.x * QPC;
+  if (tid < KP_K * 3) s_kp[tid] = kpts[tid];
+  if (tid < QPC) {
+    s_nvalid[tid] = 0;
+    s_npos[tid] = 0;
+  }
+  __syncthreads();
+  // phase 1: influences of every (query, neighbour) of this CTA
+  for (int e = tid; e < QPC * H; e += 256) {
+    int qi = e / H, h = e - qi * H, m = m0 + qi;
+    int j = -1;
+    if (m < M) {
+      long long jj = (long long)idx[(size_t)m * H + h];
+      if (jj < N) j = (int)jj;
+    }
+    s_idx[e] = j;
+    float4* wp = (float4*)(s_w + (size_t)e * 16);
+    if (j >= 0) {
+      float dx = s_pts[3 * (size_t)j] - q_pts[3 * m], dy = s_pts[3 * (size_t)j + 1] - q_pts[3 * m + 1],
+            dz = s_pts[3 * (size_t)j + 2] - q_pts[3 * m + 2];
+      float w[16];
+#pragma unroll
+      for (int k = 0; k < KP_K; k++) {
+        float ex = dx - s_kp[3 * k], ey = dy - s_kp[3 * k + 1], ez = dz - s_kp[3 * k + 2];
+        w[k] = fmaxf(0.f, 1.f - sqrtf(ex * ex + ey * ey + ez * ez) / sigma);  // kpconv.py:98-99
+      }
+      w[15] = 0.f;
+      wp[0] = make_float4(w[0], w[1], w[2], w[3]);
+      wp[1] = make_float4(w[4], w[5], w[6], w[7]);
+      wp[2] = make_float4(w[8], w[9], w[10], w[11]);
+      wp[3] = make_float4(w[12], w[13], w[14], w[15]);
+      atomicMax(&s_nvalid[qi], h + 1);
+      if (rowpos[j]) atomicAdd(&s_npos[qi], 1);
+    } else {
+      wp[0] = wp[1] = wp[2] = wp[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  __syncthreads();
+  // phase 2: one warp per (query, channel slice)
+  const int qi = warp / NS, sl = warp - qi * NS, m = m0 + qi;
+  if (qi >= QPC || m >= M) return;
+  const int c0 = sl * 32 * VEC + lane * VEC;
+  const bool active = c0 < C;  // only false on the ragged VEC==1 path
+  float acc[KP_K][VEC];
+#pragma unroll
+  for (int k = 0; k < KP_K; k++)
+#pragma unroll
+    for (int v = 0; v < VEC; v++) acc[k][v] = 0.f;
+  const int nv = s_nvalid[qi];
+  const float* wq = s_w + (size_t)qi * H * 16;
+  const int* iq = s_idx + qi * H;
+#pragma unroll 4
+  for (int h = 0; h < nv; h++) {
+    int j = iq[h];
+    float f[VEC];
+    if (j >= 0 && active) {
+      const float* fp = feats + (size_t)j * C + c0;
+      if constexpr (VEC == 4) {
+        float4 t = *(const float4*)fp;
+        f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
+      } else if constexpr (VEC == 2) {
+        float2 t = *(const float2*)fp;
+        f[0] = t.x; f[1] = t.y;
+      } else {
+        f[0] = *fp;
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < VEC; v++) f[v] = 0.f;
+    }
+    const float4* wp = (const float4*)(wq + (size_t)h * 16);
+    float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+    float w[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+    for (int k = 0; k < KP_K; k++)
+#pragma unroll
+      for (int v = 0; v < VEC; v++) acc[k][v] = fmaf(w[k], f[v], acc[k][v]);
+  }
+  if (!active) return;
+  const float inv = 1.f / (float)max(s_npos[qi], 1);  // kpconv.py:113-116
+  float* op = out + (size_t)m * KP_K * C + c0;
+#pragma unroll
+  for (int k = 0; k < KP_K; k++) {
+    if constexpr (VEC == 4) {
+      *(float4*)(op + (size_t)k * C) = make_float4(acc[k][0] * inv, acc[k][1] * inv, acc[k][2] * inv, acc[k][3] * inv);
+    } else if constexpr (VEC == 2) {
+      *(float2*)(op + (size_t)k * C) = make_float2(acc[k][0] * inv, acc[k][1] * inv);
+    } else {
+      op[(size_t)k * C] = acc[k][0] * inv;
+    }
+  }
+}
+
+template <typename IdxT>
+static int launch_gather(const float* feats, const unsigned char* rowpos, const float* q, const float* s,
+                         const IdxT* idx, const float* kpts, float sigma, int M, int N, int H, int C, float* out,
+                         cudaStream_t stream) {
+  if (C == 1) {
+    kpconv_gather_c1_kernel<IdxT><<<cdiv(M, 8), 256, 0, stream>>>(feats, q, s, idx, kpts, sigma, M, N, H, out);
+    RDM_LAUNCH_CHECK();
+    return RDM_OK;
+  }
+  int VEC = (C % 128 == 0) ? 4 : (C % 64 == 0 ? 2 : 1);
+  int NS = cdiv(C, 32 * VEC);
+  RDM_CHECK_ARG(NS <= 8, "rdm_kpconv_gather: C_in=%d too wide for one CTA (max 1024)", C);
+  int QPC = 8 / NS;
+  size_t smem = (size_t)QPC * H * 16 * 4 + (size_t)QPC * H * 4 + 2 * QPC * 4;
+  int grid = cdiv(M, QPC);
+#define LAUNCH(V)                                                                                                  \
+  do {                                                                                                             \
+    if (smem > 48 * 1024)                                                                                          \
+      RDM_CUDA(cudaFuncSetAttribute(kpconv_gather_kernel<V, IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                    (int)smem));                                                                   \
+    kpconv_gather_kernel<V, IdxT><<<grid, 256, smem, stream>>>(feats, rowpos, q, s, idx, kpts, sigma, M, N, H, C,  \
+                                                               NS, QPC, out);                                      \
+  } while (0)
+  RDM_CHECK_ARG(smem <= 200 * 1024, "rdm_kpconv_gather: neighbour width H=%d too large", H);
+  if (VEC == 4) LAUNCH(4);
+  else if (VEC == 2) LAUNCH(2);
+  else LAUNCH(1);
+#undef LAUNCH
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
+
+extern "C" int rdm_kpconv_gather(const float* s_feats, const float* q_points, const float* s_points,
+                                 const void* neighbor_indices, int index_bytes, const float* kernel_points, float sigma,
+                                 int M, int N, int H, int C_in, float* out_weighted, unsigned char* rowpos_scratch,
+                                 cudaStream_t stream) {
+  RDM_CHECK_ARG(M >= 0 && N >= 0 && H >= 1 && C_in >= 1 && sigma > 0.f, "rdm_kpconv_gather: bad arguments");
+  RDM_CHECK_ARG(index_bytes == 4 || index_bytes == 8, "rdm_kpconv_gather: index_bytes must be 4 or 8");
+  if (M == 0) return RDM_OK;
+  if (C_in > 1 && N > 0) {
+    row_positive_kernel<<<cdiv(N, 8), 256, 0, stream>>>(s_feats, N, C_in, rowpos_scratch);
+    RDM_LAUNCH_CHECK();
+  }
+  if (index_bytes == 8)
+    return launch_gather<int64_t>(s_feats, rowpos_scratch, q_points, s_points, (const int64_t*)neighbor_indices,
+                                  kernel_points, sigma, M, N, H, C_in, out_weighted, stream);
+  return launch_gather<int>(s_feats, rowpos_scratch, q_points, s_points, (const int*)neighbor_indices, kernel_points,
+                            sigma, M, N, H, C_in, out_weighted, stream);
+}
+
+// ---------------------------------------------------------------------------------------------- maxpool / upsample
+// out[m, c] = max_h F'[idx[m,h], c]  with F' = F plus one zero row (functional.py:64-66)
+template <typename IdxT>
+__global__ void maxpool_kernel(const float* __restrict__ f, const IdxT* __restrict__ idx, int M, int N, int H, int C,
+                               float* __restrict__ out) {
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  int cv = C >> 2;
+  if (e >= (long long)M * cv) return;
+  int m = (int)(e / cv), c4 = (int)(e - (long long)m * cv);
+  float4 best = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f);
+  const IdxT* row = idx + (size_t)m * H;
+  for (int h = 0; h < H; h++) {
+    long long j = (long long)row[h];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < N) v = *(const float4*)(f + (size_t)j * C + 4 * c4);
+    best.x = fmaxf(best.x, v.x);
+    best.y = fmaxf(best.y, v.y);
+    best.z = fmaxf(best.z, v.z);
+    best.w = fmaxf(best.w, v.w);
+  }
+  *(float4*)(out + (size_t)m * C + 4 * c4) = best;
+}
+
+extern "C" int rdm_maxpool(const float* feats, const void* neighbor_indices, int index_bytes, int M, int N, int H, int C,
+                           float* out, cudaStream_t stream) {
+  RDM_CHECK_ARG(C % 4 == 0 && H >= 1, "rdm_maxpool: C must be a multiple of 4");
+  RDM_CHECK_ARG(index_bytes == 4 || index_bytes == 8, "rdm_maxpool: index_bytes must be 4 or 8");
+  if (M == 0) return RDM_OK;
+  long long total = (long long)M * (C / 4);
+  if (index_bytes == 8)
+    maxpool_kernel<int64_t><<<cdiv(total, 256), 256, 0, stream>>>(feats, (const int64_t*)neighbor_indices, M, N, H, C, out);
+  else
+    maxpool_kernel<int><<<cdiv(total, 256), 256, 0, stream>>>(feats, (const int*)neighbor_indices, M, N, H, C, out);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
+
+// out[m, :C1] = F'[idx[m,0]] ; out[m, C1:] = skip[m]   (functional.py:6-22 + backbone.py:129-141 concat)
+template <typename IdxT>
+__global__ void upsample_concat_kernel(const float* __restrict__ f, const IdxT* __restrict__ idx, int idx_stride,
+                                       const float* __restrict__ skip, int M, int N, int C1, int C2,
+                                       float* __restrict__ out) {
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  int C = C1 + C2;
+  if (e >= (long long)M * C) return;
+  int m = (int)(e / C), c = (int)(e - (long long)m * C);
+  float v;
+  if (c < C1) {
+    long long j = (long long)idx[(size_t)m * idx_stride];
+    v = j < N ? f[(size_t)j * C1 + c] : 0.f;
+  } else {
+    v = skip[(size_t)m * C2 + (c - C1)];
+  }
+  out[e] = v;
+}
+
+extern "C" int rdm_upsample_concat(const float* feats, const void* upsample_indices, int index_bytes, int index_stride,
+                                   const float* skip, int M, int N, int C1, int C2, float* out, cudaStream_t stream) {
+  RDM_CHECK_ARG(index_bytes == 4 || index_bytes == 8, "rdm_upsample_concat: index_bytes must be 4 or 8");
+  if (M == 0) return RDM_OK;
+  long long total = (long long)M * (C1 + C2);
+  if (index_bytes == 8)
+    upsample_concat_kernel<int64_t><<<cdiv(total, 256), 256, 0, stream>>>(feats, (const int64_t*)upsample_indices,
+                                                                         index_stride, skip, M, N, C1, C2, out);
+  else
+    upsample_concat_kernel<int><<<cdiv(total, 256), 256, 0, stream>>>(feats, (const int*)upsample_indices,
+                                                                     index_stride, skip, M, N, C1, C2, out);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
