@@ -74,11 +74,12 @@ int rdm_maxpool(const float* feats, const void* neighbor_indices, int index_byte
 int rdm_upsample_concat(const float* feats, const void* upsample_indices, int index_bytes, int index_stride,
                         const float* skip, int M, int N, int C1, int C2, float* out, rdm_stream_t stream);
 
-/* ---- nn.Linear / KPConv weight contraction: C[M,N] = A[M,K] * B (+ bias). b_is_nk = 1: B is an nn.Linear weight
- * [N,K]; 0: B is [K,N]. workspace (optional) enables deterministic split-K for small M*N. */
+/* ---- nn.Linear / KPConv weight contraction: C[M,N] = act(A[M,K] * B (+ bias)). b_is_nk = 1: B is an nn.Linear
+ * weight [N,K]; 0: B is [K,N]. act: 0 none, 1 LeakyReLU(0.1), 2 ReLU (AttentionOutput, transformer/output_layer.py:16-17).
+ * workspace (optional) enables deterministic split-K for small M*N. */
 size_t rdm_linear_workspace(int M, int N, int K);
 int rdm_linear(const float* A, int lda, const float* B, int ldb, int b_is_nk, const float* bias, float* C, int ldc,
-               int M, int N, int K, void* workspace, size_t workspace_bytes, rdm_stream_t stream);
+               int M, int N, int K, int act, void* workspace, size_t workspace_bytes, rdm_stream_t stream);
 
 /* ---- GroupNorm over stacked features (geotransformer/modules/kpconv/modules.py:33-50) fused with the optional
  * residual add and LeakyReLU of UnaryBlock/ConvBlock/ResidualBlock (:78-83, :143-147, :222-224).
@@ -93,6 +94,61 @@ int rdm_layernorm(const float* x, const float* residual, const float* gamma, con
 
 /* ---- elementwise: act 1 LeakyReLU(slope), 2 ReLU, 3 clamp(sigmoid(x), 0, 1) (experiments/model.py:162-174) */
 int rdm_activation(const float* x, float* y, int64_t n, int act, float slope, rdm_stream_t stream);
+
+/* ---- RotaryPositionalEmbedding.forward (rdmnet/thdroformer/thdroformer.py:56-85): y = x*cos(t) + rot(x)*sin(t),
+ * t = 2*pi*sigmoid(repeat_interleave(emb, 2)); x,y [N, C] (heads contiguous), emb [N, C/2]; ld* = row strides. */
+int rdm_rope(const float* x, int ldx, const float* emb, int lde, float* y, int ldy, int N, int C, rdm_stream_t stream);
+
+/* ---- dynamic_attention (k=None) / MultiHeadAttention core (thdroformer.py:20-40, vanilla_transformer.py:54-66):
+ * O[n, h*D:(h+1)*D] = softmax_j(Q_n.K_j / sqrt(D)) V, heads laid out along the channel axis, D <= 64. */
+int rdm_attention(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, float* O, int ldo, int Nq,
+                  int Nk, int heads, int head_dim, rdm_stream_t stream);
+
+/* ---- NMS.forward greedy loop (rdmnet/vote/vote.py:33-40) over a radius-search table [N,H] (H <= 128). */
+int rdm_nms(const void* neighbor_indices, int index_bytes, int N, int H, unsigned char* out_mask, rdm_stream_t stream);
+
+/* ---- point_to_node_partition (geotransformer/modules/ops/pointcloud_partition.py:60-107). */
+size_t rdm_point_to_node_workspace(int num_points, int num_nodes);
+int rdm_point_to_node(const float* points, int num_points, const float* nodes, int num_nodes, int point_limit,
+                      int* out_point_to_node, unsigned char* out_node_masks, int64_t* out_knn_indices,
+                      unsigned char* out_knn_masks, void* workspace, size_t workspace_bytes, rdm_stream_t stream);
+
+/* ---- SuperPointMatching.forward (geotransformer/modules/geotransformer/superpoint_matching.py:14-83).
+ * xy_scores [M,N] holds ref_feats @ src_feats^T on entry (rdm_linear) and is overwritten. sums_scratch: M+N floats.
+ * Results sorted by descending score; out_count = min(num_correspondences, #valid pairs). */
+int rdm_coarse_matching(float* xy_scores, int M, int N, const unsigned char* ref_masks, const unsigned char* src_masks,
+                        int num_correspondences, int dual_normalization, int64_t* out_ref_indices,
+                        int64_t* out_src_indices, float* out_scores, int* out_count, float* sums_scratch,
+                        rdm_stream_t stream);
+
+/* ---- patch gather + einsum('bnd,bmd->bnm') * scale (experiments/model.py:323-343); point_limit must be 128. */
+int rdm_patch_scores(const float* ref_feats, int Nr, const float* src_feats, int Ns, int C,
+                     const int64_t* ref_knn_indices, const int64_t* src_knn_indices, const int64_t* ref_corr_indices,
+                     const int64_t* src_corr_indices, int num_patches, int point_limit, float scale, float* out_scores,
+                     rdm_stream_t stream);
+
+/* ---- LearnableLogOptimalTransport.forward (geotransformer/modules/sinkhorn/learnable_sinkhorn.py:13-66).
+ * scores [P,R,C]; row_masks/col_masks are [P,R]/[P,C] or, when *_gather != NULL, node-level tables indexed through
+ * the gather arrays (= knn_masks[corr_indices]); out [P,R+1,C+1]. */
+int rdm_sinkhorn(const float* scores, int num_patches, int R, int C, const unsigned char* row_masks,
+                 const unsigned char* col_masks, const int64_t* row_mask_gather, const int64_t* col_mask_gather,
+                 const float* alpha, int num_iterations, float inf, float* out, rdm_stream_t stream);
+
+/* ---- weighted_procrustes (geotransformer/modules/registration/procrustes.py:6-73): [B,n,3] x2 + [B,n] -> [B,4,4];
+ * the SVD runs in-kernel (one warp per problem) instead of the reference's CPU round trip (:53). */
+int rdm_weighted_procrustes(const float* src_points, const float* ref_points, const float* weights, int batch, int n,
+                            float eps, float* out_transforms, rdm_stream_t stream);
+
+/* ---- LocalGlobalRegistration.forward (geotransformer/modules/geotransformer/local_global_registration.py:204-243)
+ * for k=1, mutual=False, use_dustbin=True, correspondence_limit=None. matching_scores [P,K+1,K+1] (log domain).
+ * Outputs have capacity P*2*K rows; out_meta[0] = #correspondences, [1] = #local hypotheses, [2] = max chunk. */
+size_t rdm_lgr_workspace(int num_patches, int K);
+int rdm_lgr(const float* matching_scores, int num_patches, int K, const float* ref_points_f, const float* src_points_f,
+            const int64_t* ref_knn_indices, const int64_t* src_knn_indices, const unsigned char* ref_knn_masks,
+            const unsigned char* src_knn_masks, const int64_t* ref_corr_indices, const int64_t* src_corr_indices,
+            float acceptance_radius, int correspondence_threshold, int num_refinement_steps, float* out_ref_corr_points,
+            float* out_src_corr_points, float* out_corr_scores, int* out_corr_bij, float* out_transform, int* out_meta,
+            void* workspace, size_t workspace_bytes, rdm_stream_t stream);
 
 #ifdef __cplusplus
 }

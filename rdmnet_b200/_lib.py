@@ -25,12 +25,30 @@ SIGNATURES = {
     "rdm_maxpool": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "rdm_upsample_concat": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "rdm_linear_workspace": (c_size_t, [c_int, c_int, c_int]),
-    "rdm_linear": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+    "rdm_linear": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                            c_void_p, c_size_t, c_void_p]),
     "rdm_groupnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int,
                               c_float, c_void_p, c_void_p]),
     "rdm_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p]),
     "rdm_activation": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_float, c_void_p]),
+    "rdm_rope": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "rdm_attention": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                              c_void_p]),
+    "rdm_nms": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "rdm_point_to_node_workspace": (c_size_t, [c_int, c_int]),
+    "rdm_point_to_node": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_size_t, c_void_p]),
+    "rdm_coarse_matching": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p]),
+    "rdm_patch_scores": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                 c_int, c_float, c_void_p, c_void_p]),
+    "rdm_sinkhorn": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                             c_float, c_void_p, c_void_p]),
+    "rdm_weighted_procrustes": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "rdm_lgr_workspace": (c_size_t, [c_int, c_int]),
+    "rdm_lgr": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                        c_void_p, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                        c_void_p, c_size_t, c_void_p]),
 }
 
 

@@ -15,7 +15,7 @@ template <int BM, int BN, bool B_NK>
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B,
                                                     int ldb, const float* __restrict__ bias, float* __restrict__ C,
                                                     int ldc, int M, int N, int K, int k_per_split, int vecA, int vecB,
-                                                    int vecC) {
+                                                    int vecC, int act) {
   constexpr int TM = BM / 16, TN = BN / 16;  // 8x8 (128 tile) or 4x4 (64 tile)
   constexpr int PAD = 4;
   __shared__ __align__(16) float As[2][GEMM_BK][BM + PAD];
@@ -162,6 +162,10 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
       for (int j = 0; j < 4; j++) {
         v[j] = acc[i][jh * 4 + j];
         if (add_bias && col + j < N) v[j] += bias[col + j];
+        if (gridDim.z == 1) {
+          if (act == 1) v[j] = v[j] > 0.f ? v[j] : 0.1f * v[j];
+          else if (act == 2) v[j] = fmaxf(v[j], 0.f);
+        }
       }
       float* cp = C + (size_t)row * ldc + col;
       if (vecC && col + 3 < N) {
@@ -176,13 +180,15 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
 }
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, const float* __restrict__ bias,
-                                     float* __restrict__ C, int ldc, int M, int N) {
+                                     float* __restrict__ C, int ldc, int M, int N, int act) {
   long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (e >= (long long)M * N) return;
   int m = (int)(e / N), n = (int)(e - (long long)m * N);
   float s = 0.f;
   for (int z = 0; z < splits; z++) s += part[(size_t)z * M * N + e];
   if (bias) s += bias[n];
+  if (act == 1) s = s > 0.f ? s : 0.1f * s;
+  else if (act == 2) s = fmaxf(s, 0.f);
   C[(size_t)m * ldc + n] = s;
 }
 
@@ -194,7 +200,7 @@ extern "C" size_t rdm_linear_workspace(int M, int N, int K) {
 }
 
 extern "C" int rdm_linear(const float* A, int lda, const float* B, int ldb, int b_is_nk, const float* bias, float* C,
-                          int ldc, int M, int N, int K, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                          int ldc, int M, int N, int K, int act, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   RDM_CHECK_ARG(M >= 0 && N >= 1 && K >= 1, "rdm_linear: bad shape M=%d N=%d K=%d", M, N, K);
   if (M == 0) return RDM_OK;
   int vecA = (lda % 4 == 0) && aligned16(A), vecB = (ldb % 4 == 0) && aligned16(B), vecC = (ldc % 4 == 0) && aligned16(C);
@@ -214,19 +220,19 @@ extern "C" int rdm_linear(const float* A, int lda, const float* B, int ldb, int 
   if (big) {
     dim3 grid(cdiv(N, 128), cdiv(M, 128), 1);
     if (b_is_nk)
-      sgemm_kernel<128, 128, true><<<grid, 256, 0, stream>>>(A, lda, B, ldb, bias, out, ldo, M, N, K, kps, vecA, vecB, vecO);
+      sgemm_kernel<128, 128, true><<<grid, 256, 0, stream>>>(A, lda, B, ldb, bias, out, ldo, M, N, K, kps, vecA, vecB, vecO, act);
     else
-      sgemm_kernel<128, 128, false><<<grid, 256, 0, stream>>>(A, lda, B, ldb, bias, out, ldo, M, N, K, kps, vecA, vecB, vecO);
+      sgemm_kernel<128, 128, false><<<grid, 256, 0, stream>>>(A, lda, B, ldb, bias, out, ldo, M, N, K, kps, vecA, vecB, vecO, act);
   } else {
     dim3 grid(cdiv(N, 64), cdiv(M, 64), splits);
     if (b_is_nk)
-      sgemm_kernel<64, 64, true><<<grid, 256, 0, stream>>>(A, lda, B, ldb, bias, out, ldo, M, N, K, kps, vecA, vecB, vecO);
+      sgemm_kernel<64, 64, true><<<grid, 256, 0, stream>>>(A, lda, B, ldb, bias, out, ldo, M, N, K, kps, vecA, vecB, vecO, act);
     else
-      sgemm_kernel<64, 64, false><<<grid, 256, 0, stream>>>(A, lda, B, ldb, bias, out, ldo, M, N, K, kps, vecA, vecB, vecO);
+      sgemm_kernel<64, 64, false><<<grid, 256, 0, stream>>>(A, lda, B, ldb, bias, out, ldo, M, N, K, kps, vecA, vecB, vecO, act);
   }
   RDM_LAUNCH_CHECK();
   if (splits > 1) {
-    splitk_reduce_kernel<<<cdiv((long long)M * N, 256), 256, 0, stream>>>((const float*)workspace, splits, bias, C, ldc, M, N);
+    splitk_reduce_kernel<<<cdiv((long long)M * N, 256), 256, 0, stream>>>((const float*)workspace, splits, bias, C, ldc, M, N, act);
     RDM_LAUNCH_CHECK();
   }
   return RDM_OK;

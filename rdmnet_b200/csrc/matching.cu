@@ -1,0 +1,605 @@
+// Superpoint detection / matching kernels: greedy NMS, point-to-node partition, coarse (superpoint) matching,
+// patch score GEMM with row gather, and the log-domain Sinkhorn solver.
+//
+// Reference semantics:
+//   NMS greedy loop             rdmnet/vote/vote.py:33-40
+//   point_to_node_partition     geotransformer/modules/ops/pointcloud_partition.py:60-107 (+ pairwise_distance.py:4-31)
+//   SuperPointMatching.forward  geotransformer/modules/geotransformer/superpoint_matching.py:14-83
+//   patch gather + einsum       experiments/model.py:323-343
+//   LearnableLogOptimalTransport geotransformer/modules/sinkhorn/learnable_sinkhorn.py:13-66
+#include "common.cuh"
+#include "../../include/rdm_sm100.h"
+
+// ------------------------------------------------------------------------------------------------------ NMS
+// sel[i] = !any(sel[j] for j in nbrs(i)), i = 0..N-1 in order (sel starts all-false; entries >= N are the sentinel).
+// One warp walks the nodes sequentially; neighbour rows are prefetched PF rows at a time (they do not depend on sel).
+#define NMS_PF 8
+#define NMS_R 4  // ceil(H/32) <= 4  ->  H <= 128
+template <typename IdxT>
+__global__ void __launch_bounds__(32) nms_kernel(const IdxT* __restrict__ nbr, int N, int H,
+                                                 unsigned char* __restrict__ mask) {
+  extern __shared__ unsigned char s_sel[];  // N bytes
+  const int lane = threadIdx.x;
+  for (int i = lane; i < N; i += 32) s_sel[i] = 0;
+  __syncwarp();
+  for (int base = 0; base < N; base += NMS_PF) {
+    int rows[NMS_PF][NMS_R];
+#pragma unroll
+    for (int p = 0; p < NMS_PF; p++)
+#pragma unroll
+      for (int r = 0; r < NMS_R; r++) {
+        int i = base + p, h = lane + 32 * r;
+        rows[p][r] = (i < N && h < H) ? (int)min((long long)nbr[(size_t)i * H + h], (long long)N) : N;
+      }
+#pragma unroll
+    for (int p = 0; p < NMS_PF; p++) {
+      int i = base + p;
+      if (i >= N) break;
+      bool hit = false;
+#pragma unroll
+      for (int r = 0; r < NMS_R; r++) {
+        int j = rows[p][r];
+        if (j < N) hit |= (s_sel[j] != 0);
+      }
+      bool any = __any_sync(FULL_MASK, hit);
+      if (lane == 0 && !any) s_sel[i] = 1;
+      __syncwarp();
+    }
+  }
+  for (int i = lane; i < N; i += 32) mask[i] = s_sel[i];
+}
+
+extern "C" int rdm_nms(const void* neighbor_indices, int index_bytes, int N, int H, unsigned char* out_mask,
+                       cudaStream_t stream) {
+  RDM_CHECK_ARG(index_bytes == 4 || index_bytes == 8, "rdm_nms: index_bytes must be 4 or 8");
+  RDM_CHECK_ARG(H >= 1 && H <= 32 * NMS_R, "rdm_nms: neighbour width must be <= 128");
+  RDM_CHECK_ARG(N >= 0 && N <= 200000, "rdm_nms: too many nodes");
+  if (N == 0) return RDM_OK;
+  size_t smem = (size_t)N;
+  if (index_bytes == 8) {
+    if (smem > 48 * 1024)
+      RDM_CUDA(cudaFuncSetAttribute(nms_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_kernel<int64_t><<<1, 32, smem, stream>>>((const int64_t*)neighbor_indices, N, H, out_mask);
+  } else {
+    if (smem > 48 * 1024)
+      RDM_CUDA(cudaFuncSetAttribute(nms_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_kernel<int><<<1, 32, smem, stream>>>((const int*)neighbor_indices, N, H, out_mask);
+  }
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
+
+// ---------------------------------------------------------------------------------------- point_to_node_partition
+// d(node, point) = max(1e-12, (|n|^2 - 2 n.p) + |p|^2)   (pairwise_distance.py:24-30)
+__device__ __forceinline__ float p2n_dist(float nx, float ny, float nz, float n2, float px, float py, float pz,
+                                          float p2) {
+  float xy = fmaf(nz, pz, fmaf(ny, py, __fmul_rn(nx, px)));
+  float d = __fadd_rn(__fsub_rn(n2, __fmul_rn(2.0f, xy)), p2);
+  return fmaxf(d, 1e-12f);
+}
+__device__ __forceinline__ float sq3(float x, float y, float z) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+
+__global__ void __launch_bounds__(256) p2n_assign_kernel(const float* __restrict__ pts, int NP,
+                                                         const float* __restrict__ nodes, int NN,
+                                                         int* __restrict__ p2n, float* __restrict__ pdist,
+                                                         int* __restrict__ node_cnt) {
+  __shared__ float4 s_nodes[256];
+  int i = blockIdx.x * 256 + threadIdx.x;
+  float px = 0, py = 0, pz = 0, p2 = 0;
+  if (i < NP) {
+    px = pts[3 * i];
+    py = pts[3 * i + 1];
+    pz = pts[3 * i + 2];
+    p2 = sq3(px, py, pz);
+  }
+  float best = 3.4e38f;
+  int bi = 0;
+  for (int n0 = 0; n0 < NN; n0 += 256) {
+    __syncthreads();
+    int n = n0 + threadIdx.x;
+    if (n < NN) {
+      float x = nodes[3 * n], y = nodes[3 * n + 1], z = nodes[3 * n + 2];
+      s_nodes[threadIdx.x] = make_float4(x, y, z, sq3(x, y, z));
+    }
+    __syncthreads();
+    int lim = min(256, NN - n0);
+    for (int k = 0; k < lim; k++) {
+      float4 nd = s_nodes[k];
+      float d = p2n_dist(nd.x, nd.y, nd.z, nd.w, px, py, pz, p2);
+      if (d < best) {  // strict: the lowest node index wins ties (torch.min on CPU)
+        best = d;
+        bi = n0 + k;
+      }
+    }
+  }
+  if (i < NP) {
+    p2n[i] = bi;
+    pdist[i] = best;
+    atomicAdd(&node_cnt[bi], 1);
+  }
+}
+
+__global__ void __launch_bounds__(1024) p2n_scan_kernel(int* __restrict__ node_cnt, int* __restrict__ node_off, int NN) {
+  __shared__ int s_scan[33];
+  int nt = blockDim.x, tid = threadIdx.x;
+  int chunk = (NN + nt - 1) / nt;
+  int beg = min(NN, tid * chunk), end = min(NN, beg + chunk);
+  int s = 0;
+  for (int i = beg; i < end; i++) s += node_cnt[i];
+  int total;
+  int pre = block_exclusive_scan(s, s_scan, &total);
+  for (int i = beg; i < end; i++) {
+    int v = node_cnt[i];
+    node_off[i] = pre;
+    pre += v;
+    node_cnt[i] = 0;  // becomes the fill cursor
+  }
+  if (tid == 0) node_off[NN] = total;
+}
+
+__global__ void p2n_scatter_kernel(const int* __restrict__ p2n, const float* __restrict__ pdist, int NP,
+                                   const int* __restrict__ node_off, int* __restrict__ node_cur,
+                                   unsigned long long* __restrict__ keys) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NP) return;
+  int n = p2n[i];
+  int pos = node_off[n] + atomicAdd(&node_cur[n], 1);
+  keys[pos] = ((unsigned long long)__float_as_uint(pdist[i]) << 32) | (unsigned int)i;
+}
+
+// one warp per node: the K owned points with the smallest (distance, index)
+__global__ void __launch_bounds__(128) p2n_select_kernel(const unsigned long long* __restrict__ keys,
+                                                         const int* __restrict__ node_off, int NN, int NP, int K, int KP,
+                                                         int64_t* __restrict__ knn_idx, unsigned char* __restrict__ knn_mask,
+                                                         unsigned char* __restrict__ node_mask) {
+  extern __shared__ unsigned long long s_buf[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 4 + warp;
+  if (n >= NN) return;
+  unsigned long long* buf = s_buf + (size_t)warp * 2 * KP;
+  const int beg = node_off[n], end = node_off[n + 1];
+  int cnt = 0;
+  for (int p0 = beg; p0 < end; p0 += 32) {
+    int p = p0 + lane;
+    if (cnt + 32 > 2 * KP) {
+      for (int i = cnt + lane; i < 2 * KP; i += 32) buf[i] = ~0ULL;
+      __syncwarp();
+      warp_bitonic_sort_u64(buf, 2 * KP, lane);
+      cnt = min(cnt, KP);
+    }
+    if (p < end) buf[cnt + lane] = keys[p];
+    cnt += min(32, end - p0);
+    __syncwarp();
+  }
+  int P = 32;
+  while (P < cnt) P <<= 1;
+  for (int i = cnt + lane; i < P; i += 32) buf[i] = ~0ULL;
+  __syncwarp();
+  warp_bitonic_sort_u64(buf, P, lane);
+  for (int i = lane; i < K; i += 32) {
+    bool ok = i < cnt;
+    knn_idx[(size_t)n * K + i] = ok ? (int64_t)(unsigned int)(buf[i] & 0xffffffffULL) : (int64_t)NP;
+    knn_mask[(size_t)n * K + i] = ok ? 1 : 0;
+  }
+  if (lane == 0) node_mask[n] = end > beg ? 1 : 0;
+}
+
+extern "C" size_t rdm_point_to_node_workspace(int num_points, int num_nodes) {
+  return align_up((size_t)num_points * 4, 256) * 2 + align_up((size_t)(num_nodes + 1) * 4, 256) * 2 +
+         align_up((size_t)num_points * 8, 256) + 1024;
+}
+
+extern "C" int rdm_point_to_node(const float* points, int num_points, const float* nodes, int num_nodes, int point_limit,
+                                 int* out_point_to_node, unsigned char* out_node_masks, int64_t* out_knn_indices,
+                                 unsigned char* out_knn_masks, void* workspace, size_t workspace_bytes,
+                                 cudaStream_t stream) {
+  RDM_CHECK_ARG(num_points >= 0 && num_nodes >= 1 && point_limit >= 1 && point_limit <= 2048,
+                "rdm_point_to_node: bad arguments");
+  Workspace ws(workspace, workspace_bytes);
+  float* pdist = ws.get<float>(num_points);
+  int* cnt = ws.get<int>(num_nodes + 1);
+  int* off = ws.get<int>(num_nodes + 1);
+  unsigned long long* keys = ws.get<unsigned long long>(num_points);
+  if (!ws.ok) {
+    rdm_set_error("rdm_point_to_node: workspace too small");
+    return RDM_ERR_WORKSPACE;
+  }
+  RDM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (num_nodes + 1), stream));
+  if (num_points > 0) {
+    p2n_assign_kernel<<<cdiv(num_points, 256), 256, 0, stream>>>(points, num_points, nodes, num_nodes, out_point_to_node,
+                                                                pdist, cnt);
+    RDM_LAUNCH_CHECK();
+  }
+  p2n_scan_kernel<<<1, 1024, 0, stream>>>(cnt, off, num_nodes);
+  RDM_LAUNCH_CHECK();
+  if (num_points > 0) {
+    p2n_scatter_kernel<<<cdiv(num_points, 256), 256, 0, stream>>>(out_point_to_node, pdist, num_points, off, cnt, keys);
+    RDM_LAUNCH_CHECK();
+  }
+  int KP = 32;
+  while (KP < point_limit) KP <<= 1;
+  size_t smem = (size_t)4 * 2 * KP * 8;
+  if (smem > 48 * 1024)
+    RDM_CUDA(cudaFuncSetAttribute(p2n_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  p2n_select_kernel<<<cdiv(num_nodes, 4), 128, smem, stream>>>(keys, off, num_nodes, num_points, point_limit, KP,
+                                                              out_knn_indices, out_knn_masks, out_node_masks);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------- coarse matching
+// xy[M,N] (= ref_feats @ src_feats^T, computed by rdm_linear) -> S = exp(-max(1e-12, 2 - 2 xy)) on valid (i,j), else 0;
+// row sums (one warp per row).
+__global__ void __launch_bounds__(256) cm_exp_rowsum_kernel(float* __restrict__ S, int M, int N,
+                                                            const unsigned char* __restrict__ rmask,
+                                                            const unsigned char* __restrict__ cmask,
+                                                            float* __restrict__ rowsum) {
+  int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= M) return;
+  bool rv = rmask[i] != 0;
+  float s = 0.f;
+  for (int j = lane; j < N; j += 32) {
+    float v = 0.f;
+    if (rv && cmask[j]) {
+      float d = fmaxf(2.0f - 2.0f * S[(size_t)i * N + j], 1e-12f);
+      v = expf(-d);
+    }
+    S[(size_t)i * N + j] = v;
+    s += v;
+  }
+  s = warp_sum(s);
+  if (lane == 0) rowsum[i] = s;
+}
+__global__ void cm_colsum_kernel(const float* __restrict__ S, int M, int N, float* __restrict__ colsum) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  float s = 0.f;
+  for (int i = 0; i < M; i++) s += S[(size_t)i * N + j];
+  colsum[j] = s;
+}
+// score = (S/rowsum) * (S/colsum); invalid entries get -1 so that they never enter the top-k
+__global__ void cm_normalise_kernel(float* __restrict__ S, int M, int N, const unsigned char* __restrict__ rmask,
+                                    const unsigned char* __restrict__ cmask, const float* __restrict__ rowsum,
+                                    const float* __restrict__ colsum, int dual) {
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= (long long)M * N) return;
+  int i = (int)(e / N), j = (int)(e - (long long)i * N);
+  float v = -1.f;
+  if (rmask[i] && cmask[j]) {
+    float s = S[e];
+    v = dual ? (s / rowsum[i]) * (s / colsum[j]) : s;
+  }
+  S[e] = v;
+}
+
+// Single-CTA exact top-k (largest) over n floats >= 0 (negatives = excluded): 4-pass radix select on the float
+// bits, then the selected (value desc, index asc) are sorted with a block bitonic sort. k <= 1024.
+__global__ void __launch_bounds__(1024) topk_flat_kernel(const float* __restrict__ v, long long n, int k, int N,
+                                                         const int* __restrict__ unused, int64_t* __restrict__ out_i,
+                                                         int64_t* __restrict__ out_j, float* __restrict__ out_score,
+                                                         int* __restrict__ out_count) {
+  __shared__ unsigned int s_hist[256];
+  __shared__ unsigned int s_prefix, s_want;
+  __shared__ int s_nsel, s_neq;
+  __shared__ unsigned long long s_keys[1024];
+  const int tid = threadIdx.x;
+  // number of candidates (>= 0)
+  if (tid == 0) s_nsel = 0;
+  __syncthreads();
+  int local = 0;
+  for (long long e = tid; e < n; e += 1024) local += v[e] >= 0.f;
+  local = warp_sum_i(local);
+  if ((tid & 31) == 0) atomicAdd(&s_nsel, local);
+  __syncthreads();
+  const int nvalid = s_nsel;
+  const int kk = min(k, nvalid);
+  if (tid == 0) *out_count = kk;
+  if (kk == 0) return;
+  // radix select: find the bit pattern T of the kk-th largest value
+  unsigned int prefix = 0, want = kk;  // want = rank (1-based) among values matching the prefix so far
+  for (int pass = 0; pass < 4; pass++) {
+    int shift = 24 - 8 * pass;
+    if (tid < 256) s_hist[tid] = 0;
+    __syncthreads();
+    unsigned int pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (long long e = tid; e < n; e += 1024) {
+      float f = v[e];
+      if (f >= 0.f) {
+        unsigned int b = __float_as_uint(f);
+        if ((b & pmask) == prefix) atomicAdd(&s_hist[(b >> shift) & 255], 1u);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int acc = 0;
+      int d = 255;
+      for (; d >= 0; d--) {
+        if (acc + s_hist[d] >= want) break;
+        acc += s_hist[d];
+      }
+      s_prefix = prefix | ((unsigned int)d << shift);
+      s_want = want - acc;
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    want = s_want;
+    __syncthreads();
+  }
+  // prefix = bits of the kk-th largest value; take all strictly greater, and the `want` lowest-index equal ones
+  if (tid == 0) {
+    s_nsel = 0;
+    s_neq = 0;
+  }
+  for (int i = tid; i < 1024; i += 1024) s_keys[i] = ~0ULL;
+  __syncthreads();
+  for (long long e0 = 0; e0 < n; e0 += 1024) {
+    long long e = e0 + tid;
+    bool gt = false;
+    if (e < n) {
+      float f = v[e];
+      gt = f >= 0.f && __float_as_uint(f) > prefix;
+    }
+    if (gt) {
+      int pos = atomicAdd(&s_nsel, 1);
+      // sort key: descending value (invert bits), ascending flat index
+      s_keys[pos] = ((unsigned long long)(~__float_as_uint(v[e])) << 32) | (unsigned int)e;
+    }
+  }
+  __syncthreads();
+  // equal ones in ascending index order: sequential chunks keep the order deterministic
+  for (long long e0 = 0; e0 < n; e0 += 1024) {
+    long long e = e0 + tid;
+    bool eq = false;
+    if (e < n) {
+      float f = v[e];
+      eq = f >= 0.f && __float_as_uint(f) == prefix;
+    }
+    int total;
+    int pre = block_exclusive_scan(eq ? 1 : 0, (int*)s_hist, &total);
+    int base = s_neq;
+    if (eq && base + pre < (int)want) {
+      int pos = atomicAdd(&s_nsel, 1);
+      s_keys[pos] = ((unsigned long long)(~prefix) << 32) | (unsigned int)e;
+    }
+    __syncthreads();
+    if (tid == 0) s_neq = base + total;
+    __syncthreads();
+    if (s_neq >= (int)want) break;
+  }
+  __syncthreads();
+  // block bitonic sort of 1024 keys
+  for (int kk2 = 2; kk2 <= 1024; kk2 <<= 1) {
+    for (int j = kk2 >> 1; j > 0; j >>= 1) {
+      int t = tid;
+      if (t < 512) {
+        int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        int p = i | j;
+        unsigned long long x = s_keys[i], y = s_keys[p];
+        bool up = ((i & kk2) == 0);
+        if ((x > y) == up) {
+          s_keys[i] = y;
+          s_keys[p] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (tid < kk) {
+    unsigned long long key = s_keys[tid];
+    unsigned int e = (unsigned int)(key & 0xffffffffULL);
+    out_i[tid] = e / N;
+    out_j[tid] = e % N;
+    out_score[tid] = __uint_as_float(~(unsigned int)(key >> 32));
+  }
+}
+
+extern "C" int rdm_coarse_matching(float* xy_scores, int M, int N, const unsigned char* ref_masks,
+                                   const unsigned char* src_masks, int num_correspondences, int dual_normalization,
+                                   int64_t* out_ref_indices, int64_t* out_src_indices, float* out_scores, int* out_count,
+                                   float* sums_scratch, cudaStream_t stream) {
+  RDM_CHECK_ARG(M >= 1 && N >= 1 && num_correspondences >= 1 && num_correspondences <= 1024,
+                "rdm_coarse_matching: num_correspondences must be in [1,1024]");
+  RDM_CHECK_ARG((long long)M * N < (1LL << 31), "rdm_coarse_matching: score matrix too large");
+  float* rowsum = sums_scratch;
+  float* colsum = sums_scratch + M;
+  cm_exp_rowsum_kernel<<<cdiv(M, 8), 256, 0, stream>>>(xy_scores, M, N, ref_masks, src_masks, rowsum);
+  RDM_LAUNCH_CHECK();
+  cm_colsum_kernel<<<cdiv(N, 128), 128, 0, stream>>>(xy_scores, M, N, colsum);
+  RDM_LAUNCH_CHECK();
+  cm_normalise_kernel<<<cdiv((long long)M * N, 256), 256, 0, stream>>>(xy_scores, M, N, ref_masks, src_masks, rowsum,
+                                                                      colsum, dual_normalization);
+  RDM_LAUNCH_CHECK();
+  topk_flat_kernel<<<1, 1024, 0, stream>>>(xy_scores, (long long)M * N, num_correspondences, N, nullptr,
+                                          out_ref_indices, out_src_indices, out_scores, out_count);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------- patch scores
+// out[p, i, j] = scale * < F_ref[rknn[ridx[p], i]], F_src[sknn[sidx[p], j]] >  ; rows with index >= N are the zero row.
+// One CTA per patch; K x K tile with K = 128 (point limit), 256 threads x (8x8), BK = 16.
+#define PS_K 128
+__global__ void __launch_bounds__(256) patch_scores_kernel(const float* __restrict__ Fr, int Nr,
+                                                           const float* __restrict__ Fs, int Ns, int C,
+                                                           const int64_t* __restrict__ rknn,
+                                                           const int64_t* __restrict__ sknn,
+                                                           const int64_t* __restrict__ ridx,
+                                                           const int64_t* __restrict__ sidx, float scale,
+                                                           float* __restrict__ out) {
+  __shared__ __align__(16) float As[2][16][PS_K + 4];
+  __shared__ __align__(16) float Bs[2][16][PS_K + 4];
+  __shared__ int s_ra[PS_K], s_rb[PS_K];
+  const int p = blockIdx.x, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  if (tid < PS_K) {
+    long long a = rknn[(size_t)ridx[p] * PS_K + tid], b = sknn[(size_t)sidx[p] * PS_K + tid];
+    s_ra[tid] = a < Nr ? (int)a : -1;
+    s_rb[tid] = b < Ns ? (int)b : -1;
+  }
+  __syncthreads();
+  float4 ra[2], rb[2];
+  auto load = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      int row = (tid >> 2) + q * 64, kq = (tid & 3) * 4;
+      int ia = s_ra[row], ib = s_rb[row];
+      ra[q] = ia >= 0 ? *(const float4*)(Fr + (size_t)ia * C + k0 + kq) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rb[q] = ib >= 0 ? *(const float4*)(Fs + (size_t)ib * C + k0 + kq) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto store = [&](int buf) {
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      int row = (tid >> 2) + q * 64, kq = (tid & 3) * 4;
+      As[buf][kq + 0][row] = ra[q].x; As[buf][kq + 1][row] = ra[q].y; As[buf][kq + 2][row] = ra[q].z; As[buf][kq + 3][row] = ra[q].w;
+      Bs[buf][kq + 0][row] = rb[q].x; Bs[buf][kq + 1][row] = rb[q].y; Bs[buf][kq + 2][row] = rb[q].z; Bs[buf][kq + 3][row] = rb[q].w;
+    }
+  };
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+  const int nk = C / 16;
+  load(0);
+  store(0);
+  __syncthreads();
+  for (int t = 0; t < nk; t++) {
+    int buf = t & 1;
+    if (t + 1 < nk) load((t + 1) * 16);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      float4 a0 = *(const float4*)&As[buf][k][ty * 4], a1 = *(const float4*)&As[buf][k][64 + ty * 4];
+      float4 b0 = *(const float4*)&Bs[buf][k][tx * 4], b1 = *(const float4*)&Bs[buf][k][64 + tx * 4];
+      float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (t + 1 < nk) store(buf ^ 1);
+    __syncthreads();
+  }
+  float* op = out + (size_t)p * PS_K * PS_K;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    int row = i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4);
+#pragma unroll
+    for (int jh = 0; jh < 2; jh++) {
+      int col = jh == 0 ? tx * 4 : 64 + tx * 4;
+      *(float4*)(op + (size_t)row * PS_K + col) = make_float4(acc[i][jh * 4] * scale, acc[i][jh * 4 + 1] * scale,
+                                                              acc[i][jh * 4 + 2] * scale, acc[i][jh * 4 + 3] * scale);
+    }
+  }
+}
+
+extern "C" int rdm_patch_scores(const float* ref_feats, int Nr, const float* src_feats, int Ns, int C,
+                                const int64_t* ref_knn_indices, const int64_t* src_knn_indices,
+                                const int64_t* ref_corr_indices, const int64_t* src_corr_indices, int num_patches,
+                                int point_limit, float scale, float* out_scores, cudaStream_t stream) {
+  RDM_CHECK_ARG(point_limit == PS_K, "rdm_patch_scores: num_points_in_patch must be 128");
+  RDM_CHECK_ARG(C % 16 == 0 && C >= 16, "rdm_patch_scores: C must be a multiple of 16");
+  RDM_CHECK_ARG(((uintptr_t)ref_feats & 15) == 0 && ((uintptr_t)src_feats & 15) == 0, "rdm_patch_scores: unaligned features");
+  if (num_patches == 0) return RDM_OK;
+  patch_scores_kernel<<<num_patches, 256, 0, stream>>>(ref_feats, Nr, src_feats, Ns, C, ref_knn_indices, src_knn_indices,
+                                                      ref_corr_indices, src_corr_indices, scale, out_scores);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- Sinkhorn
+// One CTA per patch pair; the padded (R+1)x(Cc+1) score matrix stays in shared memory for all iterations.
+// Row phase: thread r owns row r; column phase: thread c owns column c (row stride odd -> conflict-free both ways).
+__global__ void __launch_bounds__(160) sinkhorn_kernel(const float* __restrict__ scores, int R, int Cc,
+                                                       const unsigned char* __restrict__ row_masks_nodes,
+                                                       const unsigned char* __restrict__ col_masks_nodes,
+                                                       const int64_t* __restrict__ ridx, const int64_t* __restrict__ sidx,
+                                                       const float* __restrict__ alpha_ptr, int iters, float inf,
+                                                       float* __restrict__ out) {
+  extern __shared__ float s_f[];
+  const int R1 = R + 1, C1 = Cc + 1;
+  const int ld = (C1 % 2 == 0) ? C1 + 1 : C1;  // odd stride
+  float* Z = s_f;                               // R1 * ld
+  float* u = Z + (size_t)R1 * ld;               // R1
+  float* v = u + R1;                            // C1
+  float* lmu = v + C1;                          // R1
+  float* lnu = lmu + R1;                        // C1
+  __shared__ int s_nr, s_nc;
+  const int p = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const unsigned char* rm = ridx ? row_masks_nodes + (size_t)ridx[p] * R : row_masks_nodes + (size_t)p * R;
+  const unsigned char* cm = sidx ? col_masks_nodes + (size_t)sidx[p] * Cc : col_masks_nodes + (size_t)p * Cc;
+  const float alpha = *alpha_ptr;
+  if (tid == 0) {
+    s_nr = 0;
+    s_nc = 0;
+  }
+  __syncthreads();
+  {
+    int a = 0, b = 0;
+    for (int i = tid; i < R; i += nt) a += rm[i] != 0;
+    for (int j = tid; j < Cc; j += nt) b += cm[j] != 0;
+    if (a) atomicAdd(&s_nr, a);
+    if (b) atomicAdd(&s_nc, b);
+  }
+  __syncthreads();
+  const float nr = (float)s_nr, nc = (float)s_nc;
+  const float norm = -logf(nr + nc);  // learnable_sinkhorn.py:49
+  const float* sp = scores + (size_t)p * R * Cc;
+  for (int e = tid; e < R1 * C1; e += nt) {
+    int i = e / C1, j = e - i * C1;
+    bool masked = (i < R && !rm[i]) || (j < Cc && !cm[j]);
+    float z = (i < R && j < Cc) ? sp[(size_t)i * Cc + j] : alpha;
+    Z[(size_t)i * ld + j] = masked ? -inf : z;
+  }
+  for (int i = tid; i < R1; i += nt) {
+    u[i] = 0.f;
+    lmu[i] = i < R ? (rm[i] ? norm : -inf) : logf(nc) + norm;
+  }
+  for (int j = tid; j < C1; j += nt) {
+    v[j] = 0.f;
+    lnu[j] = j < Cc ? (cm[j] ? norm : -inf) : logf(nr) + norm;
+  }
+  __syncthreads();
+  for (int it = 0; it < iters; it++) {
+    if (tid < R1) {  // u = log_mu - logsumexp_j(Z + v)
+      const float* zr = Z + (size_t)tid * ld;
+      float mx = -3.4e38f;
+      for (int j = 0; j < C1; j++) mx = fmaxf(mx, zr[j] + v[j]);
+      float s = 0.f;
+      for (int j = 0; j < C1; j++) s += __expf(zr[j] + v[j] - mx);
+      u[tid] = lmu[tid] - (mx + __logf(s));
+    }
+    __syncthreads();
+    if (tid < C1) {  // v = log_nu - logsumexp_i(Z + u)
+      float mx = -3.4e38f;
+      for (int i = 0; i < R1; i++) mx = fmaxf(mx, Z[(size_t)i * ld + tid] + u[i]);
+      float s = 0.f;
+      for (int i = 0; i < R1; i++) s += __expf(Z[(size_t)i * ld + tid] + u[i] - mx);
+      v[tid] = lnu[tid] - (mx + __logf(s));
+    }
+    __syncthreads();
+  }
+  float* op = out + (size_t)p * R1 * C1;
+  for (int e = tid; e < R1 * C1; e += nt) {
+    int i = e / C1, j = e - i * C1;
+    op[e] = Z[(size_t)i * ld + j] + u[i] + v[j] - norm;
+  }
+}
+
+extern "C" int rdm_sinkhorn(const float* scores, int num_patches, int R, int C, const unsigned char* row_masks,
+                            const unsigned char* col_masks, const int64_t* row_mask_gather, const int64_t* col_mask_gather,
+                            const float* alpha, int num_iterations, float inf, float* out, cudaStream_t stream) {
+  RDM_CHECK_ARG(R >= 1 && C >= 1 && R <= 159 && C <= 159, "rdm_sinkhorn: patch size must be <= 159");
+  if (num_patches == 0) return RDM_OK;
+  int R1 = R + 1, C1 = C + 1, ld = (C1 % 2 == 0) ? C1 + 1 : C1;
+  size_t smem = ((size_t)R1 * ld + 2 * R1 + 2 * C1) * sizeof(float);
+  RDM_CHECK_ARG(smem <= 200 * 1024, "rdm_sinkhorn: patch too large for shared memory");
+  if (smem > 48 * 1024)
+    RDM_CUDA(cudaFuncSetAttribute(sinkhorn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sinkhorn_kernel<<<num_patches, 160, smem, stream>>>(scores, R, C, row_masks, col_masks, row_mask_gather,
+                                                     col_mask_gather, alpha, num_iterations, inf, out);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}

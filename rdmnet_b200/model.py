@@ -1,0 +1,270 @@
+"""RDMNet forward orchestration on the GPU: host-side mirror of experiments/backbone.py (Encoder/Decoder),
+experiments/model_infer.py (RDMNet, create_model), experiments/config.py (the constants the model reads) and
+geotransformer/utils/data.py:13-77 (precompute_data_stack_mode), with every operator executed by librdm_sm100.so.
+
+Differences from the reference that are part of the design (none changes results):
+  * the voxel pyramid (4x grid_subsample + radius searches) is built on the GPU inside forward() when the
+    data_dict does not carry 'neighbors' (the reference builds it in CPU DataLoader workers and ships ~75 MB of
+    int64 tables over PCIe per pair); upsampling[0], which the reference computes and never reads
+    (experiments/backbone.py:144), is skipped on that path;
+  * NMS, partition, Sinkhorn and the pose solver run without host round trips; the only host syncs left are the
+    data-dependent output shapes (pyramid lengths, NMS survivors, number of correspondences).
+"""
+import types
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .modules import (ConvBlock, LastUnaryBlock, LearnableLogOptimalTransport, LocalGlobalRegistration, NMS,
+                      ResidualBlock, SuperPointMatching, ThDRoFormer, UnaryBlock, Vote_layer)
+
+DEFAULT_NEIGHBOR_LIMITS = [65, 63, 69, 70, 81]  # calibrate_neighbors_stack_mode on the bundled pairs
+
+
+class _NS(types.SimpleNamespace):
+    def __getitem__(self, k):
+        return getattr(self, k)
+
+
+def make_cfg():
+    """The subset of experiments/config.py:10-188 that the model reads (same attribute paths)."""
+    c = _NS()
+    c.seed = 7351
+    c.backbone = _NS(num_stages=5, init_voxel_size=0.3, kernel_size=15, base_radius=4.25, base_sigma=2.0,
+                     init_radius=4.25 * 0.3, init_sigma=2.0 * 0.3, group_norm=32, input_dim=1, init_dim=64, output_dim=256)
+    c.model = _NS(ground_truth_matching_radius=0.6, num_points_in_patch=128, num_sinkhorn_iterations=100,
+                  ground_truth_corres_radius=2.4, n2p_score_threshold=0.1, p2p_score_threshold=0.1)
+    c.coarse_matching = _NS(num_targets=128, overlap_threshold=0.1, num_correspondences=256, dual_normalization=True)
+    c.thdroformer = _NS(input_dim=2048, hidden_dim=128, output_dim=256, num_heads=4, num_layers=4, input_dim2=256,
+                        num_layers2=4, k2=None)
+    c.Vote = _NS(model_use_vote=True, inference_use_vote=True, MAX_TRANSLATE_RANGE=[3.0, 3.0, 3.0], MLPS=[512, 256],
+                 NMS_radius=2.4, n2n_overlap_threshold=1.2, n2p_overlap_threshold=0.6, p2p_overlap_threshold=0.6)
+    c.fine_matching = _NS(acceptance_radius=0.6, mutual=False, topk=1, confidence_threshold=0, use_dustbin=True,
+                          use_global_score=False, correspondence_threshold=3, correspondence_limit=None,
+                          num_refinement_steps=5)
+    c.test = _NS(vis=False)
+    c.neighbor_limits = list(DEFAULT_NEIGHBOR_LIMITS)
+    return c
+
+
+def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, neighbor_limits,
+                               index_dtype=torch.int64, skip_unused=False):
+    """geotransformer/utils/data.py:13-77 on the GPU. Returns the same dict (+ 'lengths_host')."""
+    points_list, lengths_list, host = [], [], []
+    for i in range(num_stages):
+        if i > 0:
+            points, lengths = ops.grid_subsample(points, lengths, voxel_size=voxel_size)
+        points_list.append(points)
+        lengths_list.append(lengths)
+        voxel_size *= 2
+    neighbors, subsampling, upsampling, widths = [], [], [], []
+
+    def search(q, s, ql, sl, r, lim):
+        out, maxc = ops.radius_search_raw(q, s, ql, sl, r, lim, index_dtype=index_dtype)
+        widths.append((out, maxc, lim))
+        return out
+
+    for i in range(num_stages):
+        P, Ln = points_list[i], lengths_list[i]
+        neighbors.append(search(P, P, Ln, Ln, radius, neighbor_limits[i]))
+        if i < num_stages - 1:
+            S, Sl = points_list[i + 1], lengths_list[i + 1]
+            subsampling.append(search(S, P, Sl, Ln, radius, neighbor_limits[i]))
+            if skip_unused and i == 0:
+                upsampling.append(None)
+            else:
+                upsampling.append(search(P, S, Ln, Sl, radius * 2, neighbor_limits[i + 1]))
+        radius *= 2
+    # one D2H for all data-dependent sizes: per-stage lengths and the max neighbour counts (row widths)
+    meta = torch.cat([torch.stack(lengths_list).reshape(-1).to(torch.int64)] + [w[1].to(torch.int64) for w in widths]).tolist()
+    nb = lengths_list[0].shape[0]
+    host = [meta[i * nb:(i + 1) * nb] for i in range(num_stages)]
+    maxcs = meta[num_stages * nb:]
+
+    def narrow(t):
+        if t is None:
+            return None
+        for (out, _, lim), mc in zip(widths, maxcs):
+            if out is t:
+                return t if mc >= lim else t[:, :mc].contiguous()  # radius_search.py:25-26 width semantics
+        return t
+
+    return {
+        "points": points_list, "lengths": lengths_list, "lengths_host": host,
+        "neighbors": [narrow(t) for t in neighbors], "subsampling": [narrow(t) for t in subsampling],
+        "upsampling": [narrow(t) for t in upsampling],
+    }
+
+
+class Encoder(nn.Module):
+    """experiments/backbone.py:7-107."""
+
+    def __init__(self, input_dim, init_dim, kernel_size, init_radius, init_sigma, group_norm):
+        super().__init__()
+        d, r, s, g, k = init_dim, init_radius, init_sigma, group_norm, kernel_size
+        self.encoder1_1 = ConvBlock(input_dim, d, k, r, s, g)
+        self.encoder1_2 = ResidualBlock(d, d * 2, k, r, s, g)
+        self.encoder2_1 = ResidualBlock(d * 2, d * 2, k, r, s, g, strided=True)
+        self.encoder2_2 = ResidualBlock(d * 2, d * 4, k, r * 2, s * 2, g)
+        self.encoder2_3 = ResidualBlock(d * 4, d * 4, k, r * 2, s * 2, g)
+        self.encoder3_1 = ResidualBlock(d * 4, d * 4, k, r * 2, s * 2, g, strided=True)
+        self.encoder3_2 = ResidualBlock(d * 4, d * 8, k, r * 4, s * 4, g)
+        self.encoder3_3 = ResidualBlock(d * 8, d * 8, k, r * 4, s * 4, g)
+        self.encoder4_1 = ResidualBlock(d * 8, d * 8, k, r * 4, s * 4, g, strided=True)
+        self.encoder4_2 = ResidualBlock(d * 8, d * 16, k, r * 8, s * 8, g)
+        self.encoder4_3 = ResidualBlock(d * 16, d * 16, k, r * 8, s * 8, g)
+        self.encoder5_1 = ResidualBlock(d * 16, d * 16, k, r * 8, s * 8, g, strided=True)
+        self.encoder5_2 = ResidualBlock(d * 16, d * 32, k, r * 16, s * 16, g)
+        self.encoder5_3 = ResidualBlock(d * 32, d * 32, k, r * 16, s * 16, g)
+
+    def forward(self, feats, data_dict):
+        P, NB, SUB = data_dict["points"], data_dict["neighbors"], data_dict["subsampling"]
+        out = []
+        x = self.encoder1_1(feats, P[0], P[0], NB[0])
+        x = self.encoder1_2(x, P[0], P[0], NB[0])
+        out.append(x)
+        for s in range(1, 5):
+            x = getattr(self, f"encoder{s + 1}_1")(x, P[s], P[s - 1], SUB[s - 1])
+            x = getattr(self, f"encoder{s + 1}_2")(x, P[s], P[s], NB[s])
+            x = getattr(self, f"encoder{s + 1}_3")(x, P[s], P[s], NB[s])
+            out.append(x)
+        return out
+
+
+class Decoder(nn.Module):
+    """experiments/backbone.py:110-151."""
+
+    def __init__(self, output_dim, init_dim, group_norm):
+        super().__init__()
+        self.decoder4 = UnaryBlock(init_dim * 20 + 1, init_dim * 16, group_norm)
+        self.decoder3 = UnaryBlock(init_dim * 24, init_dim * 8, group_norm)
+        self.decoder2 = LastUnaryBlock(init_dim * 12, output_dim + 1)
+
+    def forward(self, feats, data_dict):
+        UP = data_dict["upsampling"]
+        l4 = self.decoder4(ops.nearest_upsample_concat(feats[4], UP[3], feats[3]))
+        l3 = self.decoder3(ops.nearest_upsample_concat(l4, UP[2], feats[2]))
+        l2 = self.decoder2(ops.nearest_upsample_concat(l3, UP[1], feats[1]))
+        return [l2, l3, l4]
+
+
+class RDMNet(nn.Module):
+    """experiments/model_infer.py:26-354 (inference forward). Same submodule names => same checkpoint keys."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.num_points_in_patch = cfg.model.num_points_in_patch
+        b, t = cfg.backbone, cfg.thdroformer
+        self.encoder = Encoder(b.input_dim, b.init_dim, b.kernel_size, b.init_radius, b.init_sigma, b.group_norm)
+        self.decoder = Decoder(b.output_dim, b.init_dim, b.group_norm)
+        self.transformer = ThDRoFormer(t.input_dim, t.output_dim, t.hidden_dim, t.num_heads, t.num_layers)
+        self.use_vote = cfg.Vote.inference_use_vote and cfg.Vote.model_use_vote
+        if cfg.Vote.model_use_vote:
+            cfg.Vote.input_feats_dim = t.output_dim
+            self.vote = Vote_layer(cfg.Vote, 1)
+            self.nms = NMS(cfg.Vote, cfg.neighbor_limits)
+            self.proj_n2n_score = nn.Linear(t.output_dim, 1)
+            self.transformer2 = ThDRoFormer(t.input_dim2, t.output_dim, t.hidden_dim, t.num_heads, t.num_layers2, t.k2)
+        self.proj_n2p_score = nn.Linear(t.output_dim, 1)
+        self.coarse_matching = SuperPointMatching(cfg.coarse_matching.num_correspondences,
+                                                  cfg.coarse_matching.dual_normalization, cfg.model.n2p_score_threshold)
+        f = cfg.fine_matching
+        self.fine_matching = LocalGlobalRegistration(
+            f.topk, f.acceptance_radius, mutual=f.mutual, confidence_threshold=f.confidence_threshold,
+            use_dustbin=f.use_dustbin, use_global_score=f.use_global_score,
+            correspondence_threshold=f.correspondence_threshold, correspondence_limit=f.correspondence_limit,
+            num_refinement_steps=f.num_refinement_steps)
+        self.optimal_transport = LearnableLogOptimalTransport(cfg.model.num_sinkhorn_iterations)
+
+    def build_pyramid(self, points, lengths):
+        b = self.cfg.backbone
+        return precompute_data_stack_mode(points.contiguous(), lengths, b.num_stages, b.init_voxel_size, b.init_radius,
+                                          self.cfg.neighbor_limits, index_dtype=torch.int32, skip_unused=True)
+
+    @torch.no_grad()
+    def forward(self, data_dict):
+        out = {}
+        if "neighbors" not in data_dict:  # raw stacked points in: build the pyramid here, on the GPU
+            data_dict = dict(data_dict)
+            data_dict.update(self.build_pyramid(data_dict["points"], data_dict["lengths"]))
+        L = data_dict.get("lengths_host")
+        if L is None:
+            L = [l.tolist() for l in data_dict["lengths"]]
+        nc, nf, n0 = int(L[-1][0]), int(L[1][0]), int(L[0][0])
+        points_c, points_f, points = data_dict["points"][-1], data_dict["points"][1], data_dict["points"][0]
+        feats = data_dict.get("features")
+        if feats is None:
+            feats = torch.ones((points.shape[0], 1), dtype=torch.float32, device=points.device)
+        out["ori_ref_points_c"], out["ori_src_points_c"] = points_c[:nc], points_c[nc:]
+        ref_points_f, src_points_f = points_f[:nf].contiguous(), points_f[nf:].contiguous()
+        out["ref_points_f"], out["src_points_f"] = ref_points_f, src_points_f
+        out["ref_points"], out["src_points"] = points[:n0], points[n0:]
+
+        feats_list = self.encoder(feats, data_dict)
+        feats_c = feats_list[-1]
+        ref_feats_c, src_feats_c = self.transformer(points_c[:nc].contiguous(), points_c[nc:].contiguous(),
+                                                    feats_c[:nc], feats_c[nc:])
+        tf = torch.cat([ref_feats_c, src_feats_c], 0)
+        n2p_logit = ops.linear(tf, self.proj_n2p_score.weight, self.proj_n2p_score.bias)  # (Nc,1)
+        n2p = ops.activation(n2p_logit.view(-1), 3)
+        feats_list[-1] = torch.cat([tf, n2p_logit], 1)
+        dec = self.decoder(feats_list, data_dict)[0]
+        feats_f = dec[:, :-1].contiguous()
+        p2p = ops.activation(dec[:, -1].contiguous(), 3)
+        out["ref_p2p_scores_c"], out["src_p2p_scores_c"] = p2p[:nf], p2p[nf:]
+        ref_n2p, src_n2p = n2p[:nc], n2p[nc:]
+
+        if self.use_vote:
+            shifted, vf = self.vote(points_c, tf)
+            out["shifted_ref_points_c"], out["shifted_src_points_c"] = shifted[:nc], shifted[nc:]
+            n2n = ops.activation(ops.linear(vf, self.proj_n2n_score.weight, self.proj_n2n_score.bias).view(-1), 3)
+            masks = self.nms(shifted.contiguous(), data_dict["lengths"][-1])
+            out["mask"] = masks
+            ref_sel = torch.nonzero(masks[:nc], as_tuple=True)[0]  # data-dependent count: host sync
+            src_sel = torch.nonzero(masks[nc:], as_tuple=True)[0]
+            ref_points_c, src_points_c = shifted[:nc][ref_sel].contiguous(), shifted[nc:][src_sel].contiguous()
+            ref_feats_c, src_feats_c = vf[:nc][ref_sel], vf[nc:][src_sel]
+            out["ref_n2p_scores_c"], out["src_n2p_scores_c"] = ref_n2p[ref_sel], src_n2p[src_sel]
+            out["ref_n2n_scores_c"], out["src_n2n_scores_c"] = n2n[:nc][ref_sel], n2n[nc:][src_sel]
+            ref_feats_c, src_feats_c = self.transformer2(ref_points_c, src_points_c, ref_feats_c, src_feats_c)
+        else:
+            ref_points_c, src_points_c = points_c[:nc].contiguous(), points_c[nc:].contiguous()
+            out["ref_n2p_scores_c"], out["src_n2p_scores_c"] = ref_n2p, src_n2p
+        out["ref_points_c"], out["src_points_c"] = ref_points_c, src_points_c
+        ref_feats_c_norm = torch.nn.functional.normalize(ref_feats_c, p=2, dim=1)
+        src_feats_c_norm = torch.nn.functional.normalize(src_feats_c, p=2, dim=1)
+        out["ref_feats_c"], out["src_feats_c"] = ref_feats_c_norm, src_feats_c_norm
+
+        k = self.num_points_in_patch
+        _, ref_node_masks, ref_knn, ref_knn_masks = ops.point_to_node_partition(ref_points_f, ref_points_c, k)
+        _, src_node_masks, src_knn, src_knn_masks = ops.point_to_node_partition(src_points_f, src_points_c, k)
+        ref_feats_f, src_feats_f = feats_f[:nf].contiguous(), feats_f[nf:].contiguous()
+        out["ref_feats_f"], out["src_feats_f"] = ref_feats_f, src_feats_f
+
+        ref_ci, src_ci, node_corr_scores = self.coarse_matching(ref_feats_c_norm, src_feats_c_norm, ref_node_masks,
+                                                                src_node_masks)
+        out["ref_node_corr_indices"], out["src_node_corr_indices"] = ref_ci, src_ci
+        out["node_corr_scores"] = node_corr_scores
+        out["ref_node_knn_indices"], out["src_node_knn_indices"] = ref_knn, src_knn
+        out["ref_node_knn_masks"], out["src_node_knn_masks"] = ref_knn_masks, src_knn_masks
+
+        scores = ops.patch_scores(ref_feats_f, src_feats_f, ref_knn, src_knn, ref_ci, src_ci)
+        rm8, sm8 = ref_knn_masks.to(torch.uint8), src_knn_masks.to(torch.uint8)
+        ot = self.optimal_transport
+        matching_scores = ops.sinkhorn(scores, rm8, sm8, ot.alpha, ot.num_iterations, ot.inf, row_gather=ref_ci,
+                                       col_gather=src_ci)
+        out["matching_scores"] = matching_scores
+        fm = self.fine_matching
+        ref_corr, src_corr, corr_scores, T, bij = ops.local_global_registration(
+            matching_scores, ref_points_f, src_points_f, ref_knn, src_knn, rm8, sm8, ref_ci, src_ci, fm.acceptance_radius,
+            fm.correspondence_threshold, fm.num_refinement_steps)
+        out["ref_corr_points"], out["src_corr_points"], out["corr_scores"] = ref_corr, src_corr, corr_scores
+        out["estimated_transform"] = T
+        out["corr_patch_ij"] = bij
+        return out
+
+
+def create_model(cfg=None):
+    return RDMNet(cfg if cfg is not None else make_cfg())

@@ -151,3 +151,288 @@ class ResidualBlock(nn.Module):
         shortcut = self.unary_shortcut(shortcut)
         # unary2 = Linear + GroupNorm, fused with "+ shortcut" and the final LeakyReLU (:222-224)
         return self.unary2(x, residual=shortcut, act=1)
+
+
+# ------------------------------------------------------------------------------------------------- transformer
+class AttentionOutput(nn.Module):
+    """geotransformer/modules/transformer/output_layer.py:6-21 (dropout=None)."""
+
+    def __init__(self, d_model, dropout=None, activation_fn="ReLU"):
+        super().__init__()
+        if dropout is not None or activation_fn != "ReLU":
+            raise ValueError("only dropout=None / ReLU (the RDMNet configuration) is implemented")
+        self.expand = nn.Linear(d_model, d_model * 2)
+        self.squeeze = nn.Linear(d_model * 2, d_model)
+        self.norm = nn.LayerNorm(d_model)
+
+    def forward(self, x):
+        h = ops.linear(x, self.expand.weight, self.expand.bias, act=2)
+        h = ops.linear(h, self.squeeze.weight, self.squeeze.bias)
+        return ops.layer_norm(h, self.norm.weight, self.norm.bias, residual=x, eps=self.norm.eps)
+
+
+class _PosEncoderBuffers(nn.Module):
+    """Holds the (unused) `div_term` buffer of RotaryPositionalEmbedding so that checkpoints load strictly
+    (rdmnet/thdroformer/thdroformer.py:43-54)."""
+
+    def __init__(self, d_model, num_heads):
+        super().__init__()
+        d = d_model // num_heads
+        div = torch.exp(torch.arange(0, d, 2).float() * (-math.log(10000.0) / d))
+        self.register_buffer("div_term", div.repeat_interleave(2).view(1, 1, 1, -1))
+
+
+class MultiHeadAttention(nn.Module):
+    """vanilla_transformer.py:15-70 (no masks / factors: RDMNet passes none) and, with `rotary=True`,
+    RPEMultiHeadAttention (thdroformer.py:88-139, k=None)."""
+
+    def __init__(self, d_model, num_heads, dropout=None, rotary=False):
+        super().__init__()
+        if d_model % num_heads != 0:
+            raise ValueError("`d_model` ({}) must be a multiple of `num_heads` ({}).".format(d_model, num_heads))
+        self.d_model, self.num_heads, self.d_model_per_head = d_model, num_heads, d_model // num_heads
+        self.proj_q = nn.Linear(d_model, d_model)
+        self.proj_k = nn.Linear(d_model, d_model)
+        self.proj_v = nn.Linear(d_model, d_model)
+        if rotary:
+            self.pos_encoder = _PosEncoderBuffers(d_model, num_heads)
+        self.rotary = rotary
+
+    def forward(self, input_q, input_k, input_v, embed_q=None, embed_k=None):
+        q = ops.linear(input_q, self.proj_q.weight, self.proj_q.bias)
+        k = ops.linear(input_k, self.proj_k.weight, self.proj_k.bias)
+        v = ops.linear(input_v, self.proj_v.weight, self.proj_v.bias)
+        if self.rotary:
+            q = ops.rope(q, embed_q)
+            k = ops.rope(k, embed_k)
+        return ops.attention(q, k, v, self.num_heads)
+
+
+class AttentionLayer(nn.Module):
+    """vanilla_transformer.py:73-102 / RPEAttentionLayer thdroformer.py:141-172."""
+
+    def __init__(self, d_model, num_heads, dropout=None, rotary=False):
+        super().__init__()
+        self.attention = MultiHeadAttention(d_model, num_heads, dropout=dropout, rotary=rotary)
+        self.linear = nn.Linear(d_model, d_model)
+        self.norm = nn.LayerNorm(d_model)
+
+    def forward(self, input_states, memory_states, embed_q=None, embed_k=None):
+        h = self.attention(input_states, memory_states, memory_states, embed_q, embed_k)
+        h = ops.linear(h, self.linear.weight, self.linear.bias)
+        return ops.layer_norm(h, self.norm.weight, self.norm.bias, residual=input_states, eps=self.norm.eps)
+
+
+class TransformerLayer(nn.Module):
+    """vanilla_transformer.py:105-129 / RPETransformerLayer thdroformer.py:175-202. 2-D (N,C) states."""
+
+    def __init__(self, d_model, num_heads, dropout=None, activation_fn="ReLU", rotary=False):
+        super().__init__()
+        self.attention = AttentionLayer(d_model, num_heads, dropout=dropout, rotary=rotary)
+        self.output = AttentionOutput(d_model, dropout=dropout, activation_fn=activation_fn)
+
+    def forward(self, input_states, memory_states, embed_q=None, embed_k=None):
+        return self.output(self.attention(input_states, memory_states, embed_q, embed_k))
+
+
+class RPEConditionalTransformer(nn.Module):
+    """thdroformer.py:204-251: alternating self (rotary) / cross layers; cross attention is sequential
+    (feats1 attends to the already-updated feats0, :244-245)."""
+
+    def __init__(self, blocks, d_model, num_heads, dropout=None, activation_fn="ReLU", return_attention_scores=False,
+                 parallel=False, k=None):
+        super().__init__()
+        if k is not None or parallel or return_attention_scores:
+            raise ValueError("k / parallel / return_attention_scores are not used by RDMNet and are not implemented")
+        self.blocks = blocks
+        self.layers = nn.ModuleList(
+            [TransformerLayer(d_model, num_heads, dropout, activation_fn, rotary=(b == "self")) for b in blocks])
+
+    def forward(self, feats0, feats1, embeddings0, embeddings1, masks0=None, masks1=None):
+        for layer, block in zip(self.layers, self.blocks):
+            if block == "self":
+                feats0 = layer(feats0, feats0, embeddings0, embeddings0)
+                feats1 = layer(feats1, feats1, embeddings1, embeddings1)
+            else:
+                feats0 = layer(feats0, feats1)
+                feats1 = layer(feats1, feats0)
+        return feats0, feats1
+
+
+class posEmbedding(nn.Module):
+    """thdroformer.py:253-263."""
+
+    def __init__(self, hidden_dim, reduction_a="max"):
+        super().__init__()
+        self.proj = nn.Linear(3, hidden_dim // 2)
+
+    def forward(self, points):
+        return ops.linear(points, self.proj.weight, self.proj.bias)
+
+
+class ThDRoFormer(nn.Module):
+    """rdmnet/thdroformer/thdroformer.py:266-347. Accepts (1,N,3)/(1,N,C) like the reference (or 2-D tensors) and
+    returns tensors of the same rank."""
+
+    def __init__(self, input_dim, output_dim, hidden_dim, num_heads, num_layers, k=None, dropout=None,
+                 activation_fn="ReLU", reduction_a="max"):
+        super().__init__()
+        self.embedding = posEmbedding(hidden_dim, reduction_a=reduction_a)
+        self.in_proj = nn.Linear(input_dim, hidden_dim)
+        self.transformer = RPEConditionalTransformer(["self", "cross"] * num_layers, hidden_dim, num_heads,
+                                                     dropout=dropout, activation_fn=activation_fn, k=k)
+        self.out_proj = nn.Linear(hidden_dim, output_dim)
+
+    def forward(self, ref_points, src_points, ref_feats, src_feats, ref_masks=None, src_masks=None):
+        batched = ref_feats.ndim == 3
+        if batched:
+            if ref_feats.shape[0] != 1:
+                raise RuntimeError("ThDRoFormer processes one pair per call (as the reference: thdroformer.py:76)")
+            ref_points, src_points, ref_feats, src_feats = ref_points[0], src_points[0], ref_feats[0], src_feats[0]
+        e0, e1 = self.embedding(ref_points.contiguous()), self.embedding(src_points.contiguous())
+        f0 = ops.linear(ref_feats, self.in_proj.weight, self.in_proj.bias)
+        f1 = ops.linear(src_feats, self.in_proj.weight, self.in_proj.bias)
+        f0, f1 = self.transformer(f0, f1, e0, e1)
+        f0 = ops.linear(f0, self.out_proj.weight, self.out_proj.bias)
+        f1 = ops.linear(f1, self.out_proj.weight, self.out_proj.bias)
+        return (f0[None], f1[None]) if batched else (f0, f1)
+
+
+# ------------------------------------------------------------------------------------------------- vote / NMS
+class Vote_layer(nn.Module):
+    """rdmnet/vote/vote.py:43-117. `cfgs` needs MLPS, MAX_TRANSLATE_RANGE, input_feats_dim."""
+
+    def __init__(self, cfgs, r):
+        super().__init__()
+        pre = cfgs.input_feats_dim
+        layers = []
+        for width in cfgs.MLPS:
+            layers.extend([nn.Linear(pre, width), nn.LayerNorm(width), nn.ReLU()])
+            pre = width
+        self.mlp_modules = nn.Sequential(*layers) if layers else None
+        self.ctr_reg = nn.Linear(pre, 3 + cfgs.input_feats_dim)
+        rng = cfgs.MAX_TRANSLATE_RANGE
+        self.max_offset_limit = torch.tensor(rng).float() / r if rng is not None else None
+        self.out_proj = nn.Sequential(nn.LayerNorm(cfgs.input_feats_dim))
+
+    def forward(self, xyz, features, aug_rotation=None):
+        if xyz.ndim == 3:
+            xyz, features = xyz[0], features[0]
+        h = features
+        if self.mlp_modules is not None:
+            mods = list(self.mlp_modules)
+            for i in range(0, len(mods), 3):
+                h = ops.linear(h, mods[i].weight, mods[i].bias)
+                h = ops.layer_norm(h, mods[i + 1].weight, mods[i + 1].bias, relu=True, eps=mods[i + 1].eps)
+        off = ops.linear(h, self.ctr_reg.weight, self.ctr_reg.bias)
+        ctr, feat_off = off[:, :3], off[:, 3:]
+        if self.max_offset_limit is not None:
+            lim = self.max_offset_limit.to(xyz.device)
+            ctr = torch.minimum(torch.maximum(ctr, -lim), lim)  # the two torch.where clamps of vote.py:105-107
+        vote_xyz = xyz + ctr
+        ln = self.out_proj[0]
+        new_features = ops.layer_norm(features, ln.weight, ln.bias, residual=feat_off.contiguous(), eps=ln.eps)
+        return vote_xyz, new_features
+
+
+class NMS(nn.Module):
+    """rdmnet/vote/vote.py:6-40: radius search on the shifted nodes + greedy selection, both on the device."""
+
+    def __init__(self, cfgs, neighbor_limits):
+        super().__init__()
+        self.NMS_radius = cfgs.NMS_radius
+        self.neighbor_limits = int(neighbor_limits[-1])
+
+    @torch.no_grad()
+    def forward(self, nodes_dict, length_dict=None, overlap_score=None, features=None):
+        nodes = nodes_dict.contiguous()
+        if length_dict is None:
+            length_dict = torch.tensor([nodes.shape[0]], dtype=torch.int64, device=nodes.device)
+        lengths = length_dict.to(device=nodes.device, dtype=torch.int64)
+        idx, _ = ops.radius_search_raw(nodes, nodes, lengths, lengths, self.NMS_radius, self.neighbor_limits,
+                                       index_dtype=torch.int32)
+        return ops.nms(idx)
+
+
+# ------------------------------------------------------------------------------------------------- matching
+class LearnableLogOptimalTransport(nn.Module):
+    """geotransformer/modules/sinkhorn/learnable_sinkhorn.py:5-70."""
+
+    def __init__(self, num_iterations, inf=1e12):
+        super().__init__()
+        self.num_iterations = num_iterations
+        self.register_parameter("alpha", nn.Parameter(torch.tensor(1.0)))
+        self.inf = inf
+
+    def forward(self, scores, row_masks=None, col_masks=None):
+        b, m, n = scores.shape
+        if row_masks is None:
+            row_masks = torch.ones((b, m), dtype=torch.bool, device=scores.device)
+        if col_masks is None:
+            col_masks = torch.ones((b, n), dtype=torch.bool, device=scores.device)
+        return ops.sinkhorn(scores, row_masks, col_masks, self.alpha, self.num_iterations, self.inf)
+
+    def __repr__(self):
+        return self.__class__.__name__ + "(num_iterations={})".format(self.num_iterations)
+
+
+class SuperPointMatching(nn.Module):
+    """geotransformer/modules/geotransformer/superpoint_matching.py:7-83 (without the optional n2p-score gating,
+    which model.py:308-311 does not use)."""
+
+    def __init__(self, num_correspondences, dual_normalization=True, n2p_score_threshold=None):
+        super().__init__()
+        self.num_correspondences = num_correspondences
+        self.dual_normalization = dual_normalization
+        self.n2p_score_threshold = n2p_score_threshold
+
+    def forward(self, ref_feats, src_feats, ref_masks=None, src_masks=None, ref_n2p_scores_c=None, src_n2p_scores_c=None):
+        if ref_n2p_scores_c is not None:
+            raise RuntimeError("n2p-score gating is not used by RDMNet.forward and is not implemented")
+        if ref_masks is None:
+            ref_masks = torch.ones(ref_feats.shape[0], dtype=torch.bool, device=ref_feats.device)
+        if src_masks is None:
+            src_masks = torch.ones(src_feats.shape[0], dtype=torch.bool, device=src_feats.device)
+        return ops.coarse_matching(ref_feats, src_feats, ref_masks, src_masks, self.num_correspondences,
+                                   self.dual_normalization)
+
+
+class WeightedProcrustes(nn.Module):
+    """geotransformer/modules/registration/procrustes.py:76-91."""
+
+    def __init__(self, weight_thresh=0.0, eps=1e-5, return_transform=False):
+        super().__init__()
+        self.weight_thresh, self.eps, self.return_transform = weight_thresh, eps, return_transform
+
+    def forward(self, src_points, tgt_points, weights=None):
+        return ops.weighted_procrustes(src_points, tgt_points, weights, self.weight_thresh, self.eps, self.return_transform)
+
+
+class LocalGlobalRegistration(nn.Module):
+    """geotransformer/modules/geotransformer/local_global_registration.py:11-243 for the RDMNet configuration
+    (k=1, mutual=False, use_dustbin=True, use_global_score=False, correspondence_limit=None)."""
+
+    def __init__(self, k, acceptance_radius, mutual=True, confidence_threshold=0.05, use_dustbin=False,
+                 use_global_score=False, correspondence_threshold=3, correspondence_limit=None, num_refinement_steps=5):
+        super().__init__()
+        if k != 1 or mutual or not use_dustbin or use_global_score or correspondence_limit is not None:
+            raise ValueError("only k=1, mutual=False, use_dustbin=True, use_global_score=False, "
+                             "correspondence_limit=None (experiments/config.py:152-161) is implemented")
+        self.k, self.acceptance_radius, self.mutual = k, acceptance_radius, mutual
+        self.confidence_threshold, self.use_dustbin, self.use_global_score = confidence_threshold, use_dustbin, use_global_score
+        self.correspondence_threshold, self.correspondence_limit = correspondence_threshold, correspondence_limit
+        self.num_refinement_steps = num_refinement_steps
+        self.procrustes = WeightedProcrustes(return_transform=True)
+
+    def forward(self, ref_knn_points, src_knn_points, ref_knn_masks, src_knn_masks, score_mat, global_scores=None):
+        """Reference signature: (B,K,3) x2, (B,K) x2 masks, (B,K+1,K+1) log scores. The batched knn tensors are
+        treated as their own point tables (identity gather)."""
+        b, k = ref_knn_masks.shape
+        dev = score_mat.device
+        ident = torch.arange(b * k, device=dev, dtype=torch.int64).view(b, k)
+        rows = torch.arange(b, device=dev, dtype=torch.int64)
+        ref_c, src_c, sc, T, _ = ops.local_global_registration(
+            score_mat, ref_knn_points.reshape(-1, 3).contiguous(), src_knn_points.reshape(-1, 3).contiguous(), ident, ident,
+            ref_knn_masks.to(torch.uint8).contiguous(), src_knn_masks.to(torch.uint8).contiguous(), rows, rows,
+            self.acceptance_radius, self.correspondence_threshold, self.num_refinement_steps)
+        return ref_c, src_c, sc, T

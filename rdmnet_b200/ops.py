@@ -115,8 +115,10 @@ def _idx_bytes(idx):
     raise RuntimeError("neighbor indices must be int64 or int32")
 
 
-def linear(x, weight, bias=None, weight_is_kn=False):
-    """torch.nn.functional.linear on the fp32 SIMT/tensor path. weight (out,in) or, if weight_is_kn, (in,out)."""
+def linear(x, weight, bias=None, weight_is_kn=False, act=0):
+    """torch.nn.functional.linear (+ fused activation: 1 LeakyReLU(0.1), 2 ReLU). weight (out,in) or, if
+    weight_is_kn, (in,out)."""
+    x = x.contiguous()
     _chk(x, torch.float32, "x", 2)
     m, k = x.shape
     n = weight.shape[1] if weight_is_kn else weight.shape[0]
@@ -124,14 +126,14 @@ def linear(x, weight, bias=None, weight_is_kn=False):
     wsb = L.lib().rdm_linear_workspace(m, n, k) if m * n <= (1 << 20) else 0
     ws = _ws(wsb, x.device) if wsb else None
     L.call("rdm_linear", L.ptr(x), k, L.ptr(weight), weight.shape[1], 0 if weight_is_kn else 1, L.ptr(bias), L.ptr(out),
-           n, m, n, k, L.ptr(ws), wsb, L.stream())
+           n, m, n, k, act, L.ptr(ws), wsb, L.stream())
     return out
 
 
 def kpconv(s_feats, q_points, s_points, neighbor_indices, weights, kernel_points, sigma, bias=None):
     """KPConv.forward (geotransformer/modules/kpconv/kpconv.py:79-122)."""
+    s_feats, neighbor_indices = s_feats.contiguous(), neighbor_indices.contiguous()
     _chk(s_feats, torch.float32, "s_feats", 2)
-    _chk(neighbor_indices, neighbor_indices.dtype, "neighbor_indices", 2)
     m, h = neighbor_indices.shape
     n, c = s_feats.shape
     kk, cin, cout = weights.shape
@@ -148,6 +150,7 @@ def kpconv(s_feats, q_points, s_points, neighbor_indices, weights, kernel_points
 
 def maxpool(x, neighbor_indices):
     """geotransformer/modules/kpconv/functional.py:54-67."""
+    x, neighbor_indices = x.contiguous(), neighbor_indices.contiguous()
     m, h = neighbor_indices.shape
     n, c = x.shape
     out = torch.empty((m, c), dtype=torch.float32, device=x.device)
@@ -175,6 +178,7 @@ def nearest_upsample(x, upsample_indices):
 
 def group_norm(x, weight, bias, groups, residual=None, act=0, slope=0.1, eps=1e-5):
     """GroupNorm over stacked (N,C) features (kpconv/modules.py:33-50) + optional residual add + LeakyReLU."""
+    x = x.contiguous()
     _chk(x, torch.float32, "x", 2)
     n, c = x.shape
     y = torch.empty_like(x)
@@ -199,3 +203,158 @@ def activation(x, act, slope=0.1):
     y = torch.empty_like(x)
     L.call("rdm_activation", L.ptr(x), L.ptr(y), x.numel(), act, slope, L.stream())
     return y
+
+
+# ----------------------------------------------------------------------------------------------- transformer
+def rope(x, emb):
+    """RotaryPositionalEmbedding.forward (rdmnet/thdroformer/thdroformer.py:56-85). x (N,C), emb (N,C/2) -> (N,C)."""
+    n, c = x.shape
+    y = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    L.call("rdm_rope", x.data_ptr(), x.stride(0), emb.data_ptr(), emb.stride(0), L.ptr(y), c, n, c, L.stream())
+    return y
+
+
+def attention(q, k, v, heads):
+    """softmax(q k^T / sqrt(d)) v per head (thdroformer.py:20-40 with k=None; vanilla_transformer.py:54-66).
+    q (Nq,C), k/v (Nk,C): row-strided views are allowed (e.g. slices of a fused projection)."""
+    nq, c = q.shape
+    nk = k.shape[0]
+    for t in (q, k, v):
+        if t.stride(1) != 1:
+            raise RuntimeError("attention: channel dimension must be contiguous")
+    out = torch.empty((nq, c), dtype=torch.float32, device=q.device)
+    L.call("rdm_attention", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), L.ptr(out),
+           c, nq, nk, heads, c // heads, L.stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- matching
+def nms(neighbor_indices):
+    """Greedy loop of NMS.forward (rdmnet/vote/vote.py:33-40) on a radius-search table; returns a bool mask (N,)."""
+    neighbor_indices = neighbor_indices.contiguous()
+    n, h = neighbor_indices.shape
+    mask = torch.empty(n, dtype=torch.uint8, device=neighbor_indices.device)
+    L.call("rdm_nms", L.ptr(neighbor_indices), _idx_bytes(neighbor_indices), n, h, L.ptr(mask), L.stream())
+    return mask.bool()
+
+
+def pairwise_distance(x, y, normalized=False, channel_first=False):
+    """geotransformer/modules/ops/pairwise_distance.py:4-31 (2-D inputs), on the GEMM kernel."""
+    if channel_first:
+        x, y = x.t(), y.t()
+    xy = linear(x.contiguous(), y.contiguous())
+    if normalized:
+        d = 2.0 - 2.0 * xy
+    else:
+        d = (x ** 2).sum(-1)[:, None] - 2 * xy + (y ** 2).sum(-1)[None, :]
+    return d.clamp(min=1e-12)
+
+
+def point_to_node_partition(points, nodes, point_limit, return_count=False):
+    """geotransformer/modules/ops/pointcloud_partition.py:60-107."""
+    points, nodes = points.contiguous(), nodes.contiguous()
+    _chk(points, torch.float32, "points", 2)
+    _chk(nodes, torch.float32, "nodes", 2)
+    npts, nn_ = points.shape[0], nodes.shape[0]
+    dev = points.device
+    p2n = torch.empty(npts, dtype=torch.int32, device=dev)
+    node_masks = torch.empty(nn_, dtype=torch.uint8, device=dev)
+    knn = torch.empty((nn_, point_limit), dtype=torch.int64, device=dev)
+    knn_masks = torch.empty((nn_, point_limit), dtype=torch.uint8, device=dev)
+    wsb = L.lib().rdm_point_to_node_workspace(npts, nn_)
+    ws = _ws(wsb, dev)
+    L.call("rdm_point_to_node", L.ptr(points), npts, L.ptr(nodes), nn_, point_limit, L.ptr(p2n), L.ptr(node_masks),
+           L.ptr(knn), L.ptr(knn_masks), L.ptr(ws), wsb, L.stream())
+    p2n = p2n.long()
+    if return_count:
+        sizes = torch.bincount(p2n, minlength=nn_)
+        return p2n, sizes, node_masks.bool(), knn, knn_masks.bool()
+    return p2n, node_masks.bool(), knn, knn_masks.bool()
+
+
+def coarse_matching(ref_feats, src_feats, ref_masks, src_masks, num_correspondences, dual_normalization=True):
+    """SuperPointMatching.forward (geotransformer/modules/geotransformer/superpoint_matching.py:14-83)."""
+    m, n = ref_feats.shape[0], src_feats.shape[0]
+    dev = ref_feats.device
+    xy = linear(ref_feats.contiguous(), src_feats.contiguous())
+    rm = ref_masks.to(torch.uint8).contiguous()
+    sm = src_masks.to(torch.uint8).contiguous()
+    ri = torch.empty(num_correspondences, dtype=torch.int64, device=dev)
+    si = torch.empty(num_correspondences, dtype=torch.int64, device=dev)
+    sc = torch.empty(num_correspondences, dtype=torch.float32, device=dev)
+    cnt = torch.empty(1, dtype=torch.int32, device=dev)
+    sums = torch.empty(m + n, dtype=torch.float32, device=dev)
+    L.call("rdm_coarse_matching", L.ptr(xy), m, n, L.ptr(rm), L.ptr(sm), num_correspondences, 1 if dual_normalization else 0,
+           L.ptr(ri), L.ptr(si), L.ptr(sc), L.ptr(cnt), L.ptr(sums), L.stream())
+    k = int(cnt.item())  # data dependent length: min(num_correspondences, #valid node pairs)
+    return ri[:k], si[:k], sc[:k]
+
+
+def patch_scores(ref_feats_f, src_feats_f, ref_knn_indices, src_knn_indices, ref_corr_indices, src_corr_indices):
+    """index_select + einsum('bnd,bmd->bnm') / sqrt(C) (experiments/model.py:323-343) without the gathered copies."""
+    p, k = ref_corr_indices.shape[0], ref_knn_indices.shape[1]
+    c = ref_feats_f.shape[1]
+    out = torch.empty((p, k, k), dtype=torch.float32, device=ref_feats_f.device)
+    L.call("rdm_patch_scores", L.ptr(ref_feats_f), ref_feats_f.shape[0], L.ptr(src_feats_f), src_feats_f.shape[0], c,
+           L.ptr(ref_knn_indices), L.ptr(src_knn_indices), L.ptr(ref_corr_indices), L.ptr(src_corr_indices), p, k,
+           1.0 / c ** 0.5, L.ptr(out), L.stream())
+    return out
+
+
+def sinkhorn(scores, row_masks, col_masks, alpha, num_iterations, inf=1e12, row_gather=None, col_gather=None):
+    """LearnableLogOptimalTransport.forward (geotransformer/modules/sinkhorn/learnable_sinkhorn.py:13-66)."""
+    scores = scores.contiguous()
+    b, r, c = scores.shape
+    rm = row_masks.to(torch.uint8).contiguous()
+    cm = col_masks.to(torch.uint8).contiguous()
+    out = torch.empty((b, r + 1, c + 1), dtype=torch.float32, device=scores.device)
+    alpha = alpha.detach().reshape(1).float().contiguous()
+    L.call("rdm_sinkhorn", L.ptr(scores), b, r, c, L.ptr(rm), L.ptr(cm), L.ptr(row_gather), L.ptr(col_gather), L.ptr(alpha),
+           num_iterations, inf, L.ptr(out), L.stream())
+    return out
+
+
+def weighted_procrustes(src_points, ref_points, weights=None, weight_thresh=0.0, eps=1e-5, return_transform=False):
+    """geotransformer/modules/registration/procrustes.py:6-73 with the SVD on the device."""
+    squeeze = src_points.ndim == 2
+    if squeeze:
+        src_points, ref_points = src_points[None], ref_points[None]
+        weights = None if weights is None else weights[None]
+    b, n = src_points.shape[:2]
+    if weights is None:
+        weights = torch.ones((b, n), dtype=torch.float32, device=src_points.device)
+    if weight_thresh != 0.0:
+        weights = torch.where(weights < weight_thresh, torch.zeros_like(weights), weights)
+    T = torch.empty((b, 4, 4), dtype=torch.float32, device=src_points.device)
+    L.call("rdm_weighted_procrustes", L.ptr(src_points.contiguous()), L.ptr(ref_points.contiguous()),
+           L.ptr(weights.contiguous()), b, n, eps, L.ptr(T), L.stream())
+    if return_transform:
+        return T[0] if squeeze else T
+    R, t = T[:, :3, :3], T[:, :3, 3]
+    return (R[0], t[0]) if squeeze else (R, t)
+
+
+def local_global_registration(matching_scores, ref_points_f, src_points_f, ref_knn_indices, src_knn_indices,
+                              ref_knn_masks, src_knn_masks, ref_corr_indices, src_corr_indices, acceptance_radius=0.6,
+                              correspondence_threshold=3, num_refinement_steps=5):
+    """LocalGlobalRegistration.forward (local_global_registration.py:204-243) fused with the knn gathers of
+    experiments/model.py:323-329. Returns (ref_corr_points, src_corr_points, corr_scores, transform, corr_bij)."""
+    p, k1 = matching_scores.shape[0], matching_scores.shape[1]
+    k = k1 - 1
+    dev = matching_scores.device
+    cap = max(p * 2 * k, 1)
+    ref_c = torch.empty((cap, 3), dtype=torch.float32, device=dev)
+    src_c = torch.empty((cap, 3), dtype=torch.float32, device=dev)
+    sc = torch.empty(cap, dtype=torch.float32, device=dev)
+    bij = torch.empty((cap, 3), dtype=torch.int32, device=dev)
+    T = torch.empty((4, 4), dtype=torch.float32, device=dev)
+    meta = torch.empty(4, dtype=torch.int32, device=dev)
+    wsb = L.lib().rdm_lgr_workspace(p, k)
+    ws = _ws(wsb, dev)
+    L.call("rdm_lgr", L.ptr(matching_scores.contiguous()), p, k, L.ptr(ref_points_f), L.ptr(src_points_f),
+           L.ptr(ref_knn_indices), L.ptr(src_knn_indices), L.ptr(ref_knn_masks), L.ptr(src_knn_masks),
+           L.ptr(ref_corr_indices), L.ptr(src_corr_indices), acceptance_radius, correspondence_threshold,
+           num_refinement_steps, L.ptr(ref_c), L.ptr(src_c), L.ptr(sc), L.ptr(bij), L.ptr(T), L.ptr(meta), L.ptr(ws), wsb,
+           L.stream())
+    c = int(meta[0].item())  # the only host sync of the pose solver: the number of correspondences is the output shape
+    return ref_c[:c], src_c[:c], sc[:c], T, bij[:c]

@@ -90,7 +90,7 @@ def test_groupnorm_layernorm_pooling():
 
 
 def sub(g, prefix):
-    return {k[len(prefix):]: torch.from_numpy(v) for k, v in g.items() if k.startswith(prefix)}
+    return {k[len(prefix):]: torch.from_numpy(np.ascontiguousarray(v)) for k, v in g.items() if k.startswith(prefix)}
 
 
 def test_blocks_vs_reference_golden(golden_small):
@@ -109,9 +109,9 @@ def test_blocks_vs_reference_golden(golden_small):
     with torch.no_grad():
         x1 = cb(torch.ones(pts.shape[0], 1, device="cuda"), pts, pts, nb)
         close(x1, torch.from_numpy(g["cb_out"]))
-        x2 = rb(torch.from_numpy(g["cb_out"]).cuda(), pts, pts, nb)
+        x2 = rb(torch.from_numpy(np.ascontiguousarray(g["cb_out"])).cuda(), pts, pts, nb)
         close(x2, torch.from_numpy(g["rb_out"]))
-        x3 = rs(torch.from_numpy(g["rb_out"]).cuda(), p1, pts, sb)
+        x3 = rs(torch.from_numpy(np.ascontiguousarray(g["rb_out"])).cuda(), p1, pts, sb)
         close(x3, torch.from_numpy(g["rs_out"]))
         ub = M.UnaryBlock(40, 64, 32)
         ub.load_state_dict(sub(g, "ub."), strict=True)

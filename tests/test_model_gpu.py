@@ -1,0 +1,89 @@
+"""GPU parity of the whole hot path (pyramid build + RDMNet.forward) on the bundled pairs with the pretrained
+checkpoint: vs the REFERENCE's outputs (tests/golden/pair_outputs.npz) and, stage by stage, vs the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_oracle as MO
+from oracle import pyramid as OP
+
+pytestmark = pytest.mark.gpu
+
+
+def close(got, ref, tol=1e-4, what=""):
+    got = got.detach().cpu().double() if torch.is_tensor(got) else torch.as_tensor(got).double()
+    ref = ref.detach().cpu().double() if torch.is_tensor(ref) else torch.as_tensor(ref).double()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    err = (got - ref).abs().max().item()
+    assert err <= tol * max(1.0, ref.abs().max().item()), f"{what}: max abs err {err} (ref max {ref.abs().max().item()})"
+
+
+@pytest.fixture(scope="module")
+def model(pretrained_state):
+    from rdmnet_b200.model import create_model
+    m = create_model()
+    m.load_state_dict(pretrained_state, strict=True)  # the reference checkpoint loads with strict=True
+    return m.cuda().eval()
+
+
+def run_pair(model, scans, a, b):
+    pa, pb = scans[a], scans[b]
+    pts = torch.from_numpy(np.concatenate([pa, pb])).cuda()
+    lens = torch.tensor([len(pa), len(pb)], dtype=torch.int64).cuda()
+    return model({"points": pts, "lengths": lens})
+
+
+@pytest.mark.parametrize("tag,a,b", [("p04", "s000000", "s000004"), ("p07", "s000000", "s000007")])
+def test_forward_vs_reference_outputs(model, scans, golden_pairs, tag, a, b):
+    g = golden_pairs
+    out = run_pair(model, scans, a, b)
+    assert np.array_equal(out["mask"].cpu().numpy(), g[f"{tag}_nms"]), "NMS mask"
+    close(out["ref_points_c"], g[f"{tag}_ref_points_c"], 1e-4, "ref_points_c")
+    close(out["ref_feats_c"], g[f"{tag}_ref_feats_c"], 5e-4, "ref_feats_c")
+    close(out["src_feats_c"], g[f"{tag}_src_feats_c"], 5e-4, "src_feats_c")
+    assert np.array_equal(out["ref_node_corr_indices"].cpu().numpy(), g[f"{tag}_ref_node_corr_indices"])
+    assert np.array_equal(out["src_node_corr_indices"].cpu().numpy(), g[f"{tag}_src_node_corr_indices"])
+    assert np.array_equal(out["ref_corr_points"].cpu().numpy(), g[f"{tag}_ref_corr_points"]), "correspondence set"
+    assert np.array_equal(out["src_corr_points"].cpu().numpy(), g[f"{tag}_src_corr_points"]), "correspondence set"
+    close(out["corr_scores"], g[f"{tag}_corr_scores"], 2e-3, "corr_scores")
+    close(out["estimated_transform"], g[f"{tag}_estimated_transform"], 1e-4, "estimated_transform")
+
+
+def test_forward_stages_vs_oracle(model, scans, pretrained_state):
+    a, b = scans["s000000"], scans["s000004"]
+    pyr = OP.precompute_pyramid(np.concatenate([a, b]), [len(a), len(b)], 5, 0.3, 4.25 * 0.3, MO.DEFAULT_LIMITS, "port")
+    tp = MO.pyramid_to_torch(pyr)
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        ref = MO.forward(pretrained_state, tp,
+                         lambda p, l: OP.radius_search(p.numpy(), p.numpy(), l.numpy(), l.numpy(), 2.4, 81, "port"))
+    # same pyramid, int64 tables, fed through the drop-in data_dict path
+    dd = {k: [t.cuda() for t in v] for k, v in tp.items()}
+    dd["features"] = torch.ones(tp["points"][0].shape[0], 1).cuda()
+    out = model(dd)
+    feats = model.encoder(dd["features"], dd)
+    close(feats[-1], ref["feats_s5"], 2e-4, "encoder stage 5")
+    close(out["shifted_ref_points_c"], ref["shifted_points_c"][:431], 1e-4, "vote xyz")
+    assert np.array_equal(out["mask"].cpu().numpy(), ref["nms_masks"].numpy())
+    close(out["ref_feats_c"], ref["ref_feats_c"], 5e-4, "ref_feats_c")
+    close(out["ref_feats_f"], ref["feats_f"][:out["ref_feats_f"].shape[0]], 5e-4, "feats_f")
+    assert np.array_equal(out["ref_node_knn_indices"].cpu().numpy(), ref["ref_node_knn_indices"].numpy())
+    assert np.array_equal(out["ref_node_corr_indices"].cpu().numpy(), ref["ref_node_corr_indices"].numpy())
+    live = ref["matching_scores"].numpy() > -1e11
+    close(out["matching_scores"].cpu().numpy()[live], ref["matching_scores"].numpy()[live], 2e-3, "matching_scores")
+    assert np.array_equal(out["ref_corr_points"].cpu().numpy(), ref["ref_corr_points"].numpy())
+    close(out["estimated_transform"], ref["estimated_transform"], 1e-4, "estimated_transform")
+
+
+def test_gpu_pyramid_equals_reference_tables(scans):
+    """precompute_data_stack_mode on the GPU == the oracle's tables (all 13 + lengths), int64, reference widths."""
+    from rdmnet_b200.model import precompute_data_stack_mode
+    a, b = scans["s000000"], scans["s000007"]
+    lim = MO.DEFAULT_LIMITS
+    ref = OP.precompute_pyramid(np.concatenate([a, b]), [len(a), len(b)], 5, 0.3, 4.25 * 0.3, lim, "port")
+    got = precompute_data_stack_mode(torch.from_numpy(np.concatenate([a, b])).cuda(),
+                                     torch.tensor([len(a), len(b)]).cuda(), 5, 0.3, 4.25 * 0.3, lim)
+    for k in ("points", "lengths", "neighbors", "subsampling", "upsampling"):
+        for i, (x, y) in enumerate(zip(got[k], ref[k])):
+            assert np.array_equal(x.cpu().numpy(), y), f"{k}[{i}]"
+    assert got["lengths_host"][-1] == [431, 390]
