@@ -210,7 +210,9 @@ def point_to_node_partition(points, nodes, k):
     own = torch.zeros_like(d, dtype=torch.bool)
     own[p2n, torch.arange(points.shape[0])] = True
     d = d.masked_fill(~own, 1e12)
-    knn = d.topk(k, dim=1, largest=False)[1]
+    # the reference uses d.topk(k, largest=False) (:95); exact-distance ties come out of torch.topk in an
+    # implementation-defined order (CPU and CUDA differ), so the oracle fixes the canonical (d, index) order
+    knn = torch.sort(d, dim=1, stable=True)[1][:, :k]
     knn_masks = p2n[knn] == torch.arange(nodes.shape[0])[:, None]
     knn = knn.masked_fill(~knn_masks, points.shape[0])
     return p2n, node_masks, knn, knn_masks

@@ -1,0 +1,138 @@
+"""Synthetic KITTI-shaped scan pairs: there is no dataset on the GPU box.
+
+A procedural street scene (ground plane, axis-aligned boxes = buildings and cars, vertical cylinders = poles and
+trunks) is ray-cast from two sensor poses with an HDL-64-like pattern, range noise and ray dropout are added, and the
+returns are voxel-barycentre downsampled at 0.3 m - what preporcess/downsample_pcd_kitti.py:28 does offline for the
+reference. Pure numpy, seeded, deterministic: seed = 7351 + pair_id (experiments/config.py:13 is the reference seed).
+The second scan is the same scene seen from T_gt (yaw U(-10,10) deg, roll/pitch N(0,0.5 deg), 8-12 m forward), as KITTI
+pairs are >= 10 m apart (rdmnet/datasets/registration/kitti/dataset.py:106).
+"""
+import numpy as np
+
+SENSOR_HEIGHT = 1.73
+
+
+def _rot(yaw, pitch, roll):
+    cy, sy, cp, sp, cr, sr = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch), np.cos(roll), np.sin(roll)
+    rz = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]])
+    ry = np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]])
+    rx = np.array([[1, 0, 0], [0, cr, -sr], [0, sr, cr]])
+    return rz @ ry @ rx
+
+
+def make_scene(rng):
+    """Boxes (lo, hi), cylinders (cx, cy, r, z0, z1) and spheres (cx, cy, cz, r) in a 160 m x 100 m street corridor;
+    world frame = first sensor frame, ground at z = -1.73. Two rows of facades line the street, cars stand on it,
+    poles/trunks and tree crowns fill the verges - dense enough that the coarse pyramid levels see KITTI-like
+    neighbour counts."""
+    lo, hi = [], []
+    for side in (-1.0, 1.0):
+        for row, (y0lo, y0hi) in enumerate([(9.0, 14.0), (30.0, 38.0)]):
+            x = -80.0 + rng.uniform(0, 5)
+            while x < 80.0:
+                w, dep, hgt = rng.uniform(8, 20), rng.uniform(8, 15), rng.uniform(5, 15)
+                y0 = rng.uniform(y0lo, y0hi)
+                lo.append([x, min(side * y0, side * (y0 + dep)), -SENSOR_HEIGHT])
+                hi.append([x + w, max(side * y0, side * (y0 + dep)), -SENSOR_HEIGHT + hgt])
+                x += w + rng.uniform(0, 6) * (1 + row)
+    n_car = int(rng.integers(20, 41))
+    for _ in range(n_car):
+        cx, cy = rng.uniform(-78, 78), rng.choice([-1.0, 1.0]) * rng.uniform(2.5, 7.5)
+        if abs(cx) < 16 and abs(cy) < 4:  # keep both sensor poses clear
+            cy = 6.0 * np.sign(cy)
+        lo.append([cx - 2.0, cy - 0.9, -SENSOR_HEIGHT])
+        hi.append([cx + 2.0, cy + 0.9, -SENSOR_HEIGHT + 1.5])
+    cyl, sph = [], []
+    for i in range(70):
+        cx, cy = rng.uniform(-78, 78), rng.choice([-1.0, 1.0]) * rng.uniform(5.0, 8.5)
+        h = rng.uniform(3, 8)
+        cyl.append([cx, cy, rng.uniform(0.15, 0.4), -SENSOR_HEIGHT, -SENSOR_HEIGHT + h])
+        if i % 5 != 0:  # a crown on most trunks
+            sph.append([cx, cy, -SENSOR_HEIGHT + h, rng.uniform(1.5, 3.0)])
+    return np.array(lo), np.array(hi), np.array(cyl), np.array(sph)
+
+
+def ray_cast(origin, R, scene, n_elev, n_azim, rng, max_range=80.0, noise=0.02, dropout=0.1):
+    """Returns the hit points in the SENSOR frame (float64, (n,3))."""
+    lo, hi, cyl, sph = scene
+    el = np.deg2rad(np.linspace(-24.8, 2.0, n_elev))
+    az = np.linspace(-np.pi, np.pi, n_azim, endpoint=False)
+    ce, se = np.cos(el)[:, None], np.sin(el)[:, None]
+    d_s = np.stack([ce * np.cos(az)[None], ce * np.sin(az)[None], np.broadcast_to(se, (n_elev, n_azim))], -1).reshape(-1, 3)
+    d = d_s @ R.T  # world-frame directions
+    o = origin
+    t = np.full(d.shape[0], np.inf)
+    # ground plane z = -1.73 (world)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tg = (-SENSOR_HEIGHT - o[2]) / d[:, 2]
+    tg[~(tg > 0)] = np.inf
+    t = np.minimum(t, tg)
+    # boxes: slab test, chunked over boxes
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = 1.0 / d
+        for b in range(lo.shape[0]):
+            t0 = (lo[b] - o) * inv
+            t1 = (hi[b] - o) * inv
+            tn = np.minimum(t0, t1).max(1)
+            tf = np.maximum(t0, t1).min(1)
+            hit = (tf >= tn) & (tn > 0)
+            t = np.where(hit & (tn < t), tn, t)
+        # vertical cylinders
+        a = d[:, 0] ** 2 + d[:, 1] ** 2
+        for c in cyl:
+            ox, oy = o[0] - c[0], o[1] - c[1]
+            bq = ox * d[:, 0] + oy * d[:, 1]
+            cq = ox * ox + oy * oy - c[2] ** 2
+            disc = bq * bq - a * cq
+            tc = (-bq - np.sqrt(np.maximum(disc, 0))) / a
+            z = o[2] + tc * d[:, 2]
+            hit = (disc > 0) & (tc > 0) & (z >= c[3]) & (z <= c[4])
+            t = np.where(hit & (tc < t), tc, t)
+        # tree crowns (spheres)
+        for c in sph:
+            oc = o - c[:3]
+            bq = d @ oc
+            disc = bq * bq - (oc @ oc - c[3] ** 2)
+            tc = -bq - np.sqrt(np.maximum(disc, 0))
+            hit = (disc > 0) & (tc > 0)
+            t = np.where(hit & (tc < t), tc, t)
+    keep = np.isfinite(t) & (t < max_range) & (rng.random(t.shape[0]) >= dropout)
+    t = t + rng.normal(0.0, noise, t.shape[0])
+    pts = d_s[keep] * t[keep, None]  # sensor frame
+    pts[:, 2] += rng.normal(0.0, 0.03, pts.shape[0]) * (np.abs(pts[:, 2] + SENSOR_HEIGHT) < 0.2)  # ground roughness
+    return pts
+
+
+def voxel_downsample(points, voxel):
+    """Voxel-barycentre downsample (what open3d.voxel_down_sample computes), output ordered by voxel key."""
+    key = np.floor(points / voxel).astype(np.int64)
+    key -= key.min(0)
+    dims = key.max(0) + 1
+    flat = (key[:, 0] * dims[1] + key[:, 1]) * dims[2] + key[:, 2]
+    uniq, inv = np.unique(flat, return_inverse=True)
+    cnt = np.bincount(inv, minlength=uniq.shape[0]).astype(np.float64)
+    out = np.stack([np.bincount(inv, weights=points[:, a], minlength=uniq.shape[0]) / cnt for a in range(3)], 1)
+    return out
+
+
+def make_pair(pair_id=0, n_elev=64, n_azim=2000, voxel=0.3):
+    """-> dict(ref_points (Nr,3) f32, src_points (Ns,3) f32, transform (4,4) f32 with ref = T * src)."""
+    rng = np.random.default_rng(7351 + pair_id)
+    scene = make_scene(rng)
+    ref = ray_cast(np.zeros(3), np.eye(3), scene, n_elev, n_azim, rng)
+    yaw = np.deg2rad(rng.uniform(-10, 10))
+    pitch, roll = np.deg2rad(rng.normal(0, 0.5, 2))
+    R = _rot(yaw, pitch, roll)
+    tr = np.array([rng.uniform(8, 12), rng.normal(0, 0.5), 0.0])
+    src = ray_cast(tr, R, scene, n_elev, n_azim, rng)
+    T = np.eye(4)
+    T[:3, :3], T[:3, 3] = R, tr  # world(ref) = R * src + tr
+    rng2 = np.random.default_rng(99991 + pair_id)
+    ref_d, src_d = voxel_downsample(ref, voxel), voxel_downsample(src, voxel)
+    ref_d = ref_d[rng2.permutation(ref_d.shape[0])]  # sensor files are not voxel-sorted
+    src_d = src_d[rng2.permutation(src_d.shape[0])]
+    return {"ref_points": ref_d.astype(np.float32), "src_points": src_d.astype(np.float32), "transform": T.astype(np.float32)}
+
+
+# config 5 size classes: target post-voxel points per scan -> (n_elev, n_azim)
+SIZE_CLASSES = {"4k": (32, 500), "8k": (64, 1000), "16k": (64, 2000), "32k": (128, 4000)}

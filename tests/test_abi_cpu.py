@@ -1,0 +1,70 @@
+"""CPU tests of the drop-in boundary: librdm_sm100.so loads without a GPU and exports every symbol that
+include/rdm_sm100.h declares; the ctypes table of rdmnet_b200/_lib.py covers exactly those symbols; the host shim
+fails loudly (RuntimeError, the reference extension's error convention) instead of falling back to a CPU path."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "rdm_sm100.h")
+
+
+def header_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rdm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_symbols():
+    syms = header_symbols()
+    assert "rdm_grid_subsample" in syms and "rdm_radius_search" in syms and "rdm_kpconv_gather" in syms
+    assert len(syms) >= 25
+
+
+def test_library_exports_every_header_symbol():
+    from rdmnet_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "librdm_sm100.so not built (python __graft_entry__.py)"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [s for s in header_symbols() if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_ctypes_table_matches_header():
+    from rdmnet_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == header_symbols()
+    # argument counts agree with the C prototypes
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for name, (_, args) in _lib.SIGNATURES.items():
+        m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", src, flags=re.S)
+        assert m, name
+        params = m.group(1).strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(args), (name, n, len(args))
+
+
+def test_host_calls_without_gpu_are_safe():
+    from rdmnet_b200 import _lib
+    lib = _lib.lib()
+    assert lib.rdm_version() >= 100
+    assert lib.rdm_grid_subsample_workspace(1000, 2) > 0
+    assert lib.rdm_radius_search_workspace(1000, 2) > 0
+    assert lib.rdm_selfcheck_bucket_table(50000) == 0  # embedded libstdc++ bucket table == this process' unordered_map
+    # argument validation happens before any CUDA call
+    rc = lib.rdm_maxpool(None, None, 3, 1, 1, 1, 4, None, None)
+    assert rc == 1 and b"index_bytes" in lib.rdm_last_error()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from rdmnet_b200 import ops
+    pts = torch.rand(100, 3)
+    lens = torch.tensor([60, 40])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.grid_subsample(pts, lens, 0.1)
+    with pytest.raises(RuntimeError):
+        ops.radius_search(pts, pts, lens, lens, 0.2, 8)
+    with pytest.raises(RuntimeError, match="float32"):  # dtype preconditions of torch_helper.h:6-35
+        ops.grid_subsample(pts.double(), lens, 0.1)

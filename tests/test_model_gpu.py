@@ -18,6 +18,20 @@ def close(got, ref, tol=1e-4, what=""):
     assert err <= tol * max(1.0, ref.abs().max().item()), f"{what}: max abs err {err} (ref max {ref.abs().max().item()})"
 
 
+def assert_node_corr_equal(ri, si, sc, ref_ri, ref_si, rel=2e-6):
+    """Coarse correspondences must be the same (ref, src) node pairs in the same order; positions may differ only
+    inside runs whose dual-normalised scores agree to `rel` (fp32 near-ties of the flat top-k, SURVEY A.5: the
+    reference's own CPU and CUDA paths order those differently). Returns True when the order is identical."""
+    assert ri.shape == ref_ri.shape
+    assert sorted(zip(ri.tolist(), si.tolist())) == sorted(zip(ref_ri.tolist(), ref_si.tolist())), "node pair set"
+    diff = np.nonzero((ri != ref_ri) | (si != ref_si))[0]
+    pos = {p: i for i, p in enumerate(zip(ri.tolist(), si.tolist()))}
+    for i in diff:
+        j = pos[(int(ref_ri[i]), int(ref_si[i]))]
+        assert abs(sc[i] - sc[j]) <= rel * abs(sc[i]), f"order differs outside a near-tie: {i} vs {j}: {sc[i]} {sc[j]}"
+    return diff.size == 0
+
+
 @pytest.fixture(scope="module")
 def model(pretrained_state):
     from rdmnet_b200.model import create_model
@@ -41,11 +55,17 @@ def test_forward_vs_reference_outputs(model, scans, golden_pairs, tag, a, b):
     close(out["ref_points_c"], g[f"{tag}_ref_points_c"], 1e-4, "ref_points_c")
     close(out["ref_feats_c"], g[f"{tag}_ref_feats_c"], 5e-4, "ref_feats_c")
     close(out["src_feats_c"], g[f"{tag}_src_feats_c"], 5e-4, "src_feats_c")
-    assert np.array_equal(out["ref_node_corr_indices"].cpu().numpy(), g[f"{tag}_ref_node_corr_indices"])
-    assert np.array_equal(out["src_node_corr_indices"].cpu().numpy(), g[f"{tag}_src_node_corr_indices"])
-    assert np.array_equal(out["ref_corr_points"].cpu().numpy(), g[f"{tag}_ref_corr_points"]), "correspondence set"
-    assert np.array_equal(out["src_corr_points"].cpu().numpy(), g[f"{tag}_src_corr_points"]), "correspondence set"
-    close(out["corr_scores"], g[f"{tag}_corr_scores"], 2e-3, "corr_scores")
+    same_order = assert_node_corr_equal(out["ref_node_corr_indices"].cpu().numpy(), out["src_node_corr_indices"].cpu().numpy(),
+                                        out["node_corr_scores"].cpu().numpy(), g[f"{tag}_ref_node_corr_indices"],
+                                        g[f"{tag}_src_node_corr_indices"])
+    got_c = np.concatenate([out["ref_corr_points"].cpu().numpy(), out["src_corr_points"].cpu().numpy()], 1)
+    ref_c = np.concatenate([g[f"{tag}_ref_corr_points"], g[f"{tag}_src_corr_points"]], 1)
+    got_s, ref_s = out["corr_scores"].cpu().numpy(), g[f"{tag}_corr_scores"]
+    if not same_order:  # patches swapped inside a score near-tie: same correspondences, listed in another patch order
+        go, ro = np.lexsort(got_c.T[::-1]), np.lexsort(ref_c.T[::-1])
+        got_c, ref_c, got_s, ref_s = got_c[go], ref_c[ro], got_s[go], ref_s[ro]
+    assert np.array_equal(got_c, ref_c), "correspondence set (bit-exact points)"
+    close(got_s, ref_s, 2e-3, "corr_scores")
     close(out["estimated_transform"], g[f"{tag}_estimated_transform"], 1e-4, "estimated_transform")
 
 
@@ -68,6 +88,7 @@ def test_forward_stages_vs_oracle(model, scans, pretrained_state):
     close(out["ref_feats_c"], ref["ref_feats_c"], 5e-4, "ref_feats_c")
     close(out["ref_feats_f"], ref["feats_f"][:out["ref_feats_f"].shape[0]], 5e-4, "feats_f")
     assert np.array_equal(out["ref_node_knn_indices"].cpu().numpy(), ref["ref_node_knn_indices"].numpy())
+    assert np.array_equal(out["src_node_knn_indices"].cpu().numpy(), ref["src_node_knn_indices"].numpy())
     assert np.array_equal(out["ref_node_corr_indices"].cpu().numpy(), ref["ref_node_corr_indices"].numpy())
     live = ref["matching_scores"].numpy() > -1e11
     close(out["matching_scores"].cpu().numpy()[live], ref["matching_scores"].numpy()[live], 2e-3, "matching_scores")
