@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Benchmark of the RDMNet dense-matching hot path (BASELINE.json: scan-pairs/s on the infer.py path).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one scan pair through the whole path: GPU pyramid build (4x grid_subsample + 12 radius searches) +
+RDMNet.forward (KPConv encoder/decoder, 2x ThDRoFormer, vote + NMS, partition, coarse matching, Sinkhorn, LGR pose).
+Workload = BASELINE.json configs[1]: synthetic KITTI pair (~16k points per scan after the 0.3 m downsample, SURVEY.md
+8(d) config 2), forward only, fp32. One process per GPU; pairs shard across ranks with no collective on the data path
+(weak scaling: every rank runs K steps). Prints ONE JSON line on rank 0.
+
+  value    pairs/s with the raw points already resident in HBM (CUDA events around each step, L2 flushed between
+           steps, max over ranks)
+  e2e      pairs/s through the host-buffer API (rdmnet_b200.api.PairRegistrar): pinned host points -> H2D -> path ->
+           D2H of pose + correspondences, inside the timed region
+  roofline KPConv neighbour-gather kernel: algorithmic bytes / CUDA-event time of its launches inside
+           the timed steps, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the CPU oracle of the same path (reference C++ core for the pyramid when oracle/_ref was built, torch
+           fp32 restatement of the model) on the host cores, bounded sample
+--impl reference times that CPU path alone (the reference ships no GPU kernels of its own: SURVEY 2.2).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "scan_pairs_per_sec_infer_path"
+UNIT = "pairs/s"
+WORKLOAD = "synthetic KITTI pair (~16k pts/scan after 0.3 m voxel downsample), infer.py path, forward-only"
+LIMITS = [65, 63, 69, 70, 81]
+CKPT = os.path.join(ROOT, "tests", "golden", "_big", "rdmnet_state.pt")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=4, help="distinct synthetic pairs per rank (cycled)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-pairs", type=int, default=3, help="pairs in the bounded cpu_baseline sample")
+    return ap.parse_args()
+
+
+def make_pairs(n, rank):
+    from rdmnet_b200 import synthetic
+    return [synthetic.make_pair(pair_id=rank * 1000 + i) for i in range(n)]
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def load_state():
+    import torch
+    if os.path.exists(CKPT):
+        return torch.load(CKPT, map_location="cpu", weights_only=True), "pretrained reference checkpoint"
+    from rdmnet_b200.model import create_model
+    torch.manual_seed(7351)
+    return {k: v.detach().clone() for k, v in create_model().state_dict().items()}, "random-init weights (seed 7351)"
+
+
+def cpu_reference_pair(state, pair, impl):
+    """The reference's CPU path for one pair: registration_collate_fn_stack_mode (C++ ext) + RDMNet.forward (torch CPU),
+    restated by oracle/ (checker code; this is the one place outside tests/ allowed to execute it)."""
+    import torch
+    from oracle import model_oracle as MO
+    from oracle import pyramid as OP
+    pts = np.concatenate([pair["ref_points"], pair["src_points"]])
+    lens = [len(pair["ref_points"]), len(pair["src_points"])]
+    pyr = OP.precompute_pyramid(pts, lens, 5, 0.3, 4.25 * 0.3, LIMITS, impl)
+    tp = MO.pyramid_to_torch(pyr)
+    with torch.no_grad():
+        out = MO.forward(state, tp, lambda p, l: OP.radius_search(p.numpy(), p.numpy(), l.numpy(), l.numpy(), 2.4,
+                                                                  LIMITS[-1], impl))
+    return out["estimated_transform"]
+
+
+def cpu_arm(pairs, n_steps, n_warm, budget_s):
+    import torch
+    from oracle import pyramid as OP
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(cores)
+    impl = "ref" if OP.ref_available() else "port"
+    state, wdesc = load_state()
+    for i in range(n_warm):
+        cpu_reference_pair(state, pairs[i % len(pairs)], impl)
+    t0, done = time.perf_counter(), 0
+    for i in range(n_steps):
+        cpu_reference_pair(state, pairs[i % len(pairs)], impl)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    kind = "port"  # the model half (the dominant share) is the restatement; only the pyramid can run the real C++ core
+    sample = (f"{done} pair(s) of the workload after {n_warm} warm-up; pyramid = "
+              f"{'reference C++ core (oracle/_ref), 1 thread as in a DataLoader worker' if impl == 'ref' else 'C restatement'}"
+              f"; model forward = torch-CPU fp32 restatement of experiments/model_infer.py on {cores} threads; {wdesc}")
+    return {"value": done / dt, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}, done, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    pairs = make_pairs(min(args.pairs, 2), 0)
+    cb, done, dt = cpu_arm(pairs, args.steps, min(args.warmup, 1), budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / max(done, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "neighbor_limits": LIMITS, "pairs_per_step": 1,
+                       "note": "CPU path of the reference (it ships no GPU kernels); rank 0 only"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from rdmnet_b200 import _lib as L
+    from rdmnet_b200.api import PairRegistrar
+    from rdmnet_b200.model import create_model
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: rdmnet_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    L.lib()  # fail loudly if librdm_sm100.so is missing
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    pairs = make_pairs(args.pairs, rank)
+    model = create_model()
+    if os.path.exists(CKPT):
+        model.load_state_dict(torch.load(CKPT, map_location="cpu", weights_only=True), strict=True)
+        wdesc = "pretrained reference checkpoint"
+    else:
+        torch.manual_seed(7351)
+        wdesc = "random-init weights (seed 7351)"
+    model = model.to(dev).eval()
+
+    d_pairs = []
+    for p in pairs:
+        pts = torch.from_numpy(np.concatenate([p["ref_points"], p["src_points"]])).to(dev)
+        lens = torch.tensor([len(p["ref_points"]), len(p["src_points"])], dtype=torch.int64, device=dev)
+        d_pairs.append((pts, lens))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(i):
+        pts, lens = d_pairs[i % len(d_pairs)]
+        return model({"points": pts, "lengths": lens})
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+
+    # ---- timed region 1: device-resident inputs; per-step CUDA events, L2 flush (untimed) between steps
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    L.TIMER = L.KernelTimer()
+    launches0 = L.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    rre_ok = 0
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        ev[i][0].record()
+        out = step(i)
+        ev[i][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = L.launch_count() - launches0
+    timer, L.TIMER = L.TIMER, None
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    clk = clocks.stop()
+
+    # ---- timed region 2: end to end through the host-buffer API (pinned H2D of the points, D2H of the results)
+    reg = PairRegistrar(model, max_points=max(p[0].shape[0] for p in d_pairs), device=dev)
+    for i in range(min(args.warmup, 3)):
+        reg.register(pairs[i % len(pairs)]["ref_points"], pairs[i % len(pairs)]["src_points"])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        res = reg.register(pairs[i % len(pairs)]["ref_points"], pairs[i % len(pairs)]["src_points"])
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # max over ranks
+    tm = torch.tensor([total_ms, e2e_s * 1e3, t_wall * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, wall_ms = tm.tolist()
+
+    # pose sanity on the last pair (synthetic ground truth): not part of the metric, reported for context
+    T = res["estimated_transform"]
+    Tg = pairs[(args.steps - 1) % len(pairs)]["transform"]
+    rre = float(np.degrees(np.arccos(np.clip((np.trace(T[:3, :3].T @ Tg[:3, :3]) - 1) / 2, -1, 1))))
+    rte = float(np.linalg.norm(T[:3, 3] - Tg[:3, 3]))
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        ks = timer.summary()
+        g = ks.get("kpconv_gather", {"launches": 0, "ms": 0.0, "bytes": 0})
+        w = ks.get("kpconv_weight_gemm", {"launches": 0, "ms": 0.0, "bytes": 0})
+        ach = (g["bytes"] / 1e9) / (g["ms"] / 1e3) if g["ms"] > 0 else 0.0
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "kpconv_gather_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        per_layer = {}
+        for tag, e0, e1, nb, meta in timer.records:
+            if tag == "kpconv_gather":
+                d = per_layer.setdefault("M%d_H%d_C%d" % (meta[0], meta[2], meta[3]), [0.0, 0, 0])
+                d[0] += e0.elapsed_time(e1); d[1] += nb; d[2] += 1
+        line = {
+            "metric": METRIC, "value": world * args.steps / (total_ms / 1e3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_step": 1, "distinct_pairs_per_rank": len(pairs),
+                       "points_per_pair": [int(p[0].shape[0]) for p in d_pairs], "neighbor_limits": LIMITS,
+                       "weights": wdesc, "l2": "256 MiB flush write between timed steps (untimed)",
+                       "timing": "CUDA events per step on the launch stream, summed; max over ranks",
+                       "sharding": "pairs round-robin over ranks, no data-path collective"},
+            "wall_ms_per_step_incl_flush": wall_ms / args.steps,
+            "e2e": {"value": world * args.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": reg.h2d_bytes,
+                    "d2h_bytes_per_step": reg.d2h_bytes, "ms_per_step": e2e_ms / args.steps,
+                    "api": "rdmnet_b200.api.PairRegistrar.register (host numpy in, host numpy out)"},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "kpconv_gather_kernel (+row_positive prepass), 14 launches/step", "bound": "hbm",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                         "peak_source": peak_src, "launches": g["launches"],
+                         "avg_launch_us": 1e3 * g["ms"] / max(g["launches"], 1),
+                         "algorithmic_bytes_per_launch": g["bytes"] / max(g["launches"], 1),
+                         "definition": "G = M*H*(C_in*4+12+4) + M*(C_out*4+12) per launch (SURVEY 8(d), fp32, int32 idx)",
+                         "kpconv_weight_gemm_ms_per_step": w["ms"] / args.steps,
+                         "kpconv_gather_ms_per_step": g["ms"] / args.steps,
+                         "per_layer_GBps": {k: (v[1] / 1e9) / (v[0] / 1e3) for k, v in per_layer.items() if v[0] > 0}},
+            "clocks": clk,
+            "pose_check": {"rre_deg": rre, "rte_m": rte, "n_corr": int(res["corr_scores"].shape[0])},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _, _ = cpu_arm(pairs, args.cpu_pairs, 1, budget_s=60.0)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -32,6 +32,8 @@ typedef void* rdm_stream_t;
 
 const char* rdm_last_error(void);
 int rdm_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py reports the delta as gpu_launches) */
+unsigned long long rdm_launch_count(void);
 
 /* ---- rdmnet.ext.grid_subsampling (geotransformer/extensions/cpu/grid_subsampling/grid_subsampling.cpp:5-62,
  *      core grid_subsampling_cpu.cpp:3-75; Python wrapper geotransformer/modules/ops/grid_subsample.py:7-22).

@@ -14,6 +14,7 @@ c_void_p, c_int, c_i64, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctype
 SIGNATURES = {
     "rdm_last_error": (ctypes.c_char_p, []),
     "rdm_version": (c_int, []),
+    "rdm_launch_count": (ctypes.c_ulonglong, []),
     "rdm_grid_subsample_workspace": (c_size_t, [c_i64, c_int]),
     "rdm_grid_subsample": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "rdm_selfcheck_bucket_table": (c_int, [c_i64]),
@@ -90,3 +91,38 @@ def check(code, what):
 
 def call(name, *args):
     check(getattr(lib(), name)(*args), name)
+
+
+class KernelTimer:
+    """Optional CUDA-event timer around selected C-ABI calls (bench.py: live roofline of the KPConv gather kernel).
+    Events are recorded on torch's current stream, which is the stream every kernel of the library is launched on."""
+
+    def __init__(self):
+        self.records = []  # (tag, start_event, stop_event, algorithmic_bytes, meta)
+
+    def start(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def stop(self, tag, e0, nbytes, meta=None):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.records.append((tag, e0, e1, nbytes, meta))
+
+    def summary(self):
+        """-> {tag: {"launches", "ms", "bytes"}} (call after a synchronize)."""
+        out = {}
+        for tag, e0, e1, nb, _ in self.records:
+            d = out.setdefault(tag, {"launches": 0, "ms": 0.0, "bytes": 0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["bytes"] += nb
+        return out
+
+
+TIMER = None  # set to a KernelTimer to enable
+
+
+def launch_count():
+    return int(lib().rdm_launch_count())

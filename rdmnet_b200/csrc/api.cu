@@ -13,4 +13,7 @@ void rdm_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* rdm_last_error(void) { return g_err; }
-extern "C" int rdm_version(void) { return 100; }
+extern "C" int rdm_version(void) { return 101; }
+
+unsigned long long g_rdm_launches = 0;
+extern "C" unsigned long long rdm_launch_count(void) { return __atomic_load_n(&g_rdm_launches, __ATOMIC_RELAXED); }

@@ -28,7 +28,13 @@ void rdm_set_error(const char* fmt, ...);
     }                                                                                       \
   } while (0)
 
-#define RDM_LAUNCH_CHECK() RDM_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this macro: it also feeds rdm_launch_count()
+extern unsigned long long g_rdm_launches;
+#define RDM_LAUNCH_CHECK()                                      \
+  do {                                                          \
+    __atomic_fetch_add(&g_rdm_launches, 1ull, __ATOMIC_RELAXED); \
+    RDM_CUDA(cudaGetLastError());                               \
+  } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -18,9 +18,10 @@ def close(got, ref, tol=1e-4, what=""):
     assert err <= tol * max(1.0, ref.abs().max().item()), f"{what}: max abs err {err} (ref max {ref.abs().max().item()})"
 
 
-def assert_node_corr_equal(ri, si, sc, ref_ri, ref_si, rel=2e-6):
+def assert_node_corr_equal(ri, si, sc, ref_ri, ref_si, rel=2e-5):
     """Coarse correspondences must be the same (ref, src) node pairs in the same order; positions may differ only
-    inside runs whose dual-normalised scores agree to `rel` (fp32 near-ties of the flat top-k, SURVEY A.5: the
+    inside runs whose dual-normalised scores agree to `rel` (near-ties of the flat top-k on features that are
+    themselves only equal to ~1e-6; SURVEY A.5: the
     reference's own CPU and CUDA paths order those differently). Returns True when the order is identical."""
     assert ri.shape == ref_ri.shape
     assert sorted(zip(ri.tolist(), si.tolist())) == sorted(zip(ref_ri.tolist(), ref_si.tolist())), "node pair set"
@@ -87,11 +88,34 @@ def test_forward_stages_vs_oracle(model, scans, pretrained_state):
     assert np.array_equal(out["mask"].cpu().numpy(), ref["nms_masks"].numpy())
     close(out["ref_feats_c"], ref["ref_feats_c"], 5e-4, "ref_feats_c")
     close(out["ref_feats_f"], ref["feats_f"][:out["ref_feats_f"].shape[0]], 5e-4, "feats_f")
-    assert np.array_equal(out["ref_node_knn_indices"].cpu().numpy(), ref["ref_node_knn_indices"].numpy())
-    assert np.array_equal(out["src_node_knn_indices"].cpu().numpy(), ref["src_node_knn_indices"].numpy())
+    # knn tables: the node coordinates fed to the partition are GPU-computed (vote MLP, equal to ~1e-6), so squared
+    # distances that tie EXACTLY in the oracle may differ by an ulp here: rows must hold the same point sets, and
+    # positions may differ only inside runs of oracle distances that agree to 1e-5 relative
+    perms = {}
+    for side, npts in (("ref", out["ref_points_f"].shape[0]), ("src", out["src_points_f"].shape[0])):
+        got_k, ref_k = out[f"{side}_node_knn_indices"].cpu().numpy(), ref[f"{side}_node_knn_indices"].numpy()
+        nodes, pts = ref[f"{side}_points_c"], out[f"{side}_points_f"].cpu()
+        assert np.array_equal(np.sort(got_k, 1), np.sort(ref_k, 1)), f"{side} knn point sets"
+        perm = np.tile(np.arange(got_k.shape[1]), (got_k.shape[0], 1))  # perm[n, i] = column of got holding ref_k[n, i]
+        for n, i in np.argwhere(got_k != ref_k):
+            j = int(np.nonzero(got_k[n] == ref_k[n, i])[0][0])
+            di = MO.pairwise_distance(nodes[n:n + 1], pts[ref_k[n, i]][None])[0, 0].item()
+            dj = MO.pairwise_distance(nodes[n:n + 1], pts[ref_k[n, j]][None])[0, 0].item()
+            assert abs(di - dj) <= 1e-5 * di, f"{side} knn order differs outside a near-tie: node {n} cols {i},{j}"
+            perm[n, i] = j
+        perms[side] = perm
     assert np.array_equal(out["ref_node_corr_indices"].cpu().numpy(), ref["ref_node_corr_indices"].numpy())
+    assert np.array_equal(out["src_node_corr_indices"].cpu().numpy(), ref["src_node_corr_indices"].numpy())
+    # matching scores, after undoing those column swaps patch by patch
+    ms = out["matching_scores"].cpu().numpy().copy()
+    rci, sci = ref["ref_node_corr_indices"].numpy(), ref["src_node_corr_indices"].numpy()
+    K = ms.shape[1] - 1
+    for b in range(ms.shape[0]):
+        pr = np.concatenate([perms["ref"][rci[b]], [K]])
+        pc = np.concatenate([perms["src"][sci[b]], [K]])
+        ms[b] = ms[b][pr][:, pc]
     live = ref["matching_scores"].numpy() > -1e11
-    close(out["matching_scores"].cpu().numpy()[live], ref["matching_scores"].numpy()[live], 2e-3, "matching_scores")
+    close(ms[live], ref["matching_scores"].numpy()[live], 2e-3, "matching_scores")
     assert np.array_equal(out["ref_corr_points"].cpu().numpy(), ref["ref_corr_points"].numpy())
     close(out["estimated_transform"], ref["estimated_transform"], 1e-4, "estimated_transform")
 
