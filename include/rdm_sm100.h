@@ -62,9 +62,10 @@ int rdm_radius_search(const float* q_points, const float* s_points, const int64_
 /* ---- KPConv.forward, gather half (geotransformer/modules/kpconv/kpconv.py:79-116):
  * out_weighted [M, 15*C_in] = (1/neighbor_num) * sum_h influence[m,h,k] * s_feats[idx[m,h], c]; follow with
  * rdm_linear(out_weighted, W.view(15*C_in, C_out), b_is_nk = 0, bias) to finish :105-120.
- * rowpos_scratch: N bytes. */
+ * kernel_points [15,3] on the device and h_kernel_points = the same 45 floats in HOST memory (a module constant;
+ * the kernel takes them by value in its parameter bank). rowpos_scratch: N bytes. */
 int rdm_kpconv_gather(const float* s_feats, const float* q_points, const float* s_points, const void* neighbor_indices,
-                      int index_bytes, const float* kernel_points, float sigma, int M, int N, int H, int C_in,
+                      int index_bytes, const float* kernel_points, const float* h_kernel_points, float sigma, int M, int N, int H, int C_in,
                       float* out_weighted, unsigned char* rowpos_scratch, rdm_stream_t stream);
 
 /* ---- maxpool (geotransformer/modules/kpconv/functional.py:54-67) */
@@ -105,6 +106,37 @@ int rdm_rope(const float* x, int ldx, const float* emb, int lde, float* y, int l
  * O[n, h*D:(h+1)*D] = softmax_j(Q_n.K_j / sqrt(D)) V, heads laid out along the channel axis, D <= 64. */
 int rdm_attention(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, float* O, int ldo, int Nq,
                   int Nk, int heads, int head_dim, rdm_stream_t stream);
+
+/* ---- fused ThDRoFormer layers for d_model = 128, 4 heads x 32, FFN 256 (the RDMNet configuration):
+ * TransformerLayer / RPETransformerLayer = MultiHeadAttention (+RoPE) + AttentionLayer + AttentionOutput
+ * (rdmnet/thdroformer/thdroformer.py:88-202, transformer/vanilla_transformer.py:15-129, transformer/output_layer.py:6-21).
+ * Job arrays live in HOST memory (they are copied into the kernel parameters); all pointers inside are device pointers.
+ * rdm_tf_project: y[n,128] = rope?(x[n,:128] * W^T + bias) per job; wt is the TRANSPOSED weight ([in][out]); emb != NULL
+ *   applies the 3-D rotary embedding with angles 2*pi*sigmoid(emb[n, c/2]) (emb row stride lde). Up to 6 jobs / launch.
+ * rdm_tf_attend: out[nq,128] = LN2(x1 + FFN(x1)), x1 = LN1(x + Wo*softmax(q k^T / sqrt(32)) v + bo); q already holds
+ *   the projected (and rotated) queries, k / v the projected keys / values; blob = rdm_tf_layer_blob_floats() floats:
+ *   WqT WkT WvT WoT [128x128 each, k-major], W1T [128x256], W2T [256x128], bq bk bv bo [128], b1 [256], b2 [128],
+ *   ln1.weight ln1.bias ln2.weight ln2.bias [128 each]. Up to 2 jobs / launch. */
+typedef struct {
+  const float* x;    /* [n, ldx] input rows (first 128 columns used) */
+  const float* wt;   /* [128,128] transposed weight */
+  const float* bias; /* [128] */
+  const float* emb;  /* [n, lde] or NULL */
+  float* y;          /* [n,128] row-major, or, if ldy_t != 0, channel-major [128, ldy_t] (key layout of rdm_tf_attend) */
+  int n, ldx, lde, ldy_t;
+} rdm_tf_proj_job;
+typedef struct {
+  const float* q;    /* [nq,128] */
+  const float* k;    /* [128, ldk_t] channel-major, ldk_t >= nk, ldk_t % 4 == 0, 16-byte aligned */
+  const float* v;    /* [nk,128] */
+  const float* x;    /* [nq, ldx] layer input (residual) */
+  const float* blob; /* layer blob */
+  float* out;        /* [nq,128] */
+  int nq, nk, ldx, ldk_t;
+} rdm_tf_attn_job;
+size_t rdm_tf_layer_blob_floats(void);
+int rdm_tf_project(const rdm_tf_proj_job* h_jobs, int num_jobs, rdm_stream_t stream);
+int rdm_tf_attend(const rdm_tf_attn_job* h_jobs, int num_jobs, rdm_stream_t stream);
 
 /* ---- NMS.forward greedy loop (rdmnet/vote/vote.py:33-40) over a radius-search table [N,H] (H <= 128). */
 int rdm_nms(const void* neighbor_indices, int index_bytes, int N, int H, unsigned char* out_mask, rdm_stream_t stream);

@@ -21,7 +21,7 @@ SIGNATURES = {
     "rdm_radius_search_workspace": (c_size_t, [c_i64, c_int]),
     "rdm_radius_search": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_float, c_int,
                                   c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "rdm_kpconv_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_float, c_int, c_int, c_int,
+    "rdm_kpconv_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_int,
                                   c_int, c_void_p, c_void_p, c_void_p]),
     "rdm_maxpool": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "rdm_upsample_concat": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -35,6 +35,9 @@ SIGNATURES = {
     "rdm_rope": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rdm_attention": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                               c_void_p]),
+    "rdm_tf_layer_blob_floats": (c_size_t, []),
+    "rdm_tf_project": (c_int, [c_void_p, c_int, c_void_p]),
+    "rdm_tf_attend": (c_int, [c_void_p, c_int, c_void_p]),
     "rdm_nms": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "rdm_point_to_node_workspace": (c_size_t, [c_int, c_int]),
     "rdm_point_to_node": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -51,6 +54,16 @@ SIGNATURES = {
                         c_void_p, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                         c_void_p, c_size_t, c_void_p]),
 }
+
+
+class TfProjJob(ctypes.Structure):
+    _fields_ = [("x", c_void_p), ("wt", c_void_p), ("bias", c_void_p), ("emb", c_void_p), ("y", c_void_p),
+                ("n", c_int), ("ldx", c_int), ("lde", c_int), ("ldy_t", c_int)]
+
+
+class TfAttnJob(ctypes.Structure):
+    _fields_ = [("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("x", c_void_p), ("blob", c_void_p), ("out", c_void_p),
+                ("nq", c_int), ("nk", c_int), ("ldx", c_int), ("ldk_t", c_int)]
 
 
 def lib():

@@ -8,6 +8,7 @@
 // with w = max(0, 1 - |s[idx] - q - kp_k| / sigma) and cnt_m = max(1, #{h : sum_c F[idx[m,h], c] > 0}).
 // The (M,H,K,3) / (M,H,C) temporaries the reference materialises in HBM never exist; per CTA the 15 influences of
 // each neighbour are computed once into shared memory and re-used by all channel slices.
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/rdm_sm100.h"
 
@@ -23,44 +24,67 @@ __global__ void row_positive_kernel(const float* __restrict__ f, int n, int c, u
   if (lane == 0) flag[row] = s > 0.f ? 1 : 0;
 }
 
-// C_in == 1 (encoder1_1): one warp per query, lanes over neighbours.
+struct KPts {
+  float x[KP_K], y[KP_K], z[KP_K];
+};
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// C_in == 1 (encoder1_1): 8 lanes per query (4 queries per warp), lanes stride over the neighbour list; the 15
+// kernel points come by value in the constant bank; 3 shuffle rounds reduce the 15 partial sums of a query.
 template <typename IdxT>
 __global__ void __launch_bounds__(256) kpconv_gather_c1_kernel(const float* __restrict__ feats,
                                                                const float* __restrict__ q_pts,
                                                                const float* __restrict__ s_pts,
-                                                               const IdxT* __restrict__ idx,
-                                                               const float* __restrict__ kpts, float sigma, int M, int N,
-                                                               int H, float* __restrict__ out) {
-  __shared__ float s_kp[KP_K * 3];
-  if (threadIdx.x < KP_K * 3) s_kp[threadIdx.x] = kpts[threadIdx.x];
-  __syncthreads();
-  int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (m >= M) return;
-  float qx = q_pts[3 * m], qy = q_pts[3 * m + 1], qz = q_pts[3 * m + 2];
+                                                               const IdxT* __restrict__ idx, const KPts kp,
+                                                               float inv_sigma, int M, int N, int H,
+                                                               float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, t = lane & 7;
+  const int m = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4 + (lane >> 3);
+  const bool qvalid = m < M;
+  const int mm = qvalid ? m : M - 1;
+  const float qx = q_pts[3 * (size_t)mm], qy = q_pts[3 * (size_t)mm + 1], qz = q_pts[3 * (size_t)mm + 2];
   float acc[KP_K];
 #pragma unroll
   for (int k = 0; k < KP_K; k++) acc[k] = 0.f;
   int cnt = 0;
-  for (int h = lane; h < H; h += 32) {
-    long long j = (long long)idx[(size_t)m * H + h];
+  for (int h = t; h < H; h += 8) {
+    long long j = qvalid ? (long long)idx[(size_t)mm * H + h] : (long long)N;
     if (j >= N) continue;
-    float f = feats[j];
+    const float f = feats[j];
     cnt += f > 0.f;
-    float dx = s_pts[3 * j] - qx, dy = s_pts[3 * j + 1] - qy, dz = s_pts[3 * j + 2] - qz;
+    const float dx = s_pts[3 * j] - qx, dy = s_pts[3 * j + 1] - qy, dz = s_pts[3 * j + 2] - qz;
 #pragma unroll
     for (int k = 0; k < KP_K; k++) {
-      float ex = dx - s_kp[3 * k], ey = dy - s_kp[3 * k + 1], ez = dz - s_kp[3 * k + 2];
-      float w = fmaxf(0.f, 1.f - sqrtf(ex * ex + ey * ey + ez * ez) / sigma);
-      acc[k] += w * f;
+      const float ex = dx - kp.x[k], ey = dy - kp.y[k], ez = dz - kp.z[k];
+      const float w = fmaxf(0.f, fmaf(-sqrt_approx(fmaf(ez, ez, fmaf(ey, ey, ex * ex))), inv_sigma, 1.f));
+      acc[k] = fmaf(w, f, acc[k]);
     }
   }
-  cnt = warp_sum_i(cnt);
-  float inv = 1.f / (float)max(cnt, 1);
 #pragma unroll
-  for (int k = 0; k < KP_K; k++) {
-    float v = warp_sum(acc[k]);
-    if (lane == k) out[(size_t)m * KP_K + k] = v * inv;
+  for (int o = 4; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(FULL_MASK, cnt, o);
+#pragma unroll
+    for (int k = 0; k < KP_K; k++) acc[k] += __shfl_xor_sync(FULL_MASK, acc[k], o);
   }
+  if (!qvalid) return;
+  const float inv = 1.f / (float)max(cnt, 1);
+  float mine = 0.f;
+#pragma unroll
+  for (int k = 0; k < KP_K; k++)
+    if (t == (k & 7)) {  // spread the 15 stores over the 8 lanes of the group
+      if (k < 8) mine = acc[k];
+    }
+  if (t < 8) out[(size_t)m * KP_K + t] = mine * inv;
+  float mine2 = 0.f;
+#pragma unroll
+  for (int k = 8; k < KP_K; k++)
+    if (t == k - 8) mine2 = acc[k];
+  if (t < KP_K - 8) out[(size_t)m * KP_K + 8 + t] = mine2 * inv;
 }
 
 // General case. CTA = 8 warps = QPC queries x NS channel slices (slice = 32*VEC channels).
@@ -173,14 +197,221 @@ __global__ void __launch_bounds__(256) kpconv_gather_kernel(const float* __restr
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------- gather, main path
+// Warp-autonomous mapping for C_in in {32, 64, 128k}. A warp is split into G = 32/L groups of L lanes; a lane owns
+// 4 channels, so a group covers a slice of 4*L channels with 128-bit loads. Two flavours:
+//   SPLIT = false : the G groups are G different queries (L = 8 -> C = 32, L = 16 -> C = 64, L = 32 -> one query and
+//                   one 128-channel slice per warp); neighbour lists are walked in chunks of L slots.
+//   SPLIT = true  : the warp owns ONE (query, 4L-channel slice); the G groups take different L-slot parts of each
+//                   32-slot chunk and their partial sums are combined by shuffles at the end. Used when M is small,
+//                   to put 2-4x more warps on the machine (the deep stages have only ~500-1100 queries).
+// Per chunk: (A) lane i computes the 15 influences of its slot (fast sqrt, 1/sigma multiply, kernel points as
+// constant-bank operands) into a warp-private shared tile; (B) each group streams its L rows: one LDG.128 per lane
+// and 60 FFMA per row against broadcast LDS.128 reads of the influences. Rows are sorted valid-first, so (B) stops
+// at the first slot that is padding for every group. No block barrier, 2.5 KB of shared memory per warp.
+#define KP_WS 20  // influence row stride (floats): 80 B keeps STS.128 / LDS.128 of interleaved rows conflict free
+
+template <int VEC>
+struct FVec;
+template <>
+struct FVec<4> {
+  typedef float4 T;
+};
+template <>
+struct FVec<2> {
+  typedef float2 T;
+};
+
+template <int L, bool SPLIT, int VEC, typename IdxT>
+__global__ void __launch_bounds__(128, VEC == 4 ? 4 : 7) kpconv_gather_v3_kernel(const float* __restrict__ feats,
+                                                                  const unsigned char* __restrict__ rowpos,
+                                                                  const float* __restrict__ q_pts,
+                                                                  const float* __restrict__ s_pts,
+                                                                  const IdxT* __restrict__ idx, const KPts kp,
+                                                                  float inv_sigma, int M, int N, int H, int C, int NS,
+                                                                  float* __restrict__ out) {
+  constexpr int G = 32 / L;
+  constexpr int STEP = SPLIT ? 32 : L;  // neighbour slots per chunk (per query)
+  __shared__ __align__(16) float s_w[4][32 * KP_WS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane / L, t = lane % L;
+  const int gw = blockIdx.x * 4 + warp;
+  int m, slice;
+  if (SPLIT || L == 32) {
+    m = gw / NS;
+    slice = gw - m * NS;
+  } else {
+    m = gw * G + g;
+    slice = 0;
+  }
+  const bool qvalid = m < M;
+  if (__all_sync(FULL_MASK, !qvalid)) return;
+  const int mm = qvalid ? m : M - 1;
+  const float qx = q_pts[3 * (size_t)mm], qy = q_pts[3 * (size_t)mm + 1], qz = q_pts[3 * (size_t)mm + 2];
+  const IdxT* row = idx + (size_t)mm * H;
+  const float* fbase = feats + slice * (VEC * L) + VEC * t;
+  float acc[KP_K][VEC];
+#pragma unroll
+  for (int k = 0; k < KP_K; k++)
+#pragma unroll
+    for (int v = 0; v < VEC; v++) acc[k][v] = 0.f;
+  int npos = 0;
+  float* wtile = s_w[warp];
+  float4* wrow = (float4*)(wtile + (t * G + g) * KP_WS);  // rows interleaved over groups: (u, g) -> u*G + g
+  const int myslot = SPLIT ? lane : t;
+  // slot -> neighbour index of this lane (or -1); prefetched one chunk ahead
+  auto load_j = [&](int h) -> int {
+    if (qvalid && h < H) {
+      long long jj = (long long)row[h];
+      if (jj < N) return (int)jj;
+    }
+    return -1;
+  };
+  int j = load_j(myslot);
+  for (int h0 = 0; h0 < H; h0 += STEP) {
+    if (!__any_sync(FULL_MASK, j >= 0)) break;  // rows are valid-first: nothing but padding from here on
+    const int jn = load_j(h0 + STEP + myslot);  // next chunk's index: in flight during the influence math
+    // ---- (A) influences of this lane's slot
+    float w[16];
+    if (j >= 0) {
+      const float dx = s_pts[3 * (size_t)j] - qx, dy = s_pts[3 * (size_t)j + 1] - qy, dz = s_pts[3 * (size_t)j + 2] - qz;
+#pragma unroll
+      for (int k = 0; k < KP_K; k++) {
+        const float ex = dx - kp.x[k], ey = dy - kp.y[k], ez = dz - kp.z[k];
+        const float d = sqrt_approx(fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
+        w[k] = fmaxf(0.f, fmaf(-d, inv_sigma, 1.f));  // kpconv.py:98-99
+      }
+      npos += rowpos[j];
+    } else {
+#pragma unroll
+      for (int k = 0; k < KP_K; k++) w[k] = 0.f;
+    }
+    w[15] = 0.f;
+    __syncwarp();  // previous chunk's readers are done
+    wrow[0] = make_float4(w[0], w[1], w[2], w[3]);
+    wrow[1] = make_float4(w[4], w[5], w[6], w[7]);
+    wrow[2] = make_float4(w[8], w[9], w[10], w[11]);
+    wrow[3] = make_float4(w[12], w[13], w[14], w[15]);
+    __syncwarp();
+    // ---- (B) each group streams its L rows of the chunk
+    // trip count = last valid slot of any group (+1), known before the loop so that it unrolls and the loads batch
+    const unsigned vb = __ballot_sync(FULL_MASK, j >= 0);
+    int nu = 0;
+#pragma unroll
+    for (int gg = 0; gg < G; gg++) {
+      const unsigned mg = (L == 32) ? vb : ((vb >> (gg * L)) & ((1u << (L & 31)) - 1u));
+      nu = max(nu, 32 - __clz(mg));
+    }
+#pragma unroll 4
+    for (int u = 0; u < nu; u++) {
+      const int ju = __shfl_sync(FULL_MASK, j, g * L + u);
+      float f[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; v++) f[v] = 0.f;
+      if (ju >= 0) {
+        const typename FVec<VEC>::T fv = __ldg((const typename FVec<VEC>::T*)(fbase + (size_t)ju * C));
+        f[0] = fv.x;
+        f[1] = fv.y;
+        if constexpr (VEC == 4) {
+          f[2] = fv.z;
+          f[3] = fv.w;
+        }
+      }
+      const float4* wp = (const float4*)(wtile + (u * G + g) * KP_WS);
+      const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+      const float ww[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+      for (int k = 0; k < KP_K; k++)
+#pragma unroll
+        for (int v = 0; v < VEC; v++) acc[k][v] = fmaf(ww[k], f[v], acc[k][v]);
+    }
+    j = jn;
+  }
+  // neighbour count of the query (kpconv.py:113-116) and, in SPLIT mode, the sum of the groups' partial results
+  if (SPLIT) {
+    npos = warp_sum_i(npos);
+#pragma unroll
+    for (int o = L; o < 32; o <<= 1)
+#pragma unroll
+      for (int k = 0; k < KP_K; k++)
+#pragma unroll
+        for (int v = 0; v < VEC; v++) acc[k][v] += __shfl_xor_sync(FULL_MASK, acc[k][v], o);
+    if (g != 0) return;
+  } else {
+#pragma unroll
+    for (int o = L >> 1; o > 0; o >>= 1) npos += __shfl_xor_sync(FULL_MASK, npos, o);
+  }
+  if (!qvalid) return;
+  const float inv = 1.f / (float)max(npos, 1);
+  float* op = out + (size_t)m * KP_K * C + slice * (VEC * L) + VEC * t;
+#pragma unroll
+  for (int k = 0; k < KP_K; k++) {
+    if constexpr (VEC == 4)
+      *(float4*)(op + (size_t)k * C) = make_float4(acc[k][0] * inv, acc[k][1] * inv, acc[k][2] * inv, acc[k][3] * inv);
+    else
+      *(float2*)(op + (size_t)k * C) = make_float2(acc[k][0] * inv, acc[k][1] * inv);
+  }
+}
+
 template <typename IdxT>
 static int launch_gather(const float* feats, const unsigned char* rowpos, const float* q, const float* s,
-                         const IdxT* idx, const float* kpts, float sigma, int M, int N, int H, int C, float* out,
+                         const IdxT* idx, const float* kpts, const float* h_kpts, float sigma, int M, int N, int H, int C, float* out,
                          cudaStream_t stream) {
+  // the 15 kernel points travel by value in the kernel-parameter constant bank: `d - kp` costs no load
+  KPts kp;
+  for (int k = 0; k < KP_K; k++) {
+    kp.x[k] = h_kpts[3 * k];
+    kp.y[k] = h_kpts[3 * k + 1];
+    kp.z[k] = h_kpts[3 * k + 2];
+  }
+  const float inv_sigma = 1.f / sigma;
   if (C == 1) {
-    kpconv_gather_c1_kernel<IdxT><<<cdiv(M, 8), 256, 0, stream>>>(feats, q, s, idx, kpts, sigma, M, N, H, out);
+    kpconv_gather_c1_kernel<IdxT><<<cdiv(M, 32), 256, 0, stream>>>(feats, q, s, idx, kp, inv_sigma, M, N, H, out);
     RDM_LAUNCH_CHECK();
     return RDM_OK;
+  }
+  if (C == 32 || C == 64 || (C % 128 == 0 && C <= 4096)) {
+    // candidates from the cheapest mapping (largest L, groups = different queries) to the most parallel one
+    // (small L, groups split one query's neighbour list); take the first that puts >= 16 warps on each of 148 SMs.
+    // A group of L lanes covers VEC*L channels. RDM_GATHER_VEC (debug knob, read once) selects 2 or 4 channels/lane.
+    static int vec = 0;
+    if (vec == 0) {
+      const char* e = getenv("RDM_GATHER_VEC");
+      vec = (e && e[0] == '2') ? 2 : 4;
+    }
+    const long long want = 148LL * 16;
+#define GATHER(Lv, SPLITv, VECv, warps, NSv)                                                                        \
+  do {                                                                                                              \
+    kpconv_gather_v3_kernel<Lv, SPLITv, VECv, IdxT><<<cdiv((long long)(warps), 4), 128, 0, stream>>>(               \
+        feats, rowpos, q, s, idx, kp, inv_sigma, M, N, H, C, (NSv), out);                                           \
+    RDM_LAUNCH_CHECK();                                                                                             \
+    return RDM_OK;                                                                                                  \
+  } while (0)
+    if (vec == 2) {  // slices of 2L channels
+      if (C == 32) {
+        if (cdiv(M, 2) >= want) GATHER(16, false, 2, cdiv(M, 2), 1);
+        if (M >= want) GATHER(16, true, 2, M, 1);
+        GATHER(8, true, 2, 2LL * M, 2);
+      } else {
+        if ((long long)M * (C / 64) >= want) GATHER(32, false, 2, (long long)M * (C / 64), C / 64);
+        if ((long long)M * (C / 32) >= want) GATHER(16, true, 2, (long long)M * (C / 32), C / 32);
+        GATHER(8, true, 2, (long long)M * (C / 16), C / 16);
+      }
+    }
+    if (C == 32) {
+      if (cdiv(M, 4) >= want) GATHER(8, false, 4, cdiv(M, 4), 1);
+      GATHER(8, true, 4, M, 1);
+    } else if (C == 64) {
+      if (cdiv(M, 2) >= want) GATHER(16, false, 4, cdiv(M, 2), 1);
+      if (M >= want) GATHER(16, true, 4, M, 1);
+      GATHER(8, true, 4, 2LL * M, 2);
+    } else {
+      if ((long long)M * (C / 128) >= want) GATHER(32, false, 4, (long long)M * (C / 128), C / 128);
+      if ((long long)M * (C / 64) >= want) GATHER(16, true, 4, (long long)M * (C / 64), C / 64);
+      GATHER(8, true, 4, (long long)M * (C / 32), C / 32);
+    }
+#undef GATHER
   }
   int VEC = (C % 128 == 0) ? 4 : (C % 64 == 0 ? 2 : 1);
   int NS = cdiv(C, 32 * VEC);
@@ -206,11 +437,13 @@ static int launch_gather(const float* feats, const unsigned char* rowpos, const 
 }
 
 extern "C" int rdm_kpconv_gather(const float* s_feats, const float* q_points, const float* s_points,
-                                 const void* neighbor_indices, int index_bytes, const float* kernel_points, float sigma,
+                                 const void* neighbor_indices, int index_bytes, const float* kernel_points,
+                                 const float* h_kernel_points, float sigma,
                                  int M, int N, int H, int C_in, float* out_weighted, unsigned char* rowpos_scratch,
                                  cudaStream_t stream) {
   RDM_CHECK_ARG(M >= 0 && N >= 0 && H >= 1 && C_in >= 1 && sigma > 0.f, "rdm_kpconv_gather: bad arguments");
   RDM_CHECK_ARG(index_bytes == 4 || index_bytes == 8, "rdm_kpconv_gather: index_bytes must be 4 or 8");
+  RDM_CHECK_ARG(kernel_points != nullptr && h_kernel_points != nullptr, "rdm_kpconv_gather: kernel points missing");
   if (M == 0) return RDM_OK;
   if (C_in > 1 && N > 0) {
     row_positive_kernel<<<cdiv(N, 8), 256, 0, stream>>>(s_feats, N, C_in, rowpos_scratch);
@@ -218,9 +451,9 @@ extern "C" int rdm_kpconv_gather(const float* s_feats, const float* q_points, co
   }
   if (index_bytes == 8)
     return launch_gather<int64_t>(s_feats, rowpos_scratch, q_points, s_points, (const int64_t*)neighbor_indices,
-                                  kernel_points, sigma, M, N, H, C_in, out_weighted, stream);
+                                  kernel_points, h_kernel_points, sigma, M, N, H, C_in, out_weighted, stream);
   return launch_gather<int>(s_feats, rowpos_scratch, q_points, s_points, (const int*)neighbor_indices, kernel_points,
-                            sigma, M, N, H, C_in, out_weighted, stream);
+                            h_kernel_points, sigma, M, N, H, C_in, out_weighted, stream);
 }
 
 // ---------------------------------------------------------------------------------------------- maxpool / upsample

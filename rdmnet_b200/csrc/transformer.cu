@@ -1,0 +1,300 @@
+// Fused ThDRoFormer layer kernels for the RDMNet configuration (d_model = 128, 4 heads x 32, FFN 256).
+//
+// Reference semantics (one TransformerLayer / RPETransformerLayer):
+//   rdmnet/thdroformer/thdroformer.py:108-139 (RPEMultiHeadAttention: q,k,v Linear, RoPE on q,k, softmax(qk^T/sqrt(32))v),
+//   :163-172 (RPEAttentionLayer: Linear + LayerNorm(residual)), geotransformer/modules/transformer/vanilla_transformer.py:
+//   31-70, 92-102 (same without RoPE), geotransformer/modules/transformer/output_layer.py:15-21 (FFN + LayerNorm).
+//
+// The sequences are <= ~450 superpoints: the unfused path spends its time in ~25 launches per layer. Here a layer is
+// two launches, and independent problems (ref/src self-attention, the q / k,v projections of a cross layer) share one:
+//   tf_project_kernel : Y = rope?(X W^T + b) for up to 6 (input, weight) jobs; CTA = 8 rows x 128 outputs.
+//   tf_attend_kernel  : CTA = 8 query rows, all 4 heads: flash-style attention over K/V tiles staged in shared
+//                       memory, then out-projection + residual + LayerNorm + FFN(ReLU) + residual + LayerNorm for
+//                       those rows - everything after the attention is row-local.
+// Weights are read from a per-layer blob of TRANSPOSED matrices (k-major), so that the 128 threads of a row block
+// read 128 consecutive floats per k (coalesced, L2-resident) while the activations are broadcast from shared memory.
+#include "common.cuh"
+#include "../../include/rdm_sm100.h"
+
+#define TF_D 128
+#define TF_H 4
+#define TF_HD 32
+#define TF_F 256
+#define TF_R 8        // rows per CTA
+#define TF_KT 64      // keys per tile
+
+// layer blob layout (floats), all matrices k-major ([in][out])
+#define TFB_WQ 0
+#define TFB_WK (TFB_WQ + TF_D * TF_D)
+#define TFB_WV (TFB_WK + TF_D * TF_D)
+#define TFB_WO (TFB_WV + TF_D * TF_D)
+#define TFB_W1 (TFB_WO + TF_D * TF_D)          // [128][256]
+#define TFB_W2 (TFB_W1 + TF_D * TF_F)          // [256][128]
+#define TFB_BQ (TFB_W2 + TF_F * TF_D)
+#define TFB_BK (TFB_BQ + TF_D)
+#define TFB_BV (TFB_BK + TF_D)
+#define TFB_BO (TFB_BV + TF_D)
+#define TFB_B1 (TFB_BO + TF_D)                 // 256
+#define TFB_B2 (TFB_B1 + TF_F)
+#define TFB_G1 (TFB_B2 + TF_D)
+#define TFB_E1 (TFB_G1 + TF_D)
+#define TFB_G2 (TFB_E1 + TF_D)
+#define TFB_E2 (TFB_G2 + TF_D)
+#define TFB_SIZE (TFB_E2 + TF_D)
+
+struct ProjJobs {
+  rdm_tf_proj_job j[6];
+};
+struct AttnJobs {
+  rdm_tf_attn_job j[2];
+};
+
+// acc[i] += sum_k WT[k][o] * xt[k][r0 + i], i < 4.   xt is a [K][8] shared tile (rows of the CTA, transposed).
+template <int K>
+__device__ __forceinline__ void rowblock_gemv4(const float* __restrict__ WT, int ldw, int o, const float* xt, int r0,
+                                               float acc[4]) {
+#pragma unroll 4
+  for (int k = 0; k < K; k += 4) {
+    const float w0 = __ldg(WT + (size_t)(k + 0) * ldw + o), w1 = __ldg(WT + (size_t)(k + 1) * ldw + o),
+                w2 = __ldg(WT + (size_t)(k + 2) * ldw + o), w3 = __ldg(WT + (size_t)(k + 3) * ldw + o);
+    const float4 x0 = *(const float4*)(xt + (k + 0) * TF_R + r0), x1 = *(const float4*)(xt + (k + 1) * TF_R + r0),
+                 x2 = *(const float4*)(xt + (k + 2) * TF_R + r0), x3 = *(const float4*)(xt + (k + 3) * TF_R + r0);
+    acc[0] = fmaf(w0, x0.x, acc[0]); acc[1] = fmaf(w0, x0.y, acc[1]); acc[2] = fmaf(w0, x0.z, acc[2]); acc[3] = fmaf(w0, x0.w, acc[3]);
+    acc[0] = fmaf(w1, x1.x, acc[0]); acc[1] = fmaf(w1, x1.y, acc[1]); acc[2] = fmaf(w1, x1.z, acc[2]); acc[3] = fmaf(w1, x1.w, acc[3]);
+    acc[0] = fmaf(w2, x2.x, acc[0]); acc[1] = fmaf(w2, x2.y, acc[1]); acc[2] = fmaf(w2, x2.z, acc[2]); acc[3] = fmaf(w2, x2.w, acc[3]);
+    acc[0] = fmaf(w3, x3.x, acc[0]); acc[1] = fmaf(w3, x3.y, acc[1]); acc[2] = fmaf(w3, x3.z, acc[2]); acc[3] = fmaf(w3, x3.w, acc[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ projection
+// grid (ceil(maxN/8), num_jobs), 256 threads: thread (o = tid & 127, rh = tid >> 7) -> output o of rows rh*4..rh*4+3.
+__global__ void __launch_bounds__(256) tf_project_kernel(const ProjJobs jobs) {
+  const rdm_tf_proj_job jb = jobs.j[blockIdx.y];
+  const int n0 = blockIdx.x * TF_R;
+  if (n0 >= jb.n) return;
+  __shared__ __align__(16) float xt[TF_D * TF_R];
+  const int tid = threadIdx.x, o = tid & 127, rh = tid >> 7;
+  for (int e = tid; e < TF_R * TF_D; e += 256) {
+    int r = e >> 7, c = e & 127;
+    xt[c * TF_R + r] = (n0 + r < jb.n) ? jb.x[(size_t)(n0 + r) * jb.ldx + c] : 0.f;
+  }
+  __syncthreads();
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  rowblock_gemv4<TF_D>(jb.wt, TF_D, o, xt, rh * 4, acc);
+  const float b = jb.bias[o];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int n = n0 + rh * 4 + i;
+    float v = acc[i] + b;
+    if (jb.emb != nullptr) {  // RoPE: thdroformer.py:56-85; channel pair (2p, 2p+1) rotates by theta(emb[n][p])
+      const float other = __shfl_xor_sync(FULL_MASK, v, 1);
+      if (n < jb.n) {
+        const float em = jb.emb[(size_t)n * jb.lde + (o >> 1)];
+        const float theta = (1.f / (1.f + expf(-em))) * 3.14159265359f * 2.f;
+        float s, c;
+        sincosf(theta, &s, &c);
+        v = (o & 1) ? fmaf(v, c, other * s) : fmaf(v, c, -other * s);
+      }
+    }
+    if (n < jb.n) {
+      if (jb.ldy_t == 0) jb.y[(size_t)n * TF_D + o] = v;      // row-major [n][128]
+      else jb.y[(size_t)o * jb.ldy_t + n] = v;                // channel-major [128][ldy_t] (keys of rdm_tf_attend)
+    }
+  }
+}
+
+extern "C" int rdm_tf_project(const rdm_tf_proj_job* h_jobs, int num_jobs, cudaStream_t stream) {
+  RDM_CHECK_ARG(h_jobs != nullptr && num_jobs >= 1 && num_jobs <= 6, "rdm_tf_project: 1..6 jobs");
+  ProjJobs pj;
+  int maxn = 0;
+  for (int i = 0; i < num_jobs; i++) {
+    pj.j[i] = h_jobs[i];
+    RDM_CHECK_ARG(h_jobs[i].n >= 0 && h_jobs[i].ldx >= TF_D && (h_jobs[i].ldy_t == 0 || h_jobs[i].ldy_t >= h_jobs[i].n),
+                  "rdm_tf_project: bad job %d", i);
+    maxn = max(maxn, h_jobs[i].n);
+  }
+  if (maxn == 0) return RDM_OK;
+  tf_project_kernel<<<dim3(cdiv(maxn, TF_R), num_jobs), 256, 0, stream>>>(pj);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ attention + post
+struct AttnSmem {
+  float Ks[TF_D * TF_KT];       // [channel][key]: lane-per-key reads and float4 tile stores are both conflict free
+  float Vs[TF_KT * TF_D];       // [key][channel]
+  float Qt[TF_D * TF_R];        // [channel][row], pre-scaled by 1/sqrt(32)
+  float Ps[8][TF_KT * 4];       // per warp: [key][4 queries]
+  float At[TF_D * TF_R];        // attention output / x1, transposed [channel][row]
+  float Y[TF_R * TF_D];         // row-major scratch for LayerNorm
+  float X1[TF_R * TF_D];        // x1 row-major (residual of the FFN)
+  float Ft[TF_F * TF_R];        // FFN hidden, transposed
+};
+
+// LayerNorm of the 8 rows in sm.Y (one warp per row): writes row-major to dst_rm (shared or global, stride ld) and,
+// if dst_t != nullptr, transposed to dst_t[c*8 + row].
+__device__ __forceinline__ void layernorm_rows(const float* Y, const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, float* dst_rm, int ld, float* dst_t,
+                                               int nvalid, int warp, int lane) {
+  const int r = warp;
+  const float4 v = *(const float4*)(Y + r * TF_D + 4 * lane);
+  const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.f / TF_D);
+  const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+  const float var = warp_sum(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3) * (1.f / TF_D);
+  const float rstd = rsqrtf(var + 1e-5f);
+  const float4 g = *(const float4*)(gamma + 4 * lane), b = *(const float4*)(beta + 4 * lane);
+  const float4 y = make_float4(d0 * rstd * g.x + b.x, d1 * rstd * g.y + b.y, d2 * rstd * g.z + b.z, d3 * rstd * g.w + b.w);
+  if (r < nvalid) *(float4*)(dst_rm + (size_t)r * ld + 4 * lane) = y;
+  if (dst_t != nullptr) {
+    dst_t[(4 * lane + 0) * TF_R + r] = y.x;
+    dst_t[(4 * lane + 1) * TF_R + r] = y.y;
+    dst_t[(4 * lane + 2) * TF_R + r] = y.z;
+    dst_t[(4 * lane + 3) * TF_R + r] = y.w;
+  }
+}
+
+// grid (ceil(maxNq/8), num_jobs), 256 threads = 8 warps; warp w -> head w & 3, queries (w >> 2) * 4 .. + 3.
+__global__ void __launch_bounds__(256) tf_attend_kernel(const AttnJobs jobs) {
+  const rdm_tf_attn_job jb = blockIdx.y == 0 ? jobs.j[0] : jobs.j[1];
+  const int n0 = blockIdx.x * TF_R;
+  if (n0 >= jb.nq) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  AttnSmem& sm = *reinterpret_cast<AttnSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int head = warp & 3, qh = warp >> 2;
+  const int nvalid = min(TF_R, jb.nq - n0);
+  const float scale = 0.17677669529663687f;  // 1/sqrt(32)
+  for (int e = tid; e < TF_R * TF_D; e += 256) {
+    int r = e >> 7, c = e & 127;
+    sm.Qt[c * TF_R + r] = (r < nvalid) ? jb.q[(size_t)(n0 + r) * TF_D + c] * scale : 0.f;
+  }
+  float m[4], l[4], acc[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    m[i] = -3.0e38f;
+    l[i] = 0.f;
+    acc[i] = 0.f;
+  }
+  const int hoff = head * TF_HD;
+  float* Pw = sm.Ps[warp];
+  for (int k0 = 0; k0 < jb.nk; k0 += TF_KT) {
+    __syncthreads();  // previous tile fully consumed (and Qt visible on the first pass)
+    for (int e = tid; e < TF_D * (TF_KT / 4); e += 256) {  // K tile: channel-major in global (ld = ldk_t) and in smem
+      const int c = e >> 4, j4 = (e & 15) * 4;
+      const float* src = jb.k + (size_t)c * jb.ldk_t + k0 + j4;
+      float4 kk = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + j4 + 3 < jb.ldk_t) kk = __ldg((const float4*)src);  // columns >= nk hold padding: masked below
+      *(float4*)(sm.Ks + c * TF_KT + j4) = kk;
+    }
+    for (int e = tid; e < TF_KT * (TF_D / 4); e += 256) {
+      const int j = e >> 5, c4 = (e & 31) * 4;
+      float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + j < jb.nk) vv = __ldg((const float4*)(jb.v + (size_t)(k0 + j) * TF_D + c4));
+      *(float4*)(sm.Vs + j * TF_D + c4) = vv;
+    }
+    __syncthreads();
+    // scores of keys (lane, lane+32) against the warp's 4 queries
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* ka = sm.Ks + hoff * TF_KT + lane;
+    const float* qp = sm.Qt + hoff * TF_R + qh * 4;
+#pragma unroll 8
+    for (int d = 0; d < TF_HD; d++) {
+      const float4 q4 = *(const float4*)(qp + d * TF_R);
+      const float a = ka[d * TF_KT], b = ka[d * TF_KT + 32];
+      s0[0] = fmaf(q4.x, a, s0[0]); s0[1] = fmaf(q4.y, a, s0[1]); s0[2] = fmaf(q4.z, a, s0[2]); s0[3] = fmaf(q4.w, a, s0[3]);
+      s1[0] = fmaf(q4.x, b, s1[0]); s1[1] = fmaf(q4.y, b, s1[1]); s1[2] = fmaf(q4.z, b, s1[2]); s1[3] = fmaf(q4.w, b, s1[3]);
+    }
+    const bool ok0 = k0 + lane < jb.nk, ok1 = k0 + lane + 32 < jb.nk;
+    float p0[4], p1[4], corr[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float a = ok0 ? s0[i] : -3.0e38f, b = ok1 ? s1[i] : -3.0e38f;
+      const float mnew = fmaxf(m[i], warp_max(fmaxf(a, b)));
+      corr[i] = __expf(m[i] - mnew);
+      p0[i] = ok0 ? __expf(a - mnew) : 0.f;
+      p1[i] = ok1 ? __expf(b - mnew) : 0.f;
+      l[i] = l[i] * corr[i] + warp_sum(p0[i] + p1[i]);
+      m[i] = mnew;
+      acc[i] *= corr[i];
+    }
+    __syncwarp();
+    *(float4*)(Pw + lane * 4) = make_float4(p0[0], p0[1], p0[2], p0[3]);
+    *(float4*)(Pw + (lane + 32) * 4) = make_float4(p1[0], p1[1], p1[2], p1[3]);
+    __syncwarp();
+    // acc[i] (channel hoff + lane) += sum_j p[i][j] * V[j][hoff + lane]
+    const float* vp = sm.Vs + hoff + lane;
+#pragma unroll 8
+    for (int j = 0; j < TF_KT; j++) {
+      const float4 p4 = *(const float4*)(Pw + j * 4);
+      const float v = vp[j * TF_D];
+      acc[0] = fmaf(p4.x, v, acc[0]); acc[1] = fmaf(p4.y, v, acc[1]); acc[2] = fmaf(p4.z, v, acc[2]); acc[3] = fmaf(p4.w, v, acc[3]);
+    }
+  }
+  // attention output, transposed: At[channel][row]
+  *(float4*)(sm.At + (hoff + lane) * TF_R + qh * 4) =
+      make_float4(acc[0] / l[0], acc[1] / l[1], acc[2] / l[2], acc[3] / l[3]);
+  __syncthreads();
+  const float* B = jb.blob;
+  const int o = tid & 127, rh = tid >> 7;
+  // out-projection + bias + residual(input rows) -> Y
+  {
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};
+    rowblock_gemv4<TF_D>(B + TFB_WO, TF_D, o, sm.At, rh * 4, a4);
+    const float b = B[TFB_BO + o];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int r = rh * 4 + i;
+      const float res = (r < nvalid) ? jb.x[(size_t)(n0 + r) * jb.ldx + o] : 0.f;
+      sm.Y[r * TF_D + o] = a4[i] + b + res;
+    }
+  }
+  __syncthreads();
+  layernorm_rows(sm.Y, B + TFB_G1, B + TFB_E1, sm.X1, TF_D, sm.At, TF_R, warp, lane);  // x1 (row-major + transposed)
+  __syncthreads();
+  // FFN expand 128 -> 256, ReLU: thread (o2 = tid, all 8 rows as two groups of 4)
+  {
+    float a4[4] = {0.f, 0.f, 0.f, 0.f}, c4[4] = {0.f, 0.f, 0.f, 0.f};
+    rowblock_gemv4<TF_D>(B + TFB_W1, TF_F, tid, sm.At, 0, a4);
+    rowblock_gemv4<TF_D>(B + TFB_W1, TF_F, tid, sm.At, 4, c4);
+    const float b = B[TFB_B1 + tid];
+    *(float4*)(sm.Ft + tid * TF_R) = make_float4(fmaxf(a4[0] + b, 0.f), fmaxf(a4[1] + b, 0.f), fmaxf(a4[2] + b, 0.f), fmaxf(a4[3] + b, 0.f));
+    *(float4*)(sm.Ft + tid * TF_R + 4) = make_float4(fmaxf(c4[0] + b, 0.f), fmaxf(c4[1] + b, 0.f), fmaxf(c4[2] + b, 0.f), fmaxf(c4[3] + b, 0.f));
+  }
+  __syncthreads();
+  // FFN squeeze 256 -> 128 + bias + residual(x1) -> Y
+  {
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};
+    rowblock_gemv4<TF_F>(B + TFB_W2, TF_D, o, sm.Ft, rh * 4, a4);
+    const float b = B[TFB_B2 + o];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int r = rh * 4 + i;
+      sm.Y[r * TF_D + o] = a4[i] + b + sm.X1[r * TF_D + o];
+    }
+  }
+  __syncthreads();
+  layernorm_rows(sm.Y, B + TFB_G2, B + TFB_E2, jb.out + (size_t)n0 * TF_D, TF_D, nullptr, nvalid, warp, lane);
+}
+
+extern "C" size_t rdm_tf_layer_blob_floats(void) { return (size_t)TFB_SIZE; }
+
+extern "C" int rdm_tf_attend(const rdm_tf_attn_job* h_jobs, int num_jobs, cudaStream_t stream) {
+  RDM_CHECK_ARG(h_jobs != nullptr && num_jobs >= 1 && num_jobs <= 2, "rdm_tf_attend: 1..2 jobs");
+  AttnJobs aj;
+  int maxn = 0;
+  for (int i = 0; i < num_jobs; i++) {
+    aj.j[i] = h_jobs[i];
+    RDM_CHECK_ARG(h_jobs[i].nq >= 0 && h_jobs[i].nk >= 1 && h_jobs[i].ldx >= TF_D && h_jobs[i].ldk_t >= h_jobs[i].nk &&
+                      h_jobs[i].ldk_t % 4 == 0, "rdm_tf_attend: bad job %d", i);
+    maxn = max(maxn, h_jobs[i].nq);
+  }
+  if (maxn == 0) return RDM_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RDM_CUDA(cudaFuncSetAttribute(tf_attend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmem)));
+    attr_set = true;
+  }
+  tf_attend_kernel<<<dim3(cdiv(maxn, TF_R), num_jobs), 256, sizeof(AttnSmem), stream>>>(aj);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}

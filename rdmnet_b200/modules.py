@@ -230,9 +230,33 @@ class TransformerLayer(nn.Module):
         super().__init__()
         self.attention = AttentionLayer(d_model, num_heads, dropout=dropout, rotary=rotary)
         self.output = AttentionOutput(d_model, dropout=dropout, activation_fn=activation_fn)
+        self._blob, self._blob_key = None, None
 
     def forward(self, input_states, memory_states, embed_q=None, embed_k=None):
         return self.output(self.attention(input_states, memory_states, embed_q, embed_k))
+
+    # ---- fused path (librdm_sm100: rdm_tf_project / rdm_tf_attend), d_model 128, 4 heads, FFN 256
+    def fusable(self):
+        a = self.attention.attention
+        return (a.d_model == 128 and a.num_heads == 4 and self.output.expand.out_features == 256
+                and self.attention.norm.eps == 1e-5 and self.output.norm.eps == 1e-5)
+
+    def fused_blob(self):
+        """The layer's parameters packed for the fused kernels (weights transposed to [in][out]); cached until a
+        parameter changes (storage pointer or in-place version)."""
+        a, al, o = self.attention.attention, self.attention, self.output
+        params = [a.proj_q.weight, a.proj_k.weight, a.proj_v.weight, al.linear.weight, o.expand.weight, o.squeeze.weight,
+                  a.proj_q.bias, a.proj_k.bias, a.proj_v.bias, al.linear.bias, o.expand.bias, o.squeeze.bias,
+                  al.norm.weight, al.norm.bias, o.norm.weight, o.norm.bias]
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._blob_key != key:
+            with torch.no_grad():
+                parts = [p.detach().t().contiguous().reshape(-1) for p in params[:6]] + [p.detach().reshape(-1) for p in params[6:]]
+                blob = torch.cat(parts).float().contiguous()
+            if blob.numel() != ops.L.lib().rdm_tf_layer_blob_floats():
+                raise RuntimeError("transformer layer blob layout mismatch")
+            self._blob, self._blob_key = blob, key
+        return self._blob
 
 
 class RPEConditionalTransformer(nn.Module):
@@ -249,6 +273,9 @@ class RPEConditionalTransformer(nn.Module):
             [TransformerLayer(d_model, num_heads, dropout, activation_fn, rotary=(b == "self")) for b in blocks])
 
     def forward(self, feats0, feats1, embeddings0, embeddings1, masks0=None, masks1=None):
+        if all(layer.fusable() for layer in self.layers) and feats0.shape[0] > 0 and feats1.shape[0] > 0:
+            return self._forward_fused(feats0.contiguous(), feats1.contiguous(), embeddings0.contiguous(),
+                                       embeddings1.contiguous())
         for layer, block in zip(self.layers, self.blocks):
             if block == "self":
                 feats0 = layer(feats0, feats0, embeddings0, embeddings0)
@@ -257,6 +284,34 @@ class RPEConditionalTransformer(nn.Module):
                 feats0 = layer(feats0, feats1)
                 feats1 = layer(feats1, feats0)
         return feats0, feats1
+
+    def _forward_fused(self, f0, f1, e0, e1):
+        """Two launches per (layer, independent problem set) instead of ~25: see csrc/transformer.cu."""
+        n0, n1, dev = f0.shape[0], f1.shape[0], f0.device
+        qv0 = torch.empty((2, n0, 128), dtype=torch.float32, device=dev)
+        qv1 = torch.empty((2, n1, 128), dtype=torch.float32, device=dev)
+        q0, v0, q1, v1 = qv0[0], qv0[1], qv1[0], qv1[1]
+        # projected keys are kept channel-major (128, n padded to 4): coalesced, conflict-free K tiles in rdm_tf_attend
+        k0 = torch.empty((128, (n0 + 3) // 4 * 4), dtype=torch.float32, device=dev)  # pad columns are masked
+        k1 = torch.empty((128, (n1 + 3) // 4 * 4), dtype=torch.float32, device=dev)
+        for layer, block in zip(self.layers, self.blocks):
+            blob = layer.fused_blob()
+            if block == "self":
+                ops.tf_project(blob, [(f0, "q", e0, q0), (f0, "k", e0, k0), (f0, "v", None, v0),
+                                      (f1, "q", e1, q1), (f1, "k", e1, k1), (f1, "v", None, v1)])
+                o0, o1 = torch.empty_like(q0), torch.empty_like(q1)
+                ops.tf_attend(blob, [(q0, k0, v0, f0, o0), (q1, k1, v1, f1, o1)])
+                f0, f1 = o0, o1
+            else:
+                ops.tf_project(blob, [(f0, "q", None, q0), (f1, "k", None, k1), (f1, "v", None, v1)])
+                o0 = torch.empty_like(q0)
+                ops.tf_attend(blob, [(q0, k1, v1, f0, o0)])
+                f0 = o0
+                ops.tf_project(blob, [(f1, "q", None, q1), (f0, "k", None, k0), (f0, "v", None, v0)])
+                o1 = torch.empty_like(q1)
+                ops.tf_attend(blob, [(q1, k0, v0, f1, o1)])
+                f1 = o1
+        return f0, f1
 
 
 class posEmbedding(nn.Module):

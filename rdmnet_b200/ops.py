@@ -2,6 +2,8 @@
 parts of ``geotransformer.modules.kpconv`` (same names, argument meaning and error behaviour), executing on the GPU
 through librdm_sm100.so. Reference citations are relative to /root/reference.
 """
+import ctypes
+
 import torch
 
 from . import _lib as L
@@ -130,6 +132,22 @@ def linear(x, weight, bias=None, weight_is_kn=False, act=0):
     return out
 
 
+_HOST_COPIES = {}
+
+
+def _host_copy(t):
+    """Host mirror of a small constant device tensor (KPConv kernel points), cached per (storage, version): the one
+    D2H happens the first time a module runs, not per call."""
+    key = (t.data_ptr(), t._version, t.device)
+    h = _HOST_COPIES.get(key)
+    if h is None:
+        if len(_HOST_COPIES) > 4096:
+            _HOST_COPIES.clear()
+        h = t.detach().to("cpu", torch.float32).contiguous()
+        _HOST_COPIES[key] = h
+    return h
+
+
 def kpconv(s_feats, q_points, s_points, neighbor_indices, weights, kernel_points, sigma, bias=None):
     """KPConv.forward (geotransformer/modules/kpconv/kpconv.py:79-122)."""
     s_feats, neighbor_indices = s_feats.contiguous(), neighbor_indices.contiguous()
@@ -145,7 +163,7 @@ def kpconv(s_feats, q_points, s_points, neighbor_indices, weights, kernel_points
     timer = L.TIMER
     e0 = timer.start() if timer is not None else None
     L.call("rdm_kpconv_gather", L.ptr(s_feats), L.ptr(q_points), L.ptr(s_points), L.ptr(neighbor_indices),
-           _idx_bytes(neighbor_indices), L.ptr(kernel_points), float(sigma), m, n, h, c, L.ptr(gathered), L.ptr(rowpos),
+           _idx_bytes(neighbor_indices), L.ptr(kernel_points), _host_copy(kernel_points).data_ptr(), float(sigma), m, n, h, c, L.ptr(gathered), L.ptr(rowpos),
            L.stream())
     if timer is not None:
         timer.stop("kpconv_gather", e0, kpconv_gather_bytes(m, h, c, cout, _idx_bytes(neighbor_indices)), (m, n, h, c, cout))
@@ -240,6 +258,39 @@ def attention(q, k, v, heads):
     L.call("rdm_attention", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), L.ptr(out),
            c, nq, nk, heads, c // heads, L.stream())
     return out
+
+
+_TF_W = {"q": 0, "k": 128 * 128, "v": 2 * 128 * 128}
+_TF_B0 = 4 * 128 * 128 + 2 * 128 * 256
+_TF_B = {"q": _TF_B0, "k": _TF_B0 + 128, "v": _TF_B0 + 256}
+
+
+def tf_project(blob, jobs):
+    """Fused q/k/v projections (+ RoPE) of one transformer layer: jobs = [(x (n,>=128 cols), 'q'|'k'|'v', emb or None, y)],
+    up to 6 per launch (rdm_tf_project; MultiHeadAttention.forward projections, thdroformer.py:108-131). y is (n,128)
+    for 'q'/'v' and channel-major (128, ld) with ld % 4 == 0 for 'k' (the key layout rdm_tf_attend streams)."""
+    arr = (L.TfProjJob * len(jobs))()
+    base = blob.data_ptr()
+    for i, (x, which, emb, y) in enumerate(jobs):
+        if x.stride(1) != 1 or (emb is not None and emb.stride(1) != 1) or y.stride(1) != 1:
+            raise RuntimeError("tf_project: channel dimension must be contiguous")
+        arr[i] = L.TfProjJob(x.data_ptr(), base + 4 * _TF_W[which], base + 4 * _TF_B[which],
+                             emb.data_ptr() if emb is not None else None, y.data_ptr(), x.shape[0], x.stride(0),
+                             emb.stride(0) if emb is not None else 0, y.stride(0) if which == "k" else 0)
+    L.call("rdm_tf_project", ctypes.cast(arr, ctypes.c_void_p), len(jobs), L.stream())
+
+
+def tf_attend(blob, jobs):
+    """Fused attention + output projection + LayerNorm + FFN + LayerNorm: jobs = [(q (nq,128), kt (128,ld) channel-major
+    keys, v (nk,128), x, out)], up to 2 per launch (rdm_tf_attend; TransformerLayer.forward,
+    vanilla_transformer.py:105-129 / thdroformer.py:175-202)."""
+    arr = (L.TfAttnJob * len(jobs))()
+    for i, (q, kt, v, x, out) in enumerate(jobs):
+        if x.stride(1) != 1 or kt.stride(1) != 1 or not (q.is_contiguous() and v.is_contiguous() and out.is_contiguous()):
+            raise RuntimeError("tf_attend: tensors must be contiguous")
+        arr[i] = L.TfAttnJob(q.data_ptr(), kt.data_ptr(), v.data_ptr(), x.data_ptr(), blob.data_ptr(), out.data_ptr(),
+                             q.shape[0], v.shape[0], x.stride(0), kt.stride(0))
+    L.call("rdm_tf_attend", ctypes.cast(arr, ctypes.c_void_p), len(jobs), L.stream())
 
 
 # ----------------------------------------------------------------------------------------------- matching

@@ -1,0 +1,58 @@
+"""Micro-benchmark of the KPConv neighbour-gather kernel on the real pyramid of one synthetic pair (GPU box).
+Prints per-layer time and G-roofline GB/s. Knobs come from the environment (RDM_GATHER_VEC=2|4)."""
+import os, sys
+import numpy as np
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from rdmnet_b200 import ops, synthetic, _lib as L
+from rdmnet_b200.model import precompute_data_stack_mode
+
+src = sys.argv[1] if len(sys.argv) > 1 else "synthetic"
+if src == "bundled":
+    sc = dict(np.load(os.path.join(ROOT, "tests/golden/scans.npz")))
+    a, b = sc["s000000"], sc["s000004"]
+else:
+    p = synthetic.make_pair(0)
+    a, b = p["ref_points"], p["src_points"]
+pts = torch.from_numpy(np.concatenate([a, b])).cuda()
+lens = torch.tensor([len(a), len(b)]).cuda()
+pyr = precompute_data_stack_mode(pts, lens, 5, 0.3, 4.25 * 0.3, [65, 63, 69, 70, 81], index_dtype=torch.int32)
+P, NB, SUB = pyr["points"], pyr["neighbors"], pyr["subsampling"]
+# (C_in, C_out, query stage, support stage, table) of the 14 KPConv calls (experiments/backbone.py:11-70)
+layers = [(1, 64, 0, 0, NB[0]), (32, 32, 0, 0, NB[0])]
+for s_ in range(1, 5):
+    c = 32 * 2 ** (s_ - 1)
+    layers += [(c, c, s_, s_ - 1, SUB[s_ - 1]), (2 * c, 2 * c, s_, s_, NB[s_]), (2 * c, 2 * c, s_, s_, NB[s_])]
+torch.manual_seed(0)
+kp = (torch.randn(15, 3) * 0.4).cuda()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+tot_b = tot_t = 0.0
+print(f"RDM_GATHER_VEC={os.environ.get('RDM_GATHER_VEC', '4')} source={src}")
+for (cin, cout, qs, ss, tab) in layers:
+    m, h = tab.shape
+    n = P[ss].shape[0]
+    feats = torch.randn(n, cin, device="cuda") if cin > 1 else torch.ones(n, 1, device="cuda")
+    w = torch.zeros(15, cin, 1, device="cuda")
+    sigma = 0.6 * 2 ** ss
+    out = torch.empty((m, 15 * cin), device="cuda")
+    rowpos = torch.empty(n, dtype=torch.uint8, device="cuda")
+    hk = ops._host_copy(kp)
+    def run():
+        L.call("rdm_kpconv_gather", L.ptr(feats), L.ptr(P[qs]), L.ptr(P[ss]), L.ptr(tab), 4, L.ptr(kp), hk.data_ptr(),
+               float(sigma), m, n, h, cin, L.ptr(out), L.ptr(rowpos), L.stream())
+    iters = int(os.environ.get('BG_ITERS', '10'))
+    for _ in range(3 if iters > 1 else 0):
+        run()
+    ts = []
+    for _ in range(iters):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    t = float(np.median(ts))
+    g = ops.kpconv_gather_bytes(m, h, cin, cout, 4)
+    valid = float((tab < n).float().mean())
+    tot_b += g; tot_t += t
+    print(f"C{cin:4d} M{m:6d} N{n:6d} H{h:3d} fill {valid:.2f}  {t*1e3:7.1f} us  {g/t/1e6:7.0f} GB/s")
+print(f"TOTAL {tot_t*1e3:.1f} us  {tot_b/tot_t/1e6:.0f} GB/s  frac {tot_b/tot_t/1e6/6539.9:.3f}")

@@ -44,7 +44,10 @@ def test_linear(m, n, k, nk):
 @pytest.mark.parametrize("cin,cout,m,n,h,idt", [(1, 64, 500, 500, 33, torch.int64), (32, 32, 700, 900, 65, torch.int64),
                                                  (64, 64, 300, 300, 63, torch.int32), (128, 128, 200, 250, 69, torch.int64),
                                                  (256, 256, 90, 120, 70, torch.int64), (512, 512, 50, 50, 81, torch.int32),
-                                                 (48, 20, 100, 100, 17, torch.int64)])
+                                                 (48, 20, 100, 100, 17, torch.int64),
+                                                 # large M: the non-split warp mappings of the main gather kernel
+                                                 (32, 32, 10000, 10000, 40, torch.int32), (64, 64, 5000, 6000, 33, torch.int32),
+                                                 (128, 128, 2500, 2500, 35, torch.int64), (256, 256, 1300, 1300, 37, torch.int32)])
 def test_kpconv_vs_oracle(cin, cout, m, n, h, idt):
     from rdmnet_b200 import ops
     rng = np.random.default_rng(cin + m)
