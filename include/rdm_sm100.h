@@ -35,6 +35,17 @@ int rdm_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py reports the delta as gpu_launches) */
 unsigned long long rdm_launch_count(void);
 
+/* optional kernel timing: after rdm_prof_enable(1) the library brackets selected launches with CUDA events on the launch
+ * stream; rdm_prof_read synchronises those events and returns the records. tag 1 = KPConv gather (row_positive prepass +
+ * gather kernel, m/n/h/c = M, N, H, C_in), tag 2 = KPConv weight GEMM (m, n, -, c = M, K, 0, N). */
+typedef struct {
+  int tag;
+  float ms;
+  int m, n, h, c;
+} rdm_prof_record;
+void rdm_prof_enable(int on);
+int rdm_prof_read(rdm_prof_record* h_out, int max_records);
+
 /* ---- rdmnet.ext.grid_subsampling (geotransformer/extensions/cpu/grid_subsampling/grid_subsampling.cpp:5-62,
  *      core grid_subsampling_cpu.cpp:3-75; Python wrapper geotransformer/modules/ops/grid_subsample.py:7-22).
  * points [n_total,3], lengths [batch] (device int64). out_points has capacity n_total_cap rows; the stacked result
@@ -137,6 +148,64 @@ typedef struct {
 size_t rdm_tf_layer_blob_floats(void);
 int rdm_tf_project(const rdm_tf_proj_job* h_jobs, int num_jobs, rdm_stream_t stream);
 int rdm_tf_attend(const rdm_tf_attn_job* h_jobs, int num_jobs, rdm_stream_t stream);
+
+/* ---- whole-module runners: one host call walks a module's kernels (the per-launch host cost of a Python loop is
+ * what bounds a ~10 ms pair otherwise). Descriptor structs and pointer arrays named h_* live in HOST memory; every
+ * pointer inside them is a device pointer (except h_kernel_points). `workspace` is device scratch; the matching
+ * *_workspace function returns the bytes needed for the same arguments.
+ *
+ * rdm_encoder_forward = Encoder.forward (experiments/backbone.py:72-107): ConvBlock + 13 ResidualBlocks
+ * (geotransformer/modules/kpconv/modules.py:104-225). blocks[0] is the ConvBlock (only kpconv_* and norm_conv_* set,
+ * unary1/unary2/shortcut.w == NULL); stage s > 0 starts with a strided block reading subsampling[s-1].
+ * out_feats[s] receives the last block of stage s ([n[s], c_out]). */
+typedef struct {
+  const float *w, *b;       /* nn.Linear weight [c_out, c_in], bias (w == NULL: identity / absent) */
+  const float *gn_w, *gn_b; /* GroupNorm affine (NULL: no norm, LastUnaryBlock) */
+  int c_in, c_out;
+} rdm_unary_desc;
+typedef struct {
+  rdm_unary_desc unary1, unary2, shortcut;
+  const float* kpconv_w;          /* [15, c_mid, c_mid'] */
+  const float* kpconv_b;          /* [c_mid'] or NULL */
+  const float* kernel_points;     /* [15,3] device */
+  const float* h_kernel_points;   /* the same 45 floats, host */
+  const float *norm_conv_w, *norm_conv_b;
+  int c_in, c_mid_in, c_mid_out, c_out, strided, stage;
+  float sigma;
+} rdm_block_desc;
+typedef struct {
+  const float* points[8];       /* per stage [n,3] */
+  const void* neighbors[8];     /* [n[s], nb_width[s]] */
+  const void* subsampling[8];   /* [n[s+1], sub_width[s]] */
+  const void* upsampling[8];    /* [n[s], up_width[s]] (indices into stage s+1) */
+  int n[8], nb_width[8], sub_width[8], up_width[8];
+  int num_stages, index_bytes;
+} rdm_pyramid_desc;
+size_t rdm_encoder_workspace(const rdm_block_desc* h_blocks, int num_blocks, const rdm_pyramid_desc* h_pyr, int groups);
+int rdm_encoder_forward(const rdm_block_desc* h_blocks, int num_blocks, const rdm_pyramid_desc* h_pyr, int groups,
+                        const float* in_feats, float* const* h_out_feats, void* workspace, size_t workspace_bytes,
+                        rdm_stream_t stream);
+/* rdm_decoder_forward = Decoder.forward (experiments/backbone.py:118-151): for i = 0..num-1 (coarse to fine),
+ * x = unary_i(cat(nearest_upsample(x, upsampling[stage_i]), skip_i)); h_dec[i] = decoder4, decoder3, decoder2 (no norm).
+ * coarse [n[top], c_coarse]; h_skips[i] = encoder output of stage top-1-i; out = last result [n[top-num], c_out]. */
+size_t rdm_decoder_workspace(const rdm_unary_desc* h_dec, int num, const rdm_pyramid_desc* h_pyr, int top_stage, int groups);
+int rdm_decoder_forward(const rdm_unary_desc* h_dec, int num, const rdm_pyramid_desc* h_pyr, int top_stage, int groups,
+                        const float* coarse, int c_coarse, const float* const* h_skips, float* out, void* workspace,
+                        size_t workspace_bytes, rdm_stream_t stream);
+/* rdm_thdroformer_forward = ThDRoFormer.forward (rdmnet/thdroformer/thdroformer.py:304-347) for hidden 128 / 4 heads:
+ * embedding Linear(3,64), in_proj, 2*L fused layers (h_layer_blobs[i], h_is_self[i]), out_proj. */
+typedef struct {
+  const float *emb_w, *emb_b;   /* [64,3], [64] */
+  const float *in_w, *in_b;     /* [128, c_in], [128] */
+  const float *out_w, *out_b;   /* [c_out, 128], [c_out] */
+  const float* layer_blobs[32];
+  int is_self[32];
+  int num_layers, c_in, c_out;
+} rdm_thdroformer_desc;
+size_t rdm_thdroformer_workspace(int n_ref, int n_src, int c_out);
+int rdm_thdroformer_forward(const rdm_thdroformer_desc* h_desc, const float* ref_points, int n_ref, const float* src_points,
+                            int n_src, const float* ref_feats, int ld_ref, const float* src_feats, int ld_src,
+                            float* out_ref, float* out_src, void* workspace, size_t workspace_bytes, rdm_stream_t stream);
 
 /* ---- NMS.forward greedy loop (rdmnet/vote/vote.py:33-40) over a radius-search table [N,H] (H <= 128). */
 int rdm_nms(const void* neighbor_indices, int index_bytes, int N, int H, unsigned char* out_mask, rdm_stream_t stream);

@@ -15,6 +15,8 @@ SIGNATURES = {
     "rdm_last_error": (ctypes.c_char_p, []),
     "rdm_version": (c_int, []),
     "rdm_launch_count": (ctypes.c_ulonglong, []),
+    "rdm_prof_enable": (None, [c_int]),
+    "rdm_prof_read": (c_int, [c_void_p, c_int]),
     "rdm_grid_subsample_workspace": (c_size_t, [c_i64, c_int]),
     "rdm_grid_subsample": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "rdm_selfcheck_bucket_table": (c_int, [c_i64]),
@@ -38,6 +40,14 @@ SIGNATURES = {
     "rdm_tf_layer_blob_floats": (c_size_t, []),
     "rdm_tf_project": (c_int, [c_void_p, c_int, c_void_p]),
     "rdm_tf_attend": (c_int, [c_void_p, c_int, c_void_p]),
+    "rdm_encoder_workspace": (c_size_t, [c_void_p, c_int, c_void_p, c_int]),
+    "rdm_encoder_forward": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "rdm_decoder_workspace": (c_size_t, [c_void_p, c_int, c_void_p, c_int, c_int]),
+    "rdm_decoder_forward": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                    c_size_t, c_void_p]),
+    "rdm_thdroformer_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "rdm_thdroformer_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
+                                        c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "rdm_nms": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "rdm_point_to_node_workspace": (c_size_t, [c_int, c_int]),
     "rdm_point_to_node": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -64,6 +74,29 @@ class TfProjJob(ctypes.Structure):
 class TfAttnJob(ctypes.Structure):
     _fields_ = [("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("x", c_void_p), ("blob", c_void_p), ("out", c_void_p),
                 ("nq", c_int), ("nk", c_int), ("ldx", c_int), ("ldk_t", c_int)]
+
+
+class UnaryDesc(ctypes.Structure):
+    _fields_ = [("w", c_void_p), ("b", c_void_p), ("gn_w", c_void_p), ("gn_b", c_void_p), ("c_in", c_int), ("c_out", c_int)]
+
+
+class BlockDesc(ctypes.Structure):
+    _fields_ = [("unary1", UnaryDesc), ("unary2", UnaryDesc), ("shortcut", UnaryDesc), ("kpconv_w", c_void_p),
+                ("kpconv_b", c_void_p), ("kernel_points", c_void_p), ("h_kernel_points", c_void_p),
+                ("norm_conv_w", c_void_p), ("norm_conv_b", c_void_p), ("c_in", c_int), ("c_mid_in", c_int),
+                ("c_mid_out", c_int), ("c_out", c_int), ("strided", c_int), ("stage", c_int), ("sigma", c_float)]
+
+
+class PyramidDesc(ctypes.Structure):
+    _fields_ = [("points", c_void_p * 8), ("neighbors", c_void_p * 8), ("subsampling", c_void_p * 8),
+                ("upsampling", c_void_p * 8), ("n", c_int * 8), ("nb_width", c_int * 8), ("sub_width", c_int * 8),
+                ("up_width", c_int * 8), ("num_stages", c_int), ("index_bytes", c_int)]
+
+
+class ThdroformerDesc(ctypes.Structure):
+    _fields_ = [("emb_w", c_void_p), ("emb_b", c_void_p), ("in_w", c_void_p), ("in_b", c_void_p), ("out_w", c_void_p),
+                ("out_b", c_void_p), ("layer_blobs", c_void_p * 32), ("is_self", c_int * 32), ("num_layers", c_int),
+                ("c_in", c_int), ("c_out", c_int)]
 
 
 def lib():
@@ -106,35 +139,20 @@ def call(name, *args):
     check(getattr(lib(), name)(*args), name)
 
 
-class KernelTimer:
-    """Optional CUDA-event timer around selected C-ABI calls (bench.py: live roofline of the KPConv gather kernel).
-    Events are recorded on torch's current stream, which is the stream every kernel of the library is launched on."""
-
-    def __init__(self):
-        self.records = []  # (tag, start_event, stop_event, algorithmic_bytes, meta)
-
-    def start(self):
-        e = torch.cuda.Event(enable_timing=True)
-        e.record()
-        return e
-
-    def stop(self, tag, e0, nbytes, meta=None):
-        e1 = torch.cuda.Event(enable_timing=True)
-        e1.record()
-        self.records.append((tag, e0, e1, nbytes, meta))
-
-    def summary(self):
-        """-> {tag: {"launches", "ms", "bytes"}} (call after a synchronize)."""
-        out = {}
-        for tag, e0, e1, nb, _ in self.records:
-            d = out.setdefault(tag, {"launches": 0, "ms": 0.0, "bytes": 0})
-            d["launches"] += 1
-            d["ms"] += e0.elapsed_time(e1)
-            d["bytes"] += nb
-        return out
+class ProfRecord(ctypes.Structure):
+    _fields_ = [("tag", c_int), ("ms", c_float), ("m", c_int), ("n", c_int), ("h", c_int), ("c", c_int)]
 
 
-TIMER = None  # set to a KernelTimer to enable
+def prof_enable(on):
+    """In-library CUDA-event timing of the KPConv gather / weight-GEMM launches (rdm_prof_enable)."""
+    lib().rdm_prof_enable(1 if on else 0)
+
+
+def prof_read(max_records=1 << 16):
+    """-> list of (tag, ms, m, n, h, c); synchronises the recorded events."""
+    buf = (ProfRecord * max_records)()
+    n = lib().rdm_prof_read(ctypes.cast(buf, c_void_p), max_records)
+    return [(buf[i].tag, buf[i].ms, buf[i].m, buf[i].n, buf[i].h, buf[i].c) for i in range(n)]
 
 
 def launch_count():

@@ -1,5 +1,6 @@
 // Error reporting + version for librdm_sm100.so.
 #include <stdarg.h>
+#include <vector>
 #include "common.cuh"
 #include "../../include/rdm_sm100.h"
 
@@ -17,3 +18,49 @@ extern "C" int rdm_version(void) { return 101; }
 
 unsigned long long g_rdm_launches = 0;
 extern "C" unsigned long long rdm_launch_count(void) { return __atomic_load_n(&g_rdm_launches, __ATOMIC_RELAXED); }
+
+// ---- optional in-library kernel timing (bench.py: live roofline of the KPConv gather kernel). Events are recorded on
+// the launch stream right around the launches, so the measured span holds the kernels and nothing of the host loop.
+namespace {
+struct ProfRec {
+  cudaEvent_t e0, e1;
+  int tag, m, n, h, c;
+};
+std::vector<ProfRec> g_prof;
+bool g_prof_on = false;
+}  // namespace
+
+int rdm_prof_begin(int tag, int m, int n, int h, int c, cudaStream_t stream) {
+  if (!g_prof_on) return -1;
+  ProfRec r;
+  r.tag = tag; r.m = m; r.n = n; r.h = h; r.c = c;
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return -1;
+  cudaEventRecord(r.e0, stream);
+  g_prof.push_back(r);
+  return (int)g_prof.size() - 1;
+}
+
+void rdm_prof_end(int id, cudaStream_t stream) {
+  if (id >= 0 && id < (int)g_prof.size()) cudaEventRecord(g_prof[id].e1, stream);
+}
+
+extern "C" void rdm_prof_enable(int on) {
+  for (auto& r : g_prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  g_prof_on = on != 0;
+}
+
+extern "C" int rdm_prof_read(rdm_prof_record* out, int max_records) {
+  int n = 0;
+  for (auto& r : g_prof) {
+    if (n >= max_records) break;
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.e1) != cudaSuccess || cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) continue;
+    out[n].tag = r.tag; out[n].ms = ms; out[n].m = r.m; out[n].n = r.n; out[n].h = r.h; out[n].c = r.c;
+    n++;
+  }
+  return n;
+}

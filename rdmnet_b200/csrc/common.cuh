@@ -36,6 +36,12 @@ extern unsigned long long g_rdm_launches;
     RDM_CUDA(cudaGetLastError());                               \
   } while (0)
 
+// optional kernel timing (api.cu); id < 0 = profiling off
+int rdm_prof_begin(int tag, int m, int n, int h, int c, cudaStream_t stream);
+void rdm_prof_end(int id, cudaStream_t stream);
+#define RDM_PROF_KPCONV_GATHER 1
+#define RDM_PROF_KPCONV_GEMM 2
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -445,15 +445,20 @@ extern "C" int rdm_kpconv_gather(const float* s_feats, const float* q_points, co
   RDM_CHECK_ARG(index_bytes == 4 || index_bytes == 8, "rdm_kpconv_gather: index_bytes must be 4 or 8");
   RDM_CHECK_ARG(kernel_points != nullptr && h_kernel_points != nullptr, "rdm_kpconv_gather: kernel points missing");
   if (M == 0) return RDM_OK;
+  const int prof = rdm_prof_begin(RDM_PROF_KPCONV_GATHER, M, N, H, C_in, stream);
   if (C_in > 1 && N > 0) {
     row_positive_kernel<<<cdiv(N, 8), 256, 0, stream>>>(s_feats, N, C_in, rowpos_scratch);
     RDM_LAUNCH_CHECK();
   }
+  int rc;
   if (index_bytes == 8)
-    return launch_gather<int64_t>(s_feats, rowpos_scratch, q_points, s_points, (const int64_t*)neighbor_indices,
-                                  kernel_points, h_kernel_points, sigma, M, N, H, C_in, out_weighted, stream);
-  return launch_gather<int>(s_feats, rowpos_scratch, q_points, s_points, (const int*)neighbor_indices, kernel_points,
+    rc = launch_gather<int64_t>(s_feats, rowpos_scratch, q_points, s_points, (const int64_t*)neighbor_indices,
+                                kernel_points, h_kernel_points, sigma, M, N, H, C_in, out_weighted, stream);
+  else
+    rc = launch_gather<int>(s_feats, rowpos_scratch, q_points, s_points, (const int*)neighbor_indices, kernel_points,
                             h_kernel_points, sigma, M, N, H, C_in, out_weighted, stream);
+  rdm_prof_end(prof, stream);
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------------- maxpool / upsample

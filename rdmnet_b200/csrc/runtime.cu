@@ -1,0 +1,277 @@
+// Host-side module runners: one C call walks all kernels of Encoder / Decoder / ThDRoFormer.
+// Reference wiring: experiments/backbone.py:72-107 (Encoder.forward), :118-151 (Decoder.forward),
+// geotransformer/modules/kpconv/modules.py:53-225 (UnaryBlock / ConvBlock / ResidualBlock),
+// rdmnet/thdroformer/thdroformer.py:229-251, 304-347 (RPEConditionalTransformer / ThDRoFormer forward).
+// No kernel lives here: the functions below only sequence the launch functions of the other translation units and
+// carve temporaries out of the caller's workspace (the same code runs "dry" to size that workspace).
+#include "common.cuh"
+#include "../../include/rdm_sm100.h"
+
+namespace {
+struct Arena {
+  char* base;
+  size_t cap, off, peak;
+  bool dry;
+  Arena(void* p, size_t n, bool d) : base((char*)p), cap(n), off(0), peak(0), dry(d) {}
+  float* f(size_t count) { return (float*)raw(count * sizeof(float)); }
+  void* raw(size_t bytes) {
+    off = align_up(off, 256);
+    void* r = dry ? nullptr : (void*)(base + off);
+    off += bytes;
+    if (off > peak) peak = off;
+    return r;
+  }
+  bool ok() const { return dry || peak <= cap; }
+};
+
+#define RDM_TRY(call)          \
+  do {                         \
+    int _rc = (call);          \
+    if (_rc != RDM_OK) return _rc; \
+  } while (0)
+
+int linear(Arena& a, const float* A, int lda, const float* W, int ldw, int nk, const float* bias, float* C, int M, int N, int K,
+           cudaStream_t st) {
+  void* ws = nullptr;
+  size_t wsb = 0;
+  size_t mark = a.off;
+  if ((long long)M * N <= (1 << 20)) {
+    wsb = rdm_linear_workspace(M, N, K);
+    ws = a.raw(wsb);
+  }
+  int rc = RDM_OK;
+  if (!a.dry) rc = rdm_linear(A, lda, W, ldw, nk, bias, C, N, M, N, K, 0, ws, wsb, st);
+  a.off = mark;
+  return rc;
+}
+
+int group_norm(Arena& a, float* x, const float* g, const float* b, const float* residual, int N, int C, int groups, int act,
+               cudaStream_t st) {
+  size_t mark = a.off;
+  double* stats = (double*)a.raw(sizeof(double) * 2 * groups);
+  int rc = RDM_OK;
+  if (!a.dry) rc = rdm_groupnorm(x, g, b, residual, x, N, C, groups, 1e-5f, act, 0.1f, stats, st);
+  a.off = mark;
+  return rc;
+}
+
+// UnaryBlock (kpconv/modules.py:78-83): Linear + GroupNorm (+ residual) (+ LeakyReLU); out [M, c_out]
+int unary(Arena& a, const rdm_unary_desc& u, const float* x, int ldx, float* out, int M, int groups, const float* residual, int act,
+          cudaStream_t st) {
+  RDM_TRY(linear(a, x, ldx, u.w, u.c_in, 1, u.b, out, M, u.c_out, u.c_in, st));
+  if (u.gn_w != nullptr) RDM_TRY(group_norm(a, out, u.gn_w, u.gn_b, residual, M, u.c_out, groups, act, st));
+  return RDM_OK;
+}
+
+// KPConv.forward (kpconv.py:79-122) + norm_conv + LeakyReLU: out [M, c_mid_out]
+int kpconv_norm(Arena& a, const rdm_block_desc& b, const float* feats, const float* q_pts, const float* s_pts, const void* idx,
+                int index_bytes, int M, int N, int H, float* out, int groups, cudaStream_t st) {
+  size_t mark = a.off;
+  float* gathered = a.f((size_t)M * 15 * b.c_mid_in);
+  unsigned char* rowpos = (unsigned char*)a.raw((size_t)(N > 0 ? N : 1));
+  if (!a.dry)
+    RDM_TRY(rdm_kpconv_gather(feats, q_pts, s_pts, idx, index_bytes, b.kernel_points, b.h_kernel_points, b.sigma, M, N, H,
+                              b.c_mid_in, gathered, rowpos, st));
+  const int prof = a.dry ? -1 : rdm_prof_begin(RDM_PROF_KPCONV_GEMM, M, 15 * b.c_mid_in, 0, b.c_mid_out, st);
+  RDM_TRY(linear(a, gathered, 15 * b.c_mid_in, b.kpconv_w, b.c_mid_out, 0, b.kpconv_b, out, M, b.c_mid_out, 15 * b.c_mid_in, st));
+  rdm_prof_end(prof, st);
+  RDM_TRY(group_norm(a, out, b.norm_conv_w, b.norm_conv_b, nullptr, M, b.c_mid_out, groups, 1, st));
+  a.off = mark;
+  return RDM_OK;
+}
+
+int encoder_run(Arena& a, const rdm_block_desc* blocks, int nb, const rdm_pyramid_desc& p, int groups, const float* in_feats,
+                float* const* out_feats, cudaStream_t st) {
+  const float* cur = in_feats;
+  int cur_stage = 0;
+  for (int i = 0; i < nb; i++) {
+    const rdm_block_desc& b = blocks[i];
+    const int s = b.stage;
+    RDM_CHECK_ARG(s >= 0 && s < p.num_stages && (b.strided ? s == cur_stage + 1 : s == cur_stage), "rdm_encoder_forward: block %d stage", i);
+    const int M = p.n[s], N = b.strided ? p.n[s - 1] : p.n[s];
+    const float* q_pts = p.points[s];
+    const float* s_pts = b.strided ? p.points[s - 1] : p.points[s];
+    const void* idx = b.strided ? p.subsampling[s - 1] : p.neighbors[s];
+    const int H = b.strided ? p.sub_width[s - 1] : p.nb_width[s];
+    const bool last_of_stage = (i + 1 == nb) || (blocks[i + 1].stage != s);
+    float* out = last_of_stage ? (a.dry ? nullptr : out_feats[s]) : a.f((size_t)M * b.c_out);
+    size_t mark = a.off;
+    if (b.unary2.w == nullptr) {  // ConvBlock (modules.py:143-147)
+      RDM_TRY(kpconv_norm(a, b, cur, q_pts, s_pts, idx, p.index_bytes, M, N, H, out, groups, st));
+    } else {  // ResidualBlock (modules.py:205-225)
+      const float* x = cur;
+      if (b.unary1.w != nullptr) {
+        float* t = a.f((size_t)N * b.unary1.c_out);
+        RDM_TRY(unary(a, b.unary1, cur, b.c_in, t, N, groups, nullptr, 1, st));
+        x = t;
+      }
+      float* c = a.f((size_t)M * b.c_mid_out);
+      RDM_TRY(kpconv_norm(a, b, x, q_pts, s_pts, idx, p.index_bytes, M, N, H, c, groups, st));
+      const float* sc = cur;
+      if (b.strided) {
+        float* mp = a.f((size_t)M * b.c_in);
+        if (!a.dry) RDM_TRY(rdm_maxpool(cur, idx, p.index_bytes, M, N, H, b.c_in, mp, st));
+        sc = mp;
+      }
+      if (b.shortcut.w != nullptr) {
+        float* t = a.f((size_t)M * b.c_out);
+        RDM_TRY(unary(a, b.shortcut, sc, b.c_in, t, M, groups, nullptr, 0, st));
+        sc = t;
+      }
+      RDM_TRY(unary(a, b.unary2, c, b.c_mid_out, out, M, groups, sc, 1, st));
+    }
+    a.off = mark;
+    cur = out;
+    cur_stage = s;
+  }
+  return RDM_OK;
+}
+
+int decoder_run(Arena& a, const rdm_unary_desc* dec, int num, const rdm_pyramid_desc& p, int top, int groups, const float* coarse,
+                int c_coarse, const float* const* skips, float* out, cudaStream_t st) {
+  const float* x = coarse;
+  int cx = c_coarse;
+  for (int i = 0; i < num; i++) {
+    const int s = top - 1 - i;  // target stage
+    RDM_CHECK_ARG(s >= 0, "rdm_decoder_forward: too many levels");
+    const int M = p.n[s], N = p.n[s + 1];
+    const int c_skip = dec[i].c_in - cx;
+    RDM_CHECK_ARG(c_skip >= 0, "rdm_decoder_forward: channel mismatch at level %d", i);
+    float* cat = a.f((size_t)M * dec[i].c_in);
+    if (!a.dry)
+      RDM_TRY(rdm_upsample_concat(x, p.upsampling[s], p.index_bytes, p.up_width[s], c_skip ? skips[i] : nullptr, M, N, cx, c_skip,
+                                  cat, st));
+    float* y = (i + 1 == num) ? out : a.f((size_t)M * dec[i].c_out);
+    RDM_TRY(unary(a, dec[i], cat, dec[i].c_in, y, M, groups, nullptr, 1, st));
+    x = y;
+    cx = dec[i].c_out;
+  }
+  return RDM_OK;
+}
+
+int thdroformer_run(Arena& a, const rdm_thdroformer_desc& d, const float* rp, int n0, const float* sp, int n1, const float* rf,
+                    int ld0, const float* sf, int ld1, float* o0, float* o1, cudaStream_t st) {
+  const int D = 128;
+  float* e0 = a.f((size_t)n0 * 64);
+  float* e1 = a.f((size_t)n1 * 64);
+  float* f0 = a.f((size_t)n0 * D);
+  float* f1 = a.f((size_t)n1 * D);
+  float* g0 = a.f((size_t)n0 * D);
+  float* g1 = a.f((size_t)n1 * D);
+  float *q0 = a.f((size_t)n0 * D), *v0 = a.f((size_t)n0 * D), *q1 = a.f((size_t)n1 * D), *v1 = a.f((size_t)n1 * D);
+  const int ldk0 = (n0 + 3) / 4 * 4, ldk1 = (n1 + 3) / 4 * 4;
+  float *k0 = a.f((size_t)D * ldk0), *k1 = a.f((size_t)D * ldk1);
+  RDM_TRY(linear(a, rp, 3, d.emb_w, 3, 1, d.emb_b, e0, n0, 64, 3, st));
+  RDM_TRY(linear(a, sp, 3, d.emb_w, 3, 1, d.emb_b, e1, n1, 64, 3, st));
+  RDM_TRY(linear(a, rf, ld0, d.in_w, d.c_in, 1, d.in_b, f0, n0, D, d.c_in, st));
+  RDM_TRY(linear(a, sf, ld1, d.in_w, d.c_in, 1, d.in_b, f1, n1, D, d.c_in, st));
+  const size_t WQ = 0, WK = 128 * 128, WV = 2 * 128 * 128, BQ = 4 * 128 * 128 + 2 * 128 * 256, BK = BQ + 128, BV = BQ + 256;
+  auto pj = [](const float* x, const float* blob, size_t w, size_t b, const float* emb, float* y, int n, int ldy_t) {
+    rdm_tf_proj_job j;
+    j.x = x; j.wt = blob + w; j.bias = blob + b; j.emb = emb; j.y = y; j.n = n; j.ldx = 128; j.lde = 64; j.ldy_t = ldy_t;
+    return j;
+  };
+  auto aj = [](const float* q, const float* k, const float* v, const float* x, const float* blob, float* out, int nq, int nk, int ldk) {
+    rdm_tf_attn_job j;
+    j.q = q; j.k = k; j.v = v; j.x = x; j.blob = blob; j.out = out; j.nq = nq; j.nk = nk; j.ldx = 128; j.ldk_t = ldk;
+    return j;
+  };
+  for (int l = 0; l < (a.dry ? 0 : d.num_layers); l++) {
+    const float* B = d.layer_blobs[l];
+    if (d.is_self[l]) {
+      rdm_tf_proj_job pjs[6] = {pj(f0, B, WQ, BQ, e0, q0, n0, 0), pj(f0, B, WK, BK, e0, k0, n0, ldk0), pj(f0, B, WV, BV, nullptr, v0, n0, 0),
+                                pj(f1, B, WQ, BQ, e1, q1, n1, 0), pj(f1, B, WK, BK, e1, k1, n1, ldk1), pj(f1, B, WV, BV, nullptr, v1, n1, 0)};
+      RDM_TRY(rdm_tf_project(pjs, 6, st));
+      rdm_tf_attn_job ajs[2] = {aj(q0, k0, v0, f0, B, g0, n0, n0, ldk0), aj(q1, k1, v1, f1, B, g1, n1, n1, ldk1)};
+      RDM_TRY(rdm_tf_attend(ajs, 2, st));
+      float* t = f0; f0 = g0; g0 = t;
+      t = f1; f1 = g1; g1 = t;
+    } else {  // sequential cross attention (thdroformer.py:244-245)
+      rdm_tf_proj_job p1[3] = {pj(f0, B, WQ, BQ, nullptr, q0, n0, 0), pj(f1, B, WK, BK, nullptr, k1, n1, ldk1), pj(f1, B, WV, BV, nullptr, v1, n1, 0)};
+      RDM_TRY(rdm_tf_project(p1, 3, st));
+      rdm_tf_attn_job a1[1] = {aj(q0, k1, v1, f0, B, g0, n0, n1, ldk1)};
+      RDM_TRY(rdm_tf_attend(a1, 1, st));
+      float* t = f0; f0 = g0; g0 = t;
+      rdm_tf_proj_job p2[3] = {pj(f1, B, WQ, BQ, nullptr, q1, n1, 0), pj(f0, B, WK, BK, nullptr, k0, n0, ldk0), pj(f0, B, WV, BV, nullptr, v0, n0, 0)};
+      RDM_TRY(rdm_tf_project(p2, 3, st));
+      rdm_tf_attn_job a2[1] = {aj(q1, k0, v0, f1, B, g1, n1, n0, ldk0)};
+      RDM_TRY(rdm_tf_attend(a2, 1, st));
+      t = f1; f1 = g1; g1 = t;
+    }
+  }
+  RDM_TRY(linear(a, f0, D, d.out_w, D, 1, d.out_b, o0, n0, d.c_out, D, st));
+  RDM_TRY(linear(a, f1, D, d.out_w, D, 1, d.out_b, o1, n1, d.c_out, D, st));
+  return RDM_OK;
+}
+}  // namespace
+
+extern "C" size_t rdm_encoder_workspace(const rdm_block_desc* h_blocks, int num_blocks, const rdm_pyramid_desc* h_pyr, int groups) {
+  Arena a(nullptr, 0, true);
+  float* outs[8] = {nullptr};
+  if (encoder_run(a, h_blocks, num_blocks, *h_pyr, groups, nullptr, outs, 0) != RDM_OK) return 0;
+  return a.peak + 4096;
+}
+
+extern "C" int rdm_encoder_forward(const rdm_block_desc* h_blocks, int num_blocks, const rdm_pyramid_desc* h_pyr, int groups,
+                                   const float* in_feats, float* const* h_out_feats, void* workspace, size_t workspace_bytes,
+                                   cudaStream_t stream) {
+  RDM_CHECK_ARG(h_blocks && h_pyr && h_out_feats && num_blocks >= 1 && h_pyr->num_stages >= 1 && h_pyr->num_stages <= 8,
+                "rdm_encoder_forward: bad arguments");
+  const size_t need = rdm_encoder_workspace(h_blocks, num_blocks, h_pyr, groups);
+  if (need == 0 || workspace_bytes < need) {
+    rdm_set_error("rdm_encoder_forward: workspace too small (%zu needed)", need);
+    return RDM_ERR_WORKSPACE;
+  }
+  Arena a(workspace, workspace_bytes, false);
+  return encoder_run(a, h_blocks, num_blocks, *h_pyr, groups, in_feats, h_out_feats, stream);
+}
+
+extern "C" size_t rdm_decoder_workspace(const rdm_unary_desc* h_dec, int num, const rdm_pyramid_desc* h_pyr, int top_stage, int groups) {
+  Arena a(nullptr, 0, true);
+  const float* skips[8] = {nullptr};
+  int cc = h_dec[0].c_in;  // dry run: channel split does not change the sizes
+  if (decoder_run(a, h_dec, num, *h_pyr, top_stage, groups, nullptr, cc, skips, nullptr, 0) != RDM_OK) return 0;
+  return a.peak + 4096;
+}
+
+extern "C" int rdm_decoder_forward(const rdm_unary_desc* h_dec, int num, const rdm_pyramid_desc* h_pyr, int top_stage, int groups,
+                                   const float* coarse, int c_coarse, const float* const* h_skips, float* out, void* workspace,
+                                   size_t workspace_bytes, cudaStream_t stream) {
+  RDM_CHECK_ARG(h_dec && h_pyr && h_skips && num >= 1 && num <= 7, "rdm_decoder_forward: bad arguments");
+  Arena a(workspace, workspace_bytes, false);
+  // size check first: the arena hands out pointers past the end otherwise
+  {
+    Arena d(nullptr, 0, true);
+    int rc = decoder_run(d, h_dec, num, *h_pyr, top_stage, groups, nullptr, c_coarse, h_skips, nullptr, 0);
+    if (rc != RDM_OK) return rc;
+    if (d.peak > workspace_bytes) {
+      rdm_set_error("rdm_decoder_forward: workspace too small (%zu needed)", d.peak);
+      return RDM_ERR_WORKSPACE;
+    }
+  }
+  return decoder_run(a, h_dec, num, *h_pyr, top_stage, groups, coarse, c_coarse, h_skips, out, stream);
+}
+
+extern "C" size_t rdm_thdroformer_workspace(int n_ref, int n_src, int c_out) {
+  Arena a(nullptr, 0, true);
+  rdm_thdroformer_desc d = {};
+  d.c_in = 128;  // the scratch does not depend on c_in
+  d.c_out = c_out;
+  thdroformer_run(a, d, nullptr, n_ref, nullptr, n_src, nullptr, 0, nullptr, 0, nullptr, nullptr, 0);
+  return a.peak + 4096;
+}
+
+extern "C" int rdm_thdroformer_forward(const rdm_thdroformer_desc* h_desc, const float* ref_points, int n_ref,
+                                       const float* src_points, int n_src, const float* ref_feats, int ld_ref,
+                                       const float* src_feats, int ld_src, float* out_ref, float* out_src, void* workspace,
+                                       size_t workspace_bytes, cudaStream_t stream) {
+  RDM_CHECK_ARG(h_desc && n_ref >= 1 && n_src >= 1 && h_desc->num_layers >= 0 && h_desc->num_layers <= 32,
+                "rdm_thdroformer_forward: bad arguments");
+  if (workspace_bytes < rdm_thdroformer_workspace(n_ref, n_src, h_desc->c_out)) {
+    rdm_set_error("rdm_thdroformer_forward: workspace too small");
+    return RDM_ERR_WORKSPACE;
+  }
+  Arena a(workspace, workspace_bytes, false);
+  return thdroformer_run(a, *h_desc, ref_points, n_ref, src_points, n_src, ref_feats, ld_ref, src_feats, ld_src, out_ref, out_src,
+                         stream);
+}

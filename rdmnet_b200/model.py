@@ -10,11 +10,13 @@ Differences from the reference that are part of the design (none changes results
   * NMS, partition, Sinkhorn and the pose solver run without host round trips; the only host syncs left are the
     data-dependent output shapes (pyramid lengths, NMS survivors, number of correspondences).
 """
+import ctypes
 import types
 
 import torch
 import torch.nn as nn
 
+from . import _lib as L
 from . import ops
 from .modules import (ConvBlock, LastUnaryBlock, LearnableLogOptimalTransport, LocalGlobalRegistration, NMS,
                       ResidualBlock, SuperPointMatching, ThDRoFormer, UnaryBlock, Vote_layer)
@@ -97,6 +99,54 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
     }
 
 
+def _state_key(module):
+    return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _unary_desc(u):
+    """rdm_unary_desc of a UnaryBlock / LastUnaryBlock (NULL weight for nn.Identity / None)."""
+    if u is None or isinstance(u, nn.Identity):
+        return L.UnaryDesc()
+    norm = getattr(u, "norm", None)
+    return L.UnaryDesc(_p(u.mlp.weight), _p(u.mlp.bias), _p(norm.norm.weight) if norm is not None else None,
+                       _p(norm.norm.bias) if norm is not None else None, u.mlp.in_features, u.mlp.out_features)
+
+
+def pyramid_desc(data_dict, lengths_host):
+    """rdm_pyramid_desc over a data_dict (ours or the reference's). Returns (desc, keepalive tensors)."""
+    d = L.PyramidDesc()
+    pts, nb, sub, up = data_dict["points"], data_dict["neighbors"], data_dict["subsampling"], data_dict["upsampling"]
+    keep, dtypes = [], set()
+
+    def table(t):
+        t = t.contiguous()
+        keep.append(t)
+        dtypes.add(t.dtype)
+        return t
+
+    d.num_stages = len(pts)
+    for s in range(len(pts)):
+        p = pts[s].contiguous()
+        keep.append(p)
+        d.points[s], d.n[s] = p.data_ptr(), int(sum(lengths_host[s]))
+        t = table(nb[s])
+        d.neighbors[s], d.nb_width[s] = t.data_ptr(), t.shape[1]
+        if s < len(pts) - 1:
+            t = table(sub[s])
+            d.subsampling[s], d.sub_width[s] = t.data_ptr(), t.shape[1]
+            if up[s] is not None:
+                t = table(up[s])
+                d.upsampling[s], d.up_width[s] = t.data_ptr(), t.shape[1]
+    if len(dtypes) != 1 or next(iter(dtypes)) not in (torch.int32, torch.int64):
+        raise RuntimeError("neighbour tables must all be int64 or all be int32")
+    d.index_bytes = 8 if next(iter(dtypes)) == torch.int64 else 4
+    return d, keep
+
+
 class Encoder(nn.Module):
     """experiments/backbone.py:7-107."""
 
@@ -118,7 +168,56 @@ class Encoder(nn.Module):
         self.encoder5_2 = ResidualBlock(d * 16, d * 32, k, r * 16, s * 16, g)
         self.encoder5_3 = ResidualBlock(d * 32, d * 32, k, r * 16, s * 16, g)
 
-    def forward(self, feats, data_dict):
+    def _block_descs(self):
+        """rdm_block_desc array of the 14 blocks (cached until a parameter changes)."""
+        key = _state_key(self)
+        if getattr(self, "_desc_key", None) != key:
+            names = ["encoder1_1", "encoder1_2"] + [f"encoder{s}_{j}" for s in range(2, 6) for j in (1, 2, 3)]
+            arr = (L.BlockDesc * len(names))()
+            keep = []
+            for i, name in enumerate(names):
+                b, stage = getattr(self, name), int(name[7]) - 1
+                kp = b.KPConv
+                hk = ops._host_copy(kp.kernel_points)
+                keep.append(hk)
+                d = arr[i]
+                if isinstance(b, ConvBlock):
+                    d.norm_conv_w, d.norm_conv_b = _p(b.norm.norm.weight), _p(b.norm.norm.bias)
+                    d.c_in, d.c_out, d.strided = b.in_channels, b.out_channels, 0
+                else:
+                    d.unary1, d.unary2, d.shortcut = _unary_desc(b.unary1), _unary_desc(b.unary2), _unary_desc(b.unary_shortcut)
+                    d.norm_conv_w, d.norm_conv_b = _p(b.norm_conv.norm.weight), _p(b.norm_conv.norm.bias)
+                    d.c_in, d.c_out, d.strided = b.in_channels, b.out_channels, 1 if b.strided else 0
+                d.kpconv_w, d.kpconv_b = _p(kp.weights), _p(kp.bias)
+                d.kernel_points, d.h_kernel_points = _p(kp.kernel_points), hk.data_ptr()
+                d.c_mid_in, d.c_mid_out, d.stage, d.sigma = kp.in_channels, kp.out_channels, stage, float(kp.sigma)
+            self._descs, self._desc_keep, self._desc_key = arr, keep, key
+        return self._descs
+
+    def forward(self, feats, data_dict, pyr=None):
+        """One host call for the 14 blocks (rdm_encoder_forward). Returns the 5 stage outputs."""
+        blocks = self._block_descs()
+        if pyr is None:
+            lh = data_dict.get("lengths_host") or [l.tolist() for l in data_dict["lengths"]]
+            pyr = pyramid_desc(data_dict, lh)
+        desc, _keep = pyr
+        dev = feats.device
+        last = {}
+        for d in blocks:
+            last[d.stage] = d.c_out
+        outs = [torch.empty((desc.n[s], last[s]), dtype=torch.float32, device=dev) for s in range(desc.num_stages)]
+        out_ptrs = (ctypes.c_void_p * 8)(*[o.data_ptr() for o in outs])
+        lib = L.lib()
+        wsb = lib.rdm_encoder_workspace(ctypes.cast(blocks, ctypes.c_void_p), len(blocks), ctypes.byref(desc), 32)
+        ws = torch.empty(max(int(wsb), 1), dtype=torch.uint8, device=dev)
+        feats = feats.contiguous()
+        L.call("rdm_encoder_forward", ctypes.cast(blocks, ctypes.c_void_p), len(blocks), ctypes.byref(desc),
+               self.encoder1_1.norm.num_groups, L.ptr(feats), ctypes.cast(out_ptrs, ctypes.c_void_p), L.ptr(ws), int(wsb),
+               L.stream())
+        return outs
+
+    def forward_modules(self, feats, data_dict):
+        """The same wiring through the per-block Python modules (used by the module-level parity tests)."""
         P, NB, SUB = data_dict["points"], data_dict["neighbors"], data_dict["subsampling"]
         out = []
         x = self.encoder1_1(feats, P[0], P[0], NB[0])
@@ -141,7 +240,29 @@ class Decoder(nn.Module):
         self.decoder3 = UnaryBlock(init_dim * 24, init_dim * 8, group_norm)
         self.decoder2 = LastUnaryBlock(init_dim * 12, output_dim + 1)
 
-    def forward(self, feats, data_dict):
+    def forward(self, feats, data_dict, pyr=None):
+        """rdm_decoder_forward: three (nearest upsample || skip -> unary) levels in one host call. Returns [l2]."""
+        key = _state_key(self)
+        if getattr(self, "_desc_key", None) != key:
+            arr = (L.UnaryDesc * 3)(_unary_desc(self.decoder4), _unary_desc(self.decoder3), _unary_desc(self.decoder2))
+            self._descs, self._desc_key = arr, key
+        if pyr is None:
+            lh = data_dict.get("lengths_host") or [l.tolist() for l in data_dict["lengths"]]
+            pyr = pyramid_desc(data_dict, lh)
+        desc, _keep = pyr
+        coarse = feats[4].contiguous()
+        skips = [feats[3].contiguous(), feats[2].contiguous(), feats[1].contiguous()]
+        skip_ptrs = (ctypes.c_void_p * 8)(*[t.data_ptr() for t in skips])
+        out = torch.empty((desc.n[1], self.decoder2.out_channels), dtype=torch.float32, device=coarse.device)
+        lib = L.lib()
+        wsb = lib.rdm_decoder_workspace(ctypes.cast(self._descs, ctypes.c_void_p), 3, ctypes.byref(desc), 4, 32)
+        ws = torch.empty(max(int(wsb), 1), dtype=torch.uint8, device=coarse.device)
+        L.call("rdm_decoder_forward", ctypes.cast(self._descs, ctypes.c_void_p), 3, ctypes.byref(desc), 4,
+               self.decoder4.norm.num_groups, L.ptr(coarse), coarse.shape[1], ctypes.cast(skip_ptrs, ctypes.c_void_p),
+               L.ptr(out), L.ptr(ws), int(wsb), L.stream())
+        return [out]
+
+    def forward_modules(self, feats, data_dict):
         UP = data_dict["upsampling"]
         l4 = self.decoder4(ops.nearest_upsample_concat(feats[4], UP[3], feats[3]))
         l3 = self.decoder3(ops.nearest_upsample_concat(l4, UP[2], feats[2]))
@@ -189,10 +310,10 @@ class RDMNet(nn.Module):
         if "neighbors" not in data_dict:  # raw stacked points in: build the pyramid here, on the GPU
             data_dict = dict(data_dict)
             data_dict.update(self.build_pyramid(data_dict["points"], data_dict["lengths"]))
-        L = data_dict.get("lengths_host")
-        if L is None:
-            L = [l.tolist() for l in data_dict["lengths"]]
-        nc, nf, n0 = int(L[-1][0]), int(L[1][0]), int(L[0][0])
+        L_host = data_dict.get("lengths_host")
+        if L_host is None:
+            L_host = [l.tolist() for l in data_dict["lengths"]]
+        nc, nf, n0 = int(L_host[-1][0]), int(L_host[1][0]), int(L_host[0][0])
         points_c, points_f, points = data_dict["points"][-1], data_dict["points"][1], data_dict["points"][0]
         feats = data_dict.get("features")
         if feats is None:
@@ -202,7 +323,8 @@ class RDMNet(nn.Module):
         out["ref_points_f"], out["src_points_f"] = ref_points_f, src_points_f
         out["ref_points"], out["src_points"] = points[:n0], points[n0:]
 
-        feats_list = self.encoder(feats, data_dict)
+        pyr = pyramid_desc(data_dict, L_host)
+        feats_list = self.encoder(feats, data_dict, pyr)
         feats_c = feats_list[-1]
         ref_feats_c, src_feats_c = self.transformer(points_c[:nc].contiguous(), points_c[nc:].contiguous(),
                                                     feats_c[:nc], feats_c[nc:])
@@ -210,7 +332,7 @@ class RDMNet(nn.Module):
         n2p_logit = ops.linear(tf, self.proj_n2p_score.weight, self.proj_n2p_score.bias)  # (Nc,1)
         n2p = ops.activation(n2p_logit.view(-1), 3)
         feats_list[-1] = torch.cat([tf, n2p_logit], 1)
-        dec = self.decoder(feats_list, data_dict)[0]
+        dec = self.decoder(feats_list, data_dict, pyr)[0]
         feats_f = dec[:, :-1].contiguous()
         p2p = ops.activation(dec[:, -1].contiguous(), 3)
         out["ref_p2p_scores_c"], out["src_p2p_scores_c"] = p2p[:nf], p2p[nf:]

@@ -344,6 +344,10 @@ class ThDRoFormer(nn.Module):
             if ref_feats.shape[0] != 1:
                 raise RuntimeError("ThDRoFormer processes one pair per call (as the reference: thdroformer.py:76)")
             ref_points, src_points, ref_feats, src_feats = ref_points[0], src_points[0], ref_feats[0], src_feats[0]
+        tr = self.transformer
+        if all(layer.fusable() for layer in tr.layers) and ref_feats.shape[0] > 0 and src_feats.shape[0] > 0:
+            f0, f1 = self._forward_runner(ref_points.contiguous(), src_points.contiguous(), ref_feats, src_feats)
+            return (f0[None], f1[None]) if batched else (f0, f1)
         e0, e1 = self.embedding(ref_points.contiguous()), self.embedding(src_points.contiguous())
         f0 = ops.linear(ref_feats, self.in_proj.weight, self.in_proj.bias)
         f1 = ops.linear(src_feats, self.in_proj.weight, self.in_proj.bias)
@@ -351,6 +355,37 @@ class ThDRoFormer(nn.Module):
         f0 = ops.linear(f0, self.out_proj.weight, self.out_proj.bias)
         f1 = ops.linear(f1, self.out_proj.weight, self.out_proj.bias)
         return (f0[None], f1[None]) if batched else (f0, f1)
+
+
+    def _forward_runner(self, rp, sp, rf, sf):
+        """rdm_thdroformer_forward: embedding, in_proj, all fused layers and out_proj in one host call."""
+        import ctypes
+        L = ops.L
+        tr = self.transformer
+        blobs = [layer.fused_blob() for layer in tr.layers]
+        key = tuple(b.data_ptr() for b in blobs) + tuple((p.data_ptr(), p._version) for p in (
+            self.embedding.proj.weight, self.embedding.proj.bias, self.in_proj.weight, self.in_proj.bias,
+            self.out_proj.weight, self.out_proj.bias))
+        if getattr(self, "_desc_key", None) != key:
+            d = L.ThdroformerDesc()
+            d.emb_w, d.emb_b = self.embedding.proj.weight.data_ptr(), self.embedding.proj.bias.data_ptr()
+            d.in_w, d.in_b = self.in_proj.weight.data_ptr(), self.in_proj.bias.data_ptr()
+            d.out_w, d.out_b = self.out_proj.weight.data_ptr(), self.out_proj.bias.data_ptr()
+            for i, (b, kind) in enumerate(zip(blobs, tr.blocks)):
+                d.layer_blobs[i], d.is_self[i] = b.data_ptr(), 1 if kind == "self" else 0
+            d.num_layers, d.c_in, d.c_out = len(blobs), self.in_proj.in_features, self.out_proj.out_features
+            self._desc, self._desc_key = d, key
+        d = self._desc
+        if rf.stride(1) != 1 or sf.stride(1) != 1 or rf.shape[1] != d.c_in:
+            raise RuntimeError("ThDRoFormer: feature tensors must be (N, input_dim) with contiguous channels")
+        n0, n1, dev = rf.shape[0], sf.shape[0], rf.device
+        o0 = torch.empty((n0, d.c_out), dtype=torch.float32, device=dev)
+        o1 = torch.empty((n1, d.c_out), dtype=torch.float32, device=dev)
+        wsb = L.lib().rdm_thdroformer_workspace(n0, n1, d.c_out)
+        ws = torch.empty(int(wsb), dtype=torch.uint8, device=dev)
+        L.call("rdm_thdroformer_forward", ctypes.byref(d), L.ptr(rp), n0, L.ptr(sp), n1, rf.data_ptr(), rf.stride(0),
+               sf.data_ptr(), sf.stride(0), L.ptr(o0), L.ptr(o1), L.ptr(ws), int(wsb), L.stream())
+        return o0, o1
 
 
 # ------------------------------------------------------------------------------------------------- vote / NMS

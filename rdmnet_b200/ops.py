@@ -160,18 +160,10 @@ def kpconv(s_feats, q_points, s_points, neighbor_indices, weights, kernel_points
     dev = s_feats.device
     gathered = torch.empty((m, kk * c), dtype=torch.float32, device=dev)
     rowpos = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
-    timer = L.TIMER
-    e0 = timer.start() if timer is not None else None
     L.call("rdm_kpconv_gather", L.ptr(s_feats), L.ptr(q_points), L.ptr(s_points), L.ptr(neighbor_indices),
-           _idx_bytes(neighbor_indices), L.ptr(kernel_points), _host_copy(kernel_points).data_ptr(), float(sigma), m, n, h, c, L.ptr(gathered), L.ptr(rowpos),
-           L.stream())
-    if timer is not None:
-        timer.stop("kpconv_gather", e0, kpconv_gather_bytes(m, h, c, cout, _idx_bytes(neighbor_indices)), (m, n, h, c, cout))
-        e0 = timer.start()
-    out = linear(gathered, weights.reshape(kk * c, cout), bias, weight_is_kn=True)
-    if timer is not None:
-        timer.stop("kpconv_weight_gemm", e0, 0, (m, kk * c, cout))
-    return out
+           _idx_bytes(neighbor_indices), L.ptr(kernel_points), _host_copy(kernel_points).data_ptr(), float(sigma), m, n, h, c,
+           L.ptr(gathered), L.ptr(rowpos), L.stream())
+    return linear(gathered, weights.reshape(kk * c, cout), bias, weight_is_kn=True)
 
 
 def kpconv_gather_bytes(m, h, c_in, c_out, index_bytes, feat_bytes=4):
