@@ -34,6 +34,8 @@ const char* rdm_last_error(void);
 int rdm_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py reports the delta as gpu_launches) */
 unsigned long long rdm_launch_count(void);
+/* how many of those were tensor-core GEMMs (tcgen05 kind::tf32, 3-term split): lets tests assert the path taken */
+unsigned long long rdm_tc_gemm_count(void);
 
 /* optional kernel timing: after rdm_prof_enable(1) the library brackets selected launches with CUDA events on the launch
  * stream; rdm_prof_read synchronises those events and returns the records. tag 1 = KPConv gather (row_positive prepass +
@@ -166,6 +168,7 @@ typedef struct {
 typedef struct {
   rdm_unary_desc unary1, unary2, shortcut;
   const float* kpconv_w;          /* [15, c_mid, c_mid'] */
+  const float* kpconv_wt;         /* optional: the same weights as [c_mid', 15*c_mid] (nn.Linear layout, tensor-core GEMM) */
   const float* kpconv_b;          /* [c_mid'] or NULL */
   const float* kernel_points;     /* [15,3] device */
   const float* h_kernel_points;   /* the same 45 floats, host */

@@ -15,6 +15,7 @@ SIGNATURES = {
     "rdm_last_error": (ctypes.c_char_p, []),
     "rdm_version": (c_int, []),
     "rdm_launch_count": (ctypes.c_ulonglong, []),
+    "rdm_tc_gemm_count": (ctypes.c_ulonglong, []),
     "rdm_prof_enable": (None, [c_int]),
     "rdm_prof_read": (c_int, [c_void_p, c_int]),
     "rdm_grid_subsample_workspace": (c_size_t, [c_i64, c_int]),
@@ -82,7 +83,7 @@ class UnaryDesc(ctypes.Structure):
 
 class BlockDesc(ctypes.Structure):
     _fields_ = [("unary1", UnaryDesc), ("unary2", UnaryDesc), ("shortcut", UnaryDesc), ("kpconv_w", c_void_p),
-                ("kpconv_b", c_void_p), ("kernel_points", c_void_p), ("h_kernel_points", c_void_p),
+                ("kpconv_wt", c_void_p), ("kpconv_b", c_void_p), ("kernel_points", c_void_p), ("h_kernel_points", c_void_p),
                 ("norm_conv_w", c_void_p), ("norm_conv_b", c_void_p), ("c_in", c_int), ("c_mid_in", c_int),
                 ("c_mid_out", c_int), ("c_out", c_int), ("strided", c_int), ("stage", c_int), ("sigma", c_float)]
 

@@ -3,6 +3,7 @@
 //
 // Reference semantics: torch.nn.Linear; geotransformer/modules/kpconv/modules.py:33-50 (GroupNorm over (1,C,N), eps 1e-5,
 // statistics joint over both clouds), :78-83, :205-225 (residual + LeakyReLU(0.1)); torch.nn.LayerNorm (eps 1e-5).
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/rdm_sm100.h"
 
@@ -199,10 +200,28 @@ extern "C" size_t rdm_linear_workspace(int M, int N, int K) {
   return (size_t)16 * M * N * sizeof(float) + 256;
 }
 
+int rdm_linear_tc(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N, int K,
+                  int act, void* workspace, size_t workspace_bytes, int* out_splits, cudaStream_t stream);  // gemm_tc.cu
+
 extern "C" int rdm_linear(const float* A, int lda, const float* B, int ldb, int b_is_nk, const float* bias, float* C,
                           int ldc, int M, int N, int K, int act, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   RDM_CHECK_ARG(M >= 0 && N >= 1 && K >= 1, "rdm_linear: bad shape M=%d N=%d K=%d", M, N, K);
   if (M == 0) return RDM_OK;
+  // tensor-core path (tcgen05 kind::tf32, 3-term split, fp32-level accuracy) for nn.Linear-layout weights
+  static int use_tc = -1;
+  if (use_tc < 0) {
+    const char* e = getenv("RDM_GEMM_TC");  // debug knob: RDM_GEMM_TC=0 forces the SIMT kernel
+    use_tc = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (use_tc && b_is_nk && M >= 64) {
+    int tc_splits = 1;
+    int rc = rdm_linear_tc(A, lda, B, ldb, bias, C, ldc, M, N, K, act, workspace, workspace_bytes, &tc_splits, stream);
+    if (rc == RDM_OK && tc_splits > 1) {
+      splitk_reduce_kernel<<<cdiv((long long)M * N, 256), 256, 0, stream>>>((const float*)workspace, tc_splits, bias, C, ldc, M, N, act);
+      RDM_LAUNCH_CHECK();
+    }
+    if (rc != -1) return rc;
+  }
   int vecA = (lda % 4 == 0) && aligned16(A), vecB = (ldb % 4 == 0) && aligned16(B), vecC = (ldc % 4 == 0) && aligned16(C);
   long long t128 = (long long)cdiv(M, 128) * cdiv(N, 128), t64 = (long long)cdiv(M, 64) * cdiv(N, 64);
   bool big = t128 >= 120;

@@ -1,0 +1,322 @@
+// fp32-accurate tensor-core GEMM for sm_100a: C[M,N] = act(A[M,K] * B[N,K]^T + bias), A and B fp32 row-major.
+//
+// The dense contractions of the backbone (UnaryBlock / decoder Linear layers, the KPConv weight contraction
+// (M x 15C) * (15C x C'), in_proj of the transformers) are ~100 GFLOP per pair; on the SIMT fp32 path they were ~30 % of
+// the GPU time. This kernel runs them on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in
+// TMEM) while keeping fp32-level accuracy with the 3-term split  a*b ~= ah*bh + ah*bl + al*bh  (ah = tf32(a),
+// al = tf32(a - ah)): the north-star tolerance is 1e-4 on features, which a single TF32 pass (2^-11) does not meet.
+//
+// CTA = 192 threads, one 128 x BN output tile, K blocks of 32 floats (one 128-byte swizzle atom):
+//   warp 0     TMA producer: cp.async.bulk.tensor loads of the raw fp32 A / B tiles (SWIZZLE_128B), mbarrier tx-count
+//   warps 2-5  split the landed tile in place into hi (same buffer) and lo (second buffer) - an element-wise pass
+//              at identical offsets, so the swizzle is preserved - then fence.proxy.async and arrive
+//   warp 1     one elected lane issues 3 x 4 tcgen05.mma (M128 x N x K8) per K block and tcgen05.commit's the
+//              stage back to the producer; the last commit signals the epilogue
+//   warps 2-5  epilogue: tcgen05.ld 32x32b (each warp its 32 TMEM lanes), + bias, activation, 128-bit stores
+// All waits are bounded spins that trap, so a protocol bug aborts the kernel instead of hanging the GPU.
+#include <cuda.h>
+#include "common.cuh"
+#include "../../include/rdm_sm100.h"
+
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;  // floats = 128 bytes
+constexpr int TC_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a broken pipeline aborts instead of hanging
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  // K-major, SWIZZLE_128B: start>>4 | LBO=1 (unused) | SBO = 1024 B (8 rows x 128 B) | version 1 (sm_100) | layout 2
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+template <int BN, int STAGES>
+struct TcSmem {
+  // every buffer is a multiple of 1024 B: the 128-byte swizzle pattern repeats every 8 rows
+  float a_hi[STAGES][TC_BM * TC_BK];
+  float a_lo[STAGES][TC_BM * TC_BK];
+  float b_hi[STAGES][BN * TC_BK];
+  float b_lo[STAGES][BN * TC_BK];
+  uint64_t raw_full[STAGES], conv_full[STAGES], empty[STAGES], accum_full;
+  uint32_t tmem_base;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                   const __grid_constant__ CUtensorMap map_b,
+                                                                   const float* __restrict__ bias, float* __restrict__ C,
+                                                                   int ldc, int M, int N, int K, int act, int kb_per_split) {
+  extern __shared__ unsigned char smem_raw[];
+  using Smem = TcSmem<BN, STAGES>;
+  Smem& sm = *reinterpret_cast<Smem*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  // split-K: blockIdx.z owns K blocks [kb0, kb0 + nk) and writes a raw partial tile to C + z*M*N (ldc == N there)
+  const int nk_total = (K + TC_BK - 1) / TC_BK;
+  const int kb0 = blockIdx.z * kb_per_split;
+  const int nk = min(kb_per_split, nk_total - kb0);
+  if (gridDim.z > 1) C += (size_t)blockIdx.z * M * N;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&sm.raw_full[s], 1);
+      mbar_init(&sm.conv_full[s], 128);
+      mbar_init(&sm.empty[s], 1);
+    }
+    mbar_init(&sm.accum_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: BN fp32 accumulator columns (power of two >= 32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      constexpr uint32_t bytes = (TC_BM + BN) * TC_BK * sizeof(float);
+      for (int kb = 0; kb < nk; kb++) {
+        const int s = kb % STAGES;
+        mbar_wait(&sm.empty[s], ((kb / STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&sm.raw_full[s], bytes);
+        tma_load_2d(sm.a_hi[s], &map_a, &sm.raw_full[s], (kb0 + kb) * TC_BK, m0);
+        tma_load_2d(sm.b_hi[s], &map_b, &sm.raw_full[s], (kb0 + kb) * TC_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      // kind::tf32, D = f32, A/B = tf32 K-major, N>>3 at bit 17, M>>4 at bit 24
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int kb = 0; kb < nk; kb++) {
+        const int s = kb % STAGES;
+        mbar_wait(&sm.conv_full[s], (kb / STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t dah = umma_desc_sw128(smem_u32(sm.a_hi[s])), dal = umma_desc_sw128(smem_u32(sm.a_lo[s]));
+        const uint64_t dbh = umma_desc_sw128(smem_u32(sm.b_hi[s])), dbl = umma_desc_sw128(smem_u32(sm.b_lo[s]));
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; k++) {
+          const uint64_t adv = (uint64_t)(k * 32 / 16);  // 8 tf32 = 32 bytes along K inside the swizzle atom
+          umma_tf32(tmem, dal + adv, dbh + adv, idesc, (kb | k) != 0);
+          umma_tf32(tmem, dah + adv, dbl + adv, idesc, 1);
+          umma_tf32(tmem, dah + adv, dbh + adv, idesc, 1);
+        }
+        umma_commit(&sm.empty[s]);  // frees the stage when these MMAs have read it
+      }
+      umma_commit(&sm.accum_full);
+    }
+  } else {
+    // ===== converters, then epilogue =====
+    const int t = threadIdx.x - 64;  // 0..127
+    for (int kb = 0; kb < nk; kb++) {
+      const int s = kb % STAGES;
+      mbar_wait(&sm.raw_full[s], (kb / STAGES) & 1);
+      float4* ah = reinterpret_cast<float4*>(sm.a_hi[s]);
+      float4* al = reinterpret_cast<float4*>(sm.a_lo[s]);
+#pragma unroll
+      for (int i = 0; i < TC_BM * TC_BK / 4 / 128; i++) {
+        const float4 v = ah[t + i * 128];
+        const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+        ah[t + i * 128] = h;
+        al[t + i * 128] = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+      }
+      float4* bh = reinterpret_cast<float4*>(sm.b_hi[s]);
+      float4* bl = reinterpret_cast<float4*>(sm.b_lo[s]);
+#pragma unroll
+      for (int i = 0; i < BN * TC_BK / 4 / 128; i++) {
+        const float4 v = bh[t + i * 128];
+        const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+        bh[t + i * 128] = h;
+        bl[t + i * 128] = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the UMMA reads
+      mbar_arrive(&sm.conv_full[s]);
+    }
+    mbar_wait(&sm.accum_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = m0 + q * 32 + lane;
+    float* crow = C + (size_t)row * ldc;
+    const bool vec = (ldc % 4 == 0) && (((uintptr_t)C & 15) == 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < M) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int col = n0 + c0 + j;
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            v[e] = __uint_as_float(r[j + e]);
+            if (bias != nullptr && col + e < N) v[e] += __ldg(bias + col + e);
+            if (act == 1) v[e] = v[e] > 0.f ? v[e] : 0.1f * v[e];
+            else if (act == 2) v[e] = fmaxf(v[e], 0.f);
+          }
+          if (vec && col + 3 < N) {
+            *reinterpret_cast<float4*>(crow + col) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+              if (col + e < N) crow[col + e] = v[e];
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN));
+  }
+}
+
+// ---- host side: tensor maps through the driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int g_encode_state = 0;  // 0 unknown, 1 ok, -1 unavailable
+
+bool load_encoder() {
+  if (g_encode_state == 0) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn != nullptr &&
+        qres == cudaDriverEntryPointSuccess) {
+      g_encode = (EncodeTiledFn)fn;
+      g_encode_state = 1;
+    } else {
+      g_encode_state = -1;
+    }
+  }
+  return g_encode_state == 1;
+}
+
+// row-major [rows, cols] fp32 with leading dimension ld (floats); box = 32 columns x box_rows, 128-byte swizzle,
+// out-of-bounds elements read as zero (K and M/N tails)
+bool make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+unsigned long long g_tc_launches = 0;
+
+template <int BN, int STAGES>
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, float* C, int ldc, int M, int N, int K, int act,
+              int splits, int kb_per_split, cudaStream_t stream) {
+  const size_t smem = sizeof(TcSmem<BN, STAGES>) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    RDM_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  dim3 grid(cdiv(N, BN), cdiv(M, TC_BM), splits);
+  gemm_tf32x3_kernel<BN, STAGES><<<grid, TC_THREADS, smem, stream>>>(ma, mb, bias, C, ldc, M, N, K, act, kb_per_split);
+  RDM_LAUNCH_CHECK();
+  __atomic_fetch_add(&g_tc_launches, 1ull, __ATOMIC_RELAXED);
+  return RDM_OK;
+}
+}  // namespace
+
+// Returns RDM_OK if the GEMM was launched on the tensor-core path, -1 if the shape / alignment does not qualify (the
+// caller then uses the SIMT kernel), or an error code. With a workspace, small-tile-count problems are split along K into
+// partial tiles (deterministic: `*out_splits` partials that the caller reduces with bias / activation).
+int rdm_linear_tc(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N, int K,
+                  int act, void* workspace, size_t workspace_bytes, int* out_splits, cudaStream_t stream) {
+  *out_splits = 1;
+  if (M < 1 || N < 8 || K < 8) return -1;
+  if ((lda % 4) || (ldb % 4) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) return -1;  // TMA: 16-byte strides / base
+  if (!load_encoder()) return -1;
+  const bool narrow = N <= 64 || (long long)cdiv(M, TC_BM) * cdiv(N, 128) < 148;  // prefer more CTAs when few tiles
+  const int BN = narrow ? 64 : 128;
+  const long long tiles = (long long)cdiv(M, TC_BM) * cdiv(N, BN);
+  const int nk = cdiv(K, TC_BK);
+  int splits = 1;
+  if (workspace != nullptr && tiles < 120 && nk >= 16) {
+    splits = (int)min((long long)16, (296 + tiles - 1) / tiles);
+    splits = min(splits, nk / 8);
+    while (splits > 1 && (size_t)splits * M * N * sizeof(float) > workspace_bytes) splits--;
+  }
+  const int kps = cdiv(nk, splits);
+  splits = cdiv(nk, kps);
+  CUtensorMap ma, mb;
+  if (!make_map(&ma, A, M, K, lda, TC_BM)) return -1;
+  if (!make_map(&mb, B, N, K, ldb, BN)) return -1;
+  *out_splits = splits;
+  float* out = splits > 1 ? (float*)workspace : C;
+  const int ldo = splits > 1 ? N : ldc;
+  const float* b = splits > 1 ? nullptr : bias;
+  const int a = splits > 1 ? 0 : act;
+  if (narrow) return launch_tc<64, 4>(ma, mb, b, out, ldo, M, N, K, a, splits, kps, stream);
+  return launch_tc<128, 3>(ma, mb, b, out, ldo, M, N, K, a, splits, kps, stream);
+}
+
+extern "C" unsigned long long rdm_tc_gemm_count(void) { return __atomic_load_n(&g_tc_launches, __ATOMIC_RELAXED); }

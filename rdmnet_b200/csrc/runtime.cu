@@ -73,7 +73,10 @@ int kpconv_norm(Arena& a, const rdm_block_desc& b, const float* feats, const flo
     RDM_TRY(rdm_kpconv_gather(feats, q_pts, s_pts, idx, index_bytes, b.kernel_points, b.h_kernel_points, b.sigma, M, N, H,
                               b.c_mid_in, gathered, rowpos, st));
   const int prof = a.dry ? -1 : rdm_prof_begin(RDM_PROF_KPCONV_GEMM, M, 15 * b.c_mid_in, 0, b.c_mid_out, st);
-  RDM_TRY(linear(a, gathered, 15 * b.c_mid_in, b.kpconv_w, b.c_mid_out, 0, b.kpconv_b, out, M, b.c_mid_out, 15 * b.c_mid_in, st));
+  if (b.kpconv_wt != nullptr)
+    RDM_TRY(linear(a, gathered, 15 * b.c_mid_in, b.kpconv_wt, 15 * b.c_mid_in, 1, b.kpconv_b, out, M, b.c_mid_out, 15 * b.c_mid_in, st));
+  else
+    RDM_TRY(linear(a, gathered, 15 * b.c_mid_in, b.kpconv_w, b.c_mid_out, 0, b.kpconv_b, out, M, b.c_mid_out, 15 * b.c_mid_in, st));
   rdm_prof_end(prof, st);
   RDM_TRY(group_norm(a, out, b.norm_conv_w, b.norm_conv_b, nullptr, M, b.c_mid_out, groups, 1, st));
   a.off = mark;

@@ -188,7 +188,9 @@ class Encoder(nn.Module):
                     d.unary1, d.unary2, d.shortcut = _unary_desc(b.unary1), _unary_desc(b.unary2), _unary_desc(b.unary_shortcut)
                     d.norm_conv_w, d.norm_conv_b = _p(b.norm_conv.norm.weight), _p(b.norm_conv.norm.bias)
                     d.c_in, d.c_out, d.strided = b.in_channels, b.out_channels, 1 if b.strided else 0
-                d.kpconv_w, d.kpconv_b = _p(kp.weights), _p(kp.bias)
+                wt = kp.weights.detach().reshape(-1, kp.out_channels).t().contiguous()  # [C_out, 15*C_in]
+                keep.append(wt)
+                d.kpconv_w, d.kpconv_wt, d.kpconv_b = _p(kp.weights), _p(wt), _p(kp.bias)
                 d.kernel_points, d.h_kernel_points = _p(kp.kernel_points), hk.data_ptr()
                 d.c_mid_in, d.c_mid_out, d.stage, d.sigma = kp.in_channels, kp.out_channels, stage, float(kp.sigma)
             self._descs, self._desc_keep, self._desc_key = arr, keep, key

@@ -29,7 +29,8 @@ def make_neighbors(rng, m, n, h, fill=0.7):
                                        (842, 512, 7680, False), (5000, 64, 480, False), (2236, 1024, 1281, True),
                                        (130, 130, 37, False), (1, 259, 256, True)])
 def test_linear(m, n, k, nk):
-    from rdmnet_b200 import ops
+    from rdmnet_b200 import ops, _lib
+    tc0 = _lib.lib().rdm_tc_gemm_count()
     torch.manual_seed(m + n + k)
     x = torch.randn(m, k)
     w = torch.randn(n, k) / k ** 0.5 if nk else torch.randn(k, n) / k ** 0.5
@@ -39,6 +40,26 @@ def test_linear(m, n, k, nk):
     close(got, ref, 2e-5)
     got = ops.linear(x.cuda(), w.cuda(), None, weight_is_kn=not nk)
     close(got, ref - b, 2e-5)
+    # nn.Linear-layout weights with 16-byte row strides run on the tensor cores (tcgen05 tf32 x3), the rest on SIMT
+    expect_tc = nk and m >= 64 and n >= 8 and k % 4 == 0
+    assert (_lib.lib().rdm_tc_gemm_count() - tc0 == 2) == expect_tc
+
+
+@pytest.mark.parametrize("m,n,k", [(23319, 32, 64), (23319, 128, 32), (8841, 64, 960), (494, 512, 7680), (494, 2048, 512),
+                                   (431, 128, 2048), (3078, 257, 768), (129, 72, 40)])
+def test_linear_tensor_core_shapes(m, n, k):
+    """The GEMM shapes of the backbone on the tcgen05 path (split-K included) vs an fp64 reference."""
+    from rdmnet_b200 import ops, _lib
+    torch.manual_seed(m + n + k)
+    x = torch.randn(m, k)
+    w = torch.randn(n, k) / k ** 0.5
+    b = torch.randn(n)
+    ref = (x.double() @ w.double().t() + b.double()).float()
+    tc0 = _lib.lib().rdm_tc_gemm_count()
+    for act in (0, 1):
+        got = ops.linear(x.cuda(), w.cuda(), b.cuda(), act=act)
+        close(got, torch.nn.functional.leaky_relu(ref, 0.1) if act else ref, 2e-5)
+    assert _lib.lib().rdm_tc_gemm_count() - tc0 == 2
 
 
 @pytest.mark.parametrize("cin,cout,m,n,h,idt", [(1, 64, 500, 500, 33, torch.int64), (32, 32, 700, 900, 65, torch.int64),
