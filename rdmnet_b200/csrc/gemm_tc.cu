@@ -71,10 +71,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+// round-to-nearest (ties away) to tf32 precision with two integer ops on the bit pattern: same result as
+// cvt.rna.tf32.f32 for finite values, but on the full-rate ALU pipe instead of the conversion unit
+__device__ __forceinline__ float to_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+
+// r[j] for a runtime j without spilling the array to local memory (only the ragged-N tail path uses it)
+__device__ __forceinline__ uint32_t sel32(const uint32_t (&r)[32], int j) {
+  uint32_t v = r[0];
+#pragma unroll
+  for (int i = 1; i < 32; i++) v = (j == i) ? r[i] : v;
+  return v;
 }
 
 template <int BN, int STAGES>
@@ -92,22 +98,30 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                    const __grid_constant__ CUtensorMap map_b,
                                                                    const float* __restrict__ bias, float* __restrict__ C,
-                                                                   int ldc, int M, int N, int K, int act, int kb_per_split) {
+                                                                   int ldc, int M, int N, int K, int act, int kb_per_split,
+                                                                   long long* __restrict__ dbg) {
   extern __shared__ unsigned char smem_raw[];
   using Smem = TcSmem<BN, STAGES>;
   Smem& sm = *reinterpret_cast<Smem*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
   // split-K: blockIdx.z owns K blocks [kb0, kb0 + nk) and writes a raw partial tile to C + z*M*N (ldc == N there)
+#define TC_STAMP(i)                                                        \
+  do {                                                                     \
+    if (dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) dbg[i] = clock64(); \
+  } while (0)
+  if (threadIdx.x == 0) TC_STAMP(0);
   const int nk_total = (K + TC_BK - 1) / TC_BK;
   const int kb0 = blockIdx.z * kb_per_split;
   const int nk = min(kb_per_split, nk_total - kb0);
   if (gridDim.z > 1) C += (size_t)blockIdx.z * M * N;
 
   if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");  // hide the descriptor fetch behind the set-up
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < STAGES; s++) {
       mbar_init(&sm.raw_full[s], 1);
-      mbar_init(&sm.conv_full[s], 128);
+      mbar_init(&sm.conv_full[s], 4);  // one arrival per converter warp
       mbar_init(&sm.empty[s], 1);
     }
     mbar_init(&sm.accum_full, 1);
@@ -121,6 +135,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const __grid
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = sm.tmem_base;
+  if (threadIdx.x == 0) TC_STAMP(1);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -132,6 +147,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const __grid
         mbar_arrive_expect_tx(&sm.raw_full[s], bytes);
         tma_load_2d(sm.a_hi[s], &map_a, &sm.raw_full[s], (kb0 + kb) * TC_BK, m0);
         tma_load_2d(sm.b_hi[s], &map_b, &sm.raw_full[s], (kb0 + kb) * TC_BK, n0);
+        if (kb == 0) TC_STAMP(2);
       }
     }
   } else if (warp == 1) {
@@ -142,6 +158,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const __grid
       for (int kb = 0; kb < nk; kb++) {
         const int s = kb % STAGES;
         mbar_wait(&sm.conv_full[s], (kb / STAGES) & 1);
+        if (kb == 0) TC_STAMP(4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t dah = umma_desc_sw128(smem_u32(sm.a_hi[s])), dal = umma_desc_sw128(smem_u32(sm.a_lo[s]));
         const uint64_t dbh = umma_desc_sw128(smem_u32(sm.b_hi[s])), dbl = umma_desc_sw128(smem_u32(sm.b_lo[s]));
@@ -162,6 +179,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const __grid
     for (int kb = 0; kb < nk; kb++) {
       const int s = kb % STAGES;
       mbar_wait(&sm.raw_full[s], (kb / STAGES) & 1);
+      if (kb == 0 && t == 0) TC_STAMP(3);
       float4* ah = reinterpret_cast<float4*>(sm.a_hi[s]);
       float4* al = reinterpret_cast<float4*>(sm.a_lo[s]);
 #pragma unroll
@@ -181,16 +199,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const __grid
         bl[t + i * 128] = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the UMMA reads
-      mbar_arrive(&sm.conv_full[s]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.conv_full[s]);
     }
+    if (t == 0) TC_STAMP(5);
     mbar_wait(&sm.accum_full, 0);
+    if (t == 0) TC_STAMP(6);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int row = m0 + q * 32 + lane;
     float* crow = C + (size_t)row * ldc;
-    const bool vec = (ldc % 4 == 0) && (((uintptr_t)C & 15) == 0);
+    const bool aligned = (ldc % 4 == 0) && (((uintptr_t)C & 15) == 0) && (((uintptr_t)bias & 15) == 0);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
+      const bool fast = aligned && (n0 + c0 + 32 <= N);
       uint32_t r[32];
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
       asm volatile(
@@ -204,30 +226,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const __grid
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (row < M) {
+        if (fast) {  // whole 32-column slab inside N, 16-byte aligned rows: float4 bias, float4 stores, no per-element checks
+          const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c0);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int col = n0 + c0 + j;
-          float v[4];
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            v[e] = __uint_as_float(r[j + e]);
-            if (bias != nullptr && col + e < N) v[e] += __ldg(bias + col + e);
-            if (act == 1) v[e] = v[e] > 0.f ? v[e] : 0.1f * v[e];
-            else if (act == 2) v[e] = fmaxf(v[e], 0.f);
+          for (int j = 0; j < 8; j++) {
+            float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                   __uint_as_float(r[4 * j + 3]));
+            if (bias != nullptr) {
+              const float4 b = __ldg(b4 + j);
+              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
+            if (act == 1) {
+              v.x = v.x > 0.f ? v.x : 0.1f * v.x; v.y = v.y > 0.f ? v.y : 0.1f * v.y;
+              v.z = v.z > 0.f ? v.z : 0.1f * v.z; v.w = v.w > 0.f ? v.w : 0.1f * v.w;
+            } else if (act == 2) {
+              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(crow + n0 + c0 + 4 * j) = v;
           }
-          if (vec && col + 3 < N) {
-            *reinterpret_cast<float4*>(crow + col) = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; e++)
-              if (col + e < N) crow[col + e] = v[e];
+        } else {
+#pragma unroll 1
+          for (int j = 0; j < 32; j++) {
+            const int col = n0 + c0 + j;
+            if (col >= N) break;
+            float v = __uint_as_float(sel32(r, j));
+            if (bias != nullptr) v += __ldg(bias + col);
+            if (act == 1) v = v > 0.f ? v : 0.1f * v;
+            else if (act == 2) v = fmaxf(v, 0.f);
+            crow[col] = v;
           }
         }
       }
     }
   }
+  if (threadIdx.x == 64) TC_STAMP(7);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (threadIdx.x == 0) TC_STAMP(8);
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN));
@@ -271,7 +306,7 @@ unsigned long long g_tc_launches = 0;
 
 template <int BN, int STAGES>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, float* C, int ldc, int M, int N, int K, int act,
-              int splits, int kb_per_split, cudaStream_t stream) {
+              int splits, int kb_per_split, cudaStream_t stream, long long* dbg = nullptr) {
   const size_t smem = sizeof(TcSmem<BN, STAGES>) + 1024;
   static bool attr = false;
   if (!attr) {
@@ -279,7 +314,7 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, f
     attr = true;
   }
   dim3 grid(cdiv(N, BN), cdiv(M, TC_BM), splits);
-  gemm_tf32x3_kernel<BN, STAGES><<<grid, TC_THREADS, smem, stream>>>(ma, mb, bias, C, ldc, M, N, K, act, kb_per_split);
+  gemm_tf32x3_kernel<BN, STAGES><<<grid, TC_THREADS, smem, stream>>>(ma, mb, bias, C, ldc, M, N, K, act, kb_per_split, dbg);
   RDM_LAUNCH_CHECK();
   __atomic_fetch_add(&g_tc_launches, 1ull, __ATOMIC_RELAXED);
   return RDM_OK;
@@ -295,7 +330,12 @@ int rdm_linear_tc(const float* A, int lda, const float* B, int ldb, const float*
   if (M < 1 || N < 8 || K < 8) return -1;
   if ((lda % 4) || (ldb % 4) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) return -1;  // TMA: 16-byte strides / base
   if (!load_encoder()) return -1;
-  const bool narrow = N <= 64 || (long long)cdiv(M, TC_BM) * cdiv(N, 128) < 148;  // prefer more CTAs when few tiles
+  // 128-wide tiles move 1.5x fewer shared-memory bytes per flop (the limiter of the 3-term split); use them when they
+  // still fill the machine, possibly with the help of split-K
+  const int nk_all = cdiv(K, TC_BK);
+  const long long t128 = (long long)cdiv(M, TC_BM) * cdiv(N, 128);
+  const bool can_split = workspace != nullptr && nk_all >= 16;
+  const bool narrow = N <= 64 || (t128 < 100 && !(can_split && t128 * min(16, nk_all / 8) >= 100));
   const int BN = narrow ? 64 : 128;
   const long long tiles = (long long)cdiv(M, TC_BM) * cdiv(N, BN);
   const int nk = cdiv(K, TC_BK);
@@ -320,3 +360,33 @@ int rdm_linear_tc(const float* A, int lda, const float* B, int ldb, const float*
 }
 
 extern "C" unsigned long long rdm_tc_gemm_count(void) { return __atomic_load_n(&g_tc_launches, __ATOMIC_RELAXED); }
+
+// debug: clock64 timeline of CTA (0,0,0) of one narrow-tile GEMM on scratch buffers (prints cycles since CTA start)
+extern "C" int rdm_debug_gemm_timeline(int M, int N, int K) {
+  if (!load_encoder()) return -1;
+  float *A, *B, *C;
+  long long* dbg;
+  RDM_CUDA(cudaMalloc(&A, (size_t)M * K * 4));
+  RDM_CUDA(cudaMalloc(&B, (size_t)N * K * 4));
+  RDM_CUDA(cudaMalloc(&C, (size_t)M * N * 4));
+  RDM_CUDA(cudaMalloc(&dbg, 16 * 8));
+  RDM_CUDA(cudaMemset(A, 0, (size_t)M * K * 4));
+  RDM_CUDA(cudaMemset(B, 0, (size_t)N * K * 4));
+  CUtensorMap ma, mb;
+  if (!make_map(&ma, A, M, K, K, TC_BM) || !make_map(&mb, B, N, K, K, 64)) return -1;
+  for (int rep = 0; rep < 3; rep++) {
+    RDM_CUDA(cudaMemset(dbg, 0, 16 * 8));
+    int rc = launch_tc<64, 4>(ma, mb, nullptr, C, N, M, N, K, 0, 1, cdiv(K, TC_BK), 0, dbg);
+    if (rc != RDM_OK) return rc;
+    RDM_CUDA(cudaDeviceSynchronize());
+    long long h[16];
+    RDM_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    printf("gemm timeline M%d N%d K%d rep%d:", M, N, K, rep);
+    const char* names[9] = {"start", "init+alloc", "tma0 issued", "raw0 landed", "conv0 done(mma)", "conv all done", "accum ready",
+                            "stores done", "final sync"};
+    for (int i = 1; i < 9; i++) printf("  %s=%lld", names[i], h[i] - h[0]);
+    printf("\n");
+  }
+  cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(dbg);
+  return RDM_OK;
+}

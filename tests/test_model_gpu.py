@@ -88,10 +88,13 @@ def test_forward_stages_vs_oracle(model, scans, pretrained_state):
     assert np.array_equal(out["mask"].cpu().numpy(), ref["nms_masks"].numpy())
     close(out["ref_feats_c"], ref["ref_feats_c"], 5e-4, "ref_feats_c")
     close(out["ref_feats_f"], ref["feats_f"][:out["ref_feats_f"].shape[0]], 5e-4, "feats_f")
-    # knn tables: the node coordinates fed to the partition are GPU-computed (vote MLP, equal to ~1e-6), so squared
-    # distances that tie EXACTLY in the oracle may differ by an ulp here: rows must hold the same point sets, and
-    # positions may differ only inside runs of oracle distances that agree to 1e-5 relative
+    # knn tables: the node coordinates fed to the partition are GPU-computed (vote MLP: equal to the oracle's within
+    # eps_pos, far inside the 1e-4 relative tolerance), so squared distances that tie in the oracle may order
+    # differently here: rows must hold the same point sets, and positions may differ only between points whose
+    # oracle distances are closer than the bound that position error allows, |d2_i - d2_j| <= 4 sqrt(d2) eps_pos
     perms = {}
+    eps_pos = max((out[f"{s_}_points_c"].cpu() - ref[f"{s_}_points_c"]).abs().max().item() for s_ in ("ref", "src"))
+    assert eps_pos <= 1e-3
     for side, npts in (("ref", out["ref_points_f"].shape[0]), ("src", out["src_points_f"].shape[0])):
         got_k, ref_k = out[f"{side}_node_knn_indices"].cpu().numpy(), ref[f"{side}_node_knn_indices"].numpy()
         nodes, pts = ref[f"{side}_points_c"], out[f"{side}_points_f"].cpu()
@@ -101,7 +104,8 @@ def test_forward_stages_vs_oracle(model, scans, pretrained_state):
             j = int(np.nonzero(got_k[n] == ref_k[n, i])[0][0])
             di = MO.pairwise_distance(nodes[n:n + 1], pts[ref_k[n, i]][None])[0, 0].item()
             dj = MO.pairwise_distance(nodes[n:n + 1], pts[ref_k[n, j]][None])[0, 0].item()
-            assert abs(di - dj) <= 1e-5 * di, f"{side} knn order differs outside a near-tie: node {n} cols {i},{j}"
+            assert abs(di - dj) <= 4 * max(di, dj) ** 0.5 * eps_pos + 1e-5 * di, \
+                f"{side} knn order differs outside a near-tie: node {n} cols {i},{j}: {di} {dj} eps_pos {eps_pos}"
             perm[n, i] = j
         perms[side] = perm
     assert np.array_equal(out["ref_node_corr_indices"].cpu().numpy(), ref["ref_node_corr_indices"].numpy())
