@@ -79,6 +79,7 @@ int rdm_radius_search(const float* q_points, const float* s_points, const int64_
  * the kernel takes them by value in its parameter bank). rowpos_scratch: N bytes. */
 int rdm_kpconv_gather(const float* s_feats, const float* q_points, const float* s_points, const void* neighbor_indices,
                       int index_bytes, const float* kernel_points, const float* h_kernel_points, float sigma, int M, int N, int H, int C_in,
+                      const int* query_order /* optional permutation of 0..M-1: walk order, see rdm_pyramid_desc.order */,
                       float* out_weighted, unsigned char* rowpos_scratch, rdm_stream_t stream);
 
 /* ---- maxpool (geotransformer/modules/kpconv/functional.py:54-67) */
@@ -183,7 +184,32 @@ typedef struct {
   const void* upsampling[8];    /* [n[s], up_width[s]] (indices into stage s+1) */
   int n[8], nb_width[8], sub_width[8], up_width[8];
   int num_stages, index_bytes;
+  const int* order[8];          /* optional per stage: a permutation of 0..n[s]-1, the order in which the KPConv gather
+                                 * walks the queries of stage s (spatially coherent => neighbour rows hit in L1); results
+                                 * do not depend on it. NULL = index order. */
 } rdm_pyramid_desc;
+/* rdm_build_pyramid = precompute_data_stack_mode (geotransformer/utils/data.py:13-77) in ONE host call: the
+ * (num_stages-1) grid subsamplings chained on the device, ONE internal stream synchronisation to learn the
+ * data-dependent stage sizes (the only entry point that synchronises), then every radius search at its exact size.
+ * Tables are int32, fixed width = the stage's neighbour limit (a row narrower than the limit is padded: same KPConv /
+ * max-pool results as the reference's max_count-wide table). skip_up0: upsampling[0] is not built (the reference
+ * builds it and never reads it, experiments/backbone.py:144). up_nearest_only: upsampling tables hold only column 0,
+ * the nearest coarse point - all nearest_upsample reads (geotransformer/modules/kpconv/functional.py:6-22).
+ * out_buf (device, rdm_build_pyramid_bytes) receives stage lengths, points, tables and per-stage cell orders;
+ * h_desc gets the pointers; h_lengths [num_stages*batch] the per-cloud stage sizes; h_d_lengths[s] the device int64
+ * [batch] length vectors. points/lengths are stage 0 and are referenced, not copied. */
+typedef struct {
+  int num_stages, batch;
+  float first_voxel;   /* voxel of the first subsampling (2 * init_voxel_size) */
+  float first_radius;  /* search radius of stage 0 */
+  int limits[8];
+  int skip_up0, up_nearest_only;
+} rdm_pyramid_cfg;
+size_t rdm_build_pyramid_bytes(int64_t n0, const rdm_pyramid_cfg* h_cfg);
+size_t rdm_build_pyramid_workspace(int64_t n0, const rdm_pyramid_cfg* h_cfg);
+int rdm_build_pyramid(const float* points, const int64_t* lengths, int64_t n0, const rdm_pyramid_cfg* h_cfg, void* out_buf,
+                      size_t out_bytes, void* workspace, size_t workspace_bytes, rdm_pyramid_desc* h_desc,
+                      int64_t* h_lengths, const int64_t** h_d_lengths, rdm_stream_t stream);
 size_t rdm_encoder_workspace(const rdm_block_desc* h_blocks, int num_blocks, const rdm_pyramid_desc* h_pyr, int groups);
 int rdm_encoder_forward(const rdm_block_desc* h_blocks, int num_blocks, const rdm_pyramid_desc* h_pyr, int groups,
                         const float* in_feats, float* const* h_out_feats, void* workspace, size_t workspace_bytes,
@@ -210,8 +236,11 @@ int rdm_thdroformer_forward(const rdm_thdroformer_desc* h_desc, const float* ref
                             int n_src, const float* ref_feats, int ld_ref, const float* src_feats, int ld_src,
                             float* out_ref, float* out_src, void* workspace, size_t workspace_bytes, rdm_stream_t stream);
 
-/* ---- NMS.forward greedy loop (rdmnet/vote/vote.py:33-40) over a radius-search table [N,H] (H <= 128). */
-int rdm_nms(const void* neighbor_indices, int index_bytes, int N, int H, unsigned char* out_mask, rdm_stream_t stream);
+/* ---- NMS.forward greedy loop (rdmnet/vote/vote.py:33-40) over a radius-search table [N,H]. out_mask [N] (0/1).
+ * Optional: out_selected [N] receives the selected indices in ascending order, out_counts[0] / [1] how many of them
+ * are < split / >= split (split = number of ref nodes: the two boolean-mask selections of model.py:233-236). */
+int rdm_nms(const void* neighbor_indices, int index_bytes, int N, int H, int split, unsigned char* out_mask,
+            int64_t* out_selected, int* out_counts, rdm_stream_t stream);
 
 /* ---- point_to_node_partition (geotransformer/modules/ops/pointcloud_partition.py:60-107). */
 size_t rdm_point_to_node_workspace(int num_points, int num_nodes);

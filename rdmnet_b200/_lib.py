@@ -24,8 +24,12 @@ SIGNATURES = {
     "rdm_radius_search_workspace": (c_size_t, [c_i64, c_int]),
     "rdm_radius_search": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_float, c_int,
                                   c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "rdm_build_pyramid_bytes": (c_size_t, [c_i64, c_void_p]),
+    "rdm_build_pyramid_workspace": (c_size_t, [c_i64, c_void_p]),
+    "rdm_build_pyramid": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
     "rdm_kpconv_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_int,
-                                  c_int, c_void_p, c_void_p, c_void_p]),
+                                  c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdm_maxpool": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "rdm_upsample_concat": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "rdm_linear_workspace": (c_size_t, [c_int, c_int, c_int]),
@@ -49,7 +53,7 @@ SIGNATURES = {
     "rdm_thdroformer_workspace": (c_size_t, [c_int, c_int, c_int]),
     "rdm_thdroformer_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                         c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "rdm_nms": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "rdm_nms": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdm_point_to_node_workspace": (c_size_t, [c_int, c_int]),
     "rdm_point_to_node": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_size_t, c_void_p]),
@@ -91,7 +95,12 @@ class BlockDesc(ctypes.Structure):
 class PyramidDesc(ctypes.Structure):
     _fields_ = [("points", c_void_p * 8), ("neighbors", c_void_p * 8), ("subsampling", c_void_p * 8),
                 ("upsampling", c_void_p * 8), ("n", c_int * 8), ("nb_width", c_int * 8), ("sub_width", c_int * 8),
-                ("up_width", c_int * 8), ("num_stages", c_int), ("index_bytes", c_int)]
+                ("up_width", c_int * 8), ("num_stages", c_int), ("index_bytes", c_int), ("order", c_void_p * 8)]
+
+
+class PyramidCfg(ctypes.Structure):
+    _fields_ = [("num_stages", c_int), ("batch", c_int), ("first_voxel", c_float), ("first_radius", c_float),
+                ("limits", c_int * 8), ("skip_up0", c_int), ("up_nearest_only", c_int)]
 
 
 class ThdroformerDesc(ctypes.Structure):

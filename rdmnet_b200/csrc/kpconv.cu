@@ -42,10 +42,11 @@ __global__ void __launch_bounds__(256) kpconv_gather_c1_kernel(const float* __re
                                                                const float* __restrict__ s_pts,
                                                                const IdxT* __restrict__ idx, const KPts kp,
                                                                float inv_sigma, int M, int N, int H,
-                                                               float* __restrict__ out) {
+                                                               const int* __restrict__ order, float* __restrict__ out) {
   const int lane = threadIdx.x & 31, t = lane & 7;
-  const int m = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4 + (lane >> 3);
-  const bool qvalid = m < M;
+  const int mi = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4 + (lane >> 3);
+  const bool qvalid = mi < M;
+  const int m = (qvalid && order != nullptr) ? order[mi] : mi;
   const int mm = qvalid ? m : M - 1;
   const float qx = q_pts[3 * (size_t)mm], qy = q_pts[3 * (size_t)mm + 1], qz = q_pts[3 * (size_t)mm + 2];
   float acc[KP_K];
@@ -230,6 +231,7 @@ __global__ void __launch_bounds__(128, VEC == 4 ? 4 : 7) kpconv_gather_v3_kernel
                                                                   const float* __restrict__ s_pts,
                                                                   const IdxT* __restrict__ idx, const KPts kp,
                                                                   float inv_sigma, int M, int N, int H, int C, int NS,
+                                                                  const int* __restrict__ order,
                                                                   float* __restrict__ out) {
   constexpr int G = 32 / L;
   constexpr int STEP = SPLIT ? 32 : L;  // neighbour slots per chunk (per query)
@@ -247,6 +249,7 @@ __global__ void __launch_bounds__(128, VEC == 4 ? 4 : 7) kpconv_gather_v3_kernel
   }
   const bool qvalid = m < M;
   if (__all_sync(FULL_MASK, !qvalid)) return;
+  if (qvalid && order != nullptr) m = order[m];  // spatially coherent walk: co-resident warps share neighbour rows
   const int mm = qvalid ? m : M - 1;
   const float qx = q_pts[3 * (size_t)mm], qy = q_pts[3 * (size_t)mm + 1], qz = q_pts[3 * (size_t)mm + 2];
   const IdxT* row = idx + (size_t)mm * H;
@@ -356,8 +359,8 @@ __global__ void __launch_bounds__(128, VEC == 4 ? 4 : 7) kpconv_gather_v3_kernel
 
 template <typename IdxT>
 static int launch_gather(const float* feats, const unsigned char* rowpos, const float* q, const float* s,
-                         const IdxT* idx, const float* kpts, const float* h_kpts, float sigma, int M, int N, int H, int C, float* out,
-                         cudaStream_t stream) {
+                         const IdxT* idx, const float* kpts, const float* h_kpts, float sigma, int M, int N, int H, int C,
+                         const int* order, float* out, cudaStream_t stream) {
   // the 15 kernel points travel by value in the kernel-parameter constant bank: `d - kp` costs no load
   KPts kp;
   for (int k = 0; k < KP_K; k++) {
@@ -367,7 +370,7 @@ static int launch_gather(const float* feats, const unsigned char* rowpos, const 
   }
   const float inv_sigma = 1.f / sigma;
   if (C == 1) {
-    kpconv_gather_c1_kernel<IdxT><<<cdiv(M, 32), 256, 0, stream>>>(feats, q, s, idx, kp, inv_sigma, M, N, H, out);
+    kpconv_gather_c1_kernel<IdxT><<<cdiv(M, 32), 256, 0, stream>>>(feats, q, s, idx, kp, inv_sigma, M, N, H, order, out);
     RDM_LAUNCH_CHECK();
     return RDM_OK;
   }
@@ -384,7 +387,7 @@ static int launch_gather(const float* feats, const unsigned char* rowpos, const 
 #define GATHER(Lv, SPLITv, VECv, warps, NSv)                                                                        \
   do {                                                                                                              \
     kpconv_gather_v3_kernel<Lv, SPLITv, VECv, IdxT><<<cdiv((long long)(warps), 4), 128, 0, stream>>>(               \
-        feats, rowpos, q, s, idx, kp, inv_sigma, M, N, H, C, (NSv), out);                                           \
+        feats, rowpos, q, s, idx, kp, inv_sigma, M, N, H, C, (NSv), order, out);                                           \
     RDM_LAUNCH_CHECK();                                                                                             \
     return RDM_OK;                                                                                                  \
   } while (0)
@@ -439,8 +442,8 @@ static int launch_gather(const float* feats, const unsigned char* rowpos, const 
 extern "C" int rdm_kpconv_gather(const float* s_feats, const float* q_points, const float* s_points,
                                  const void* neighbor_indices, int index_bytes, const float* kernel_points,
                                  const float* h_kernel_points, float sigma,
-                                 int M, int N, int H, int C_in, float* out_weighted, unsigned char* rowpos_scratch,
-                                 cudaStream_t stream) {
+                                 int M, int N, int H, int C_in, const int* query_order, float* out_weighted,
+                                 unsigned char* rowpos_scratch, cudaStream_t stream) {
   RDM_CHECK_ARG(M >= 0 && N >= 0 && H >= 1 && C_in >= 1 && sigma > 0.f, "rdm_kpconv_gather: bad arguments");
   RDM_CHECK_ARG(index_bytes == 4 || index_bytes == 8, "rdm_kpconv_gather: index_bytes must be 4 or 8");
   RDM_CHECK_ARG(kernel_points != nullptr && h_kernel_points != nullptr, "rdm_kpconv_gather: kernel points missing");
@@ -453,10 +456,10 @@ extern "C" int rdm_kpconv_gather(const float* s_feats, const float* q_points, co
   int rc;
   if (index_bytes == 8)
     rc = launch_gather<int64_t>(s_feats, rowpos_scratch, q_points, s_points, (const int64_t*)neighbor_indices,
-                                kernel_points, h_kernel_points, sigma, M, N, H, C_in, out_weighted, stream);
+                                kernel_points, h_kernel_points, sigma, M, N, H, C_in, query_order, out_weighted, stream);
   else
     rc = launch_gather<int>(s_feats, rowpos_scratch, q_points, s_points, (const int*)neighbor_indices, kernel_points,
-                            h_kernel_points, sigma, M, N, H, C_in, out_weighted, stream);
+                            h_kernel_points, sigma, M, N, H, C_in, query_order, out_weighted, stream);
   rdm_prof_end(prof, stream);
   return rc;
 }

@@ -13,57 +13,88 @@
 // ------------------------------------------------------------------------------------------------------ NMS
 // sel[i] = !any(sel[j] for j in nbrs(i)), i = 0..N-1 in order (sel starts all-false; entries >= N are the sentinel).
 // One warp walks the nodes sequentially; neighbour rows are prefetched PF rows at a time (they do not depend on sel).
-#define NMS_PF 8
-#define NMS_R 4  // ceil(H/32) <= 4  ->  H <= 128
+// Parallel fixpoint of the greedy rule. sel[i] = !any(sel[j], j in nbrs(i)) evaluated for i = 0..N-1 with sel initially
+// all False means: only neighbours j < i can matter, i is selected iff all of them are rejected, rejected iff one of
+// them is selected. That is a DAG in index order; every round settles the nodes whose earlier neighbours are all
+// settled (state only moves unknown -> final, so racing reads are harmless), and the result is exactly the sequential
+// one. Rounds needed = longest dependency chain (tens for spatial data) instead of N sequential steps.
+// Epilogue: the selected indices compacted in index order + counts below / at-or-above `split` (the ref | src
+// boundary), so the host needs one small readback instead of two nonzero() round trips.
 template <typename IdxT>
-__global__ void __launch_bounds__(32) nms_kernel(const IdxT* __restrict__ nbr, int N, int H,
-                                                 unsigned char* __restrict__ mask) {
-  extern __shared__ unsigned char s_sel[];  // N bytes
-  const int lane = threadIdx.x;
-  for (int i = lane; i < N; i += 32) s_sel[i] = 0;
-  __syncwarp();
-  for (int base = 0; base < N; base += NMS_PF) {
-    int rows[NMS_PF][NMS_R];
-#pragma unroll
-    for (int p = 0; p < NMS_PF; p++)
-#pragma unroll
-      for (int r = 0; r < NMS_R; r++) {
-        int i = base + p, h = lane + 32 * r;
-        rows[p][r] = (i < N && h < H) ? (int)min((long long)nbr[(size_t)i * H + h], (long long)N) : N;
+__global__ void __launch_bounds__(1024) nms_kernel(const IdxT* __restrict__ nbr, int N, int H, int split,
+                                                   unsigned char* __restrict__ mask, int64_t* __restrict__ out_sel,
+                                                   int* __restrict__ out_counts) {
+  extern __shared__ unsigned char s_state[];  // N bytes: 0 unknown, 1 selected, 2 rejected
+  __shared__ int s_scan[33];
+  volatile unsigned char* st = s_state;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < N; i += nt) st[i] = 0;
+  __syncthreads();
+  for (int round = 0; round <= N; round++) {
+    int pending = 0;
+    for (int i = tid; i < N; i += nt) {
+      if (st[i] != 0) continue;
+      bool rej = false, wait = false;
+      const IdxT* row = nbr + (size_t)i * H;
+      for (int h = 0; h < H; h++) {
+        const long long j = (long long)row[h];
+        if (j >= i) continue;  // itself, later nodes and the padding value are False when i is evaluated
+        const unsigned char sj = st[j];
+        if (sj == 1) {
+          rej = true;
+          break;
+        }
+        wait |= (sj == 0);
       }
-#pragma unroll
-    for (int p = 0; p < NMS_PF; p++) {
-      int i = base + p;
-      if (i >= N) break;
-      bool hit = false;
-#pragma unroll
-      for (int r = 0; r < NMS_R; r++) {
-        int j = rows[p][r];
-        if (j < N) hit |= (s_sel[j] != 0);
-      }
-      bool any = __any_sync(FULL_MASK, hit);
-      if (lane == 0 && !any) s_sel[i] = 1;
-      __syncwarp();
+      if (rej) st[i] = 2;
+      else if (!wait) st[i] = 1;
+      else pending = 1;
+    }
+    if (!__syncthreads_or(pending)) break;
+  }
+  // mask + compaction in index order
+  const int chunk = (N + nt - 1) / nt;
+  const int beg = min(N, tid * chunk), end = min(N, beg + chunk);
+  int c = 0, c_lo = 0;
+  for (int i = beg; i < end; i++) {
+    const int v = st[i] == 1;
+    mask[i] = (unsigned char)v;
+    c += v;
+    c_lo += v && i < split;
+  }
+  int total;
+  int pre = block_exclusive_scan(c, s_scan, &total);
+  if (out_sel != nullptr)
+    for (int i = beg; i < end; i++)
+      if (st[i] == 1) out_sel[pre++] = i;
+  if (out_counts != nullptr) {
+    int total_lo;
+    block_exclusive_scan(c_lo, s_scan, &total_lo);
+    if (tid == 0) {
+      out_counts[0] = total_lo;
+      out_counts[1] = total - total_lo;
     }
   }
-  for (int i = lane; i < N; i += 32) mask[i] = s_sel[i];
 }
 
-extern "C" int rdm_nms(const void* neighbor_indices, int index_bytes, int N, int H, unsigned char* out_mask,
-                       cudaStream_t stream) {
+extern "C" int rdm_nms(const void* neighbor_indices, int index_bytes, int N, int H, int split, unsigned char* out_mask,
+                       int64_t* out_selected, int* out_counts, cudaStream_t stream) {
   RDM_CHECK_ARG(index_bytes == 4 || index_bytes == 8, "rdm_nms: index_bytes must be 4 or 8");
-  RDM_CHECK_ARG(H >= 1 && H <= 32 * NMS_R, "rdm_nms: neighbour width must be <= 128");
+  RDM_CHECK_ARG(H >= 1, "rdm_nms: empty table");
   RDM_CHECK_ARG(N >= 0 && N <= 200000, "rdm_nms: too many nodes");
-  if (N == 0) return RDM_OK;
+  if (N == 0) {
+    if (out_counts) RDM_CUDA(cudaMemsetAsync(out_counts, 0, 2 * sizeof(int), stream));
+    return RDM_OK;
+  }
   size_t smem = (size_t)N;
   if (index_bytes == 8) {
-    if (smem > 48 * 1024)
+    if (smem > 40 * 1024)
       RDM_CUDA(cudaFuncSetAttribute(nms_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_kernel<int64_t><<<1, 32, smem, stream>>>((const int64_t*)neighbor_indices, N, H, out_mask);
+    nms_kernel<int64_t><<<1, 1024, smem, stream>>>((const int64_t*)neighbor_indices, N, H, split, out_mask, out_selected, out_counts);
   } else {
-    if (smem > 48 * 1024)
+    if (smem > 40 * 1024)
       RDM_CUDA(cudaFuncSetAttribute(nms_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_kernel<int><<<1, 32, smem, stream>>>((const int*)neighbor_indices, N, H, out_mask);
+    nms_kernel<int><<<1, 1024, smem, stream>>>((const int*)neighbor_indices, N, H, split, out_mask, out_selected, out_counts);
   }
   RDM_LAUNCH_CHECK();
   return RDM_OK;

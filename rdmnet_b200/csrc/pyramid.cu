@@ -518,7 +518,8 @@ __global__ void __launch_bounds__(1024) rs_scan_kernel(const RsCloud* __restrict
 
 __global__ void rs_scatter_kernel(const float* __restrict__ s_pts, const RsCloud* __restrict__ clouds, int batch,
                                   int* __restrict__ cell_cnt, const int* __restrict__ cell_start,
-                                  const int* __restrict__ pcell, float4* __restrict__ sorted, long long ns_cap) {
+                                  const int* __restrict__ pcell, float4* __restrict__ sorted, int* __restrict__ order,
+                                  long long ns_cap) {
   long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (j >= ns_cap) return;
   int b = rs_find_cloud_s(clouds, batch, j);
@@ -528,6 +529,7 @@ __global__ void rs_scatter_kernel(const float* __restrict__ s_pts, const RsCloud
   int pos = cell_start[(size_t)b * (RS_CELL_CAP + 1) + cell] + atomicAdd(&cell_cnt[(size_t)b * RS_CELL_CAP + cell], 1);
   sorted[c.s_start + pos] =
       make_float4(s_pts[3 * j + 0], s_pts[3 * j + 1], s_pts[3 * j + 2], __int_as_float((int)(j - c.s_start)));
+  if (order != nullptr) order[c.s_start + pos] = (int)j;  // cell-sorted (spatially coherent) order of the supports
 }
 
 // One warp per query. Hits are streamed into a per-warp shared buffer of 2*KP (d2,idx) keys; when it fills up it
@@ -623,11 +625,13 @@ extern "C" size_t rdm_radius_search_workspace(int64_t ns_cap, int batch) {
   return bytes + 4096;
 }
 
-extern "C" int rdm_radius_search(const float* q_points, const float* s_points, const int64_t* q_lengths,
-                                 const int64_t* s_lengths, int batch, int64_t nq_cap, int64_t ns_cap,
-                                 int64_t ns_total_pad, float radius, int limit, void* out_indices, int index_bytes,
-                                 int* out_counts, int* out_max_count, void* workspace, size_t workspace_bytes,
-                                 cudaStream_t stream) {
+// out_order (optional, [ns_cap] ints): the supports in cell-sorted order - a spatially coherent processing order that
+// the KPConv gather uses for its queries when the search is a self search (rdm_build_pyramid).
+int rdm_radius_search_impl(const float* q_points, const float* s_points, const int64_t* q_lengths,
+                           const int64_t* s_lengths, int batch, int64_t nq_cap, int64_t ns_cap,
+                           int64_t ns_total_pad, float radius, int limit, void* out_indices, int index_bytes,
+                           int* out_counts, int* out_max_count, int* out_order, void* workspace, size_t workspace_bytes,
+                           cudaStream_t stream) {
   RDM_CHECK_ARG(batch >= 1 && nq_cap >= 0 && ns_cap >= 0 && radius > 0.f, "rdm_radius_search: bad arguments");
   RDM_CHECK_ARG(index_bytes == 4 || index_bytes == 8, "rdm_radius_search: index_bytes must be 4 or 8");
   RDM_CHECK_ARG(limit <= 4096, "rdm_radius_search: limit > 4096 unsupported");
@@ -654,7 +658,7 @@ extern "C" int rdm_radius_search(const float* q_points, const float* s_points, c
   RDM_LAUNCH_CHECK();
   if (ns_cap > 0) {
     rs_scatter_kernel<<<cdiv(ns_cap, 256), 256, 0, stream>>>(s_points, clouds, batch, cell_cnt, cell_start, pcell,
-                                                            sorted, ns_cap);
+                                                            sorted, out_order, ns_cap);
     RDM_LAUNCH_CHECK();
   }
   int KP = 32;
@@ -681,4 +685,14 @@ extern "C" int rdm_radius_search(const float* q_points, const float* s_points, c
   }
   RDM_LAUNCH_CHECK();
   return RDM_OK;
+}
+
+extern "C" int rdm_radius_search(const float* q_points, const float* s_points, const int64_t* q_lengths,
+                                 const int64_t* s_lengths, int batch, int64_t nq_cap, int64_t ns_cap,
+                                 int64_t ns_total_pad, float radius, int limit, void* out_indices, int index_bytes,
+                                 int* out_counts, int* out_max_count, void* workspace, size_t workspace_bytes,
+                                 cudaStream_t stream) {
+  return rdm_radius_search_impl(q_points, s_points, q_lengths, s_lengths, batch, nq_cap, ns_cap, ns_total_pad, radius, limit,
+                                out_indices, index_bytes, out_counts, out_max_count, nullptr, workspace, workspace_bytes,
+                                stream);
 }

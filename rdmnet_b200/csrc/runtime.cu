@@ -4,6 +4,7 @@
 // rdmnet/thdroformer/thdroformer.py:229-251, 304-347 (RPEConditionalTransformer / ThDRoFormer forward).
 // No kernel lives here: the functions below only sequence the launch functions of the other translation units and
 // carve temporaries out of the caller's workspace (the same code runs "dry" to size that workspace).
+#include <string.h>
 #include "common.cuh"
 #include "../../include/rdm_sm100.h"
 
@@ -65,13 +66,13 @@ int unary(Arena& a, const rdm_unary_desc& u, const float* x, int ldx, float* out
 
 // KPConv.forward (kpconv.py:79-122) + norm_conv + LeakyReLU: out [M, c_mid_out]
 int kpconv_norm(Arena& a, const rdm_block_desc& b, const float* feats, const float* q_pts, const float* s_pts, const void* idx,
-                int index_bytes, int M, int N, int H, float* out, int groups, cudaStream_t st) {
+                int index_bytes, int M, int N, int H, const int* order, float* out, int groups, cudaStream_t st) {
   size_t mark = a.off;
   float* gathered = a.f((size_t)M * 15 * b.c_mid_in);
   unsigned char* rowpos = (unsigned char*)a.raw((size_t)(N > 0 ? N : 1));
   if (!a.dry)
     RDM_TRY(rdm_kpconv_gather(feats, q_pts, s_pts, idx, index_bytes, b.kernel_points, b.h_kernel_points, b.sigma, M, N, H,
-                              b.c_mid_in, gathered, rowpos, st));
+                              b.c_mid_in, order, gathered, rowpos, st));
   const int prof = a.dry ? -1 : rdm_prof_begin(RDM_PROF_KPCONV_GEMM, M, 15 * b.c_mid_in, 0, b.c_mid_out, st);
   if (b.kpconv_wt != nullptr)
     RDM_TRY(linear(a, gathered, 15 * b.c_mid_in, b.kpconv_wt, 15 * b.c_mid_in, 1, b.kpconv_b, out, M, b.c_mid_out, 15 * b.c_mid_in, st));
@@ -100,7 +101,7 @@ int encoder_run(Arena& a, const rdm_block_desc* blocks, int nb, const rdm_pyrami
     float* out = last_of_stage ? (a.dry ? nullptr : out_feats[s]) : a.f((size_t)M * b.c_out);
     size_t mark = a.off;
     if (b.unary2.w == nullptr) {  // ConvBlock (modules.py:143-147)
-      RDM_TRY(kpconv_norm(a, b, cur, q_pts, s_pts, idx, p.index_bytes, M, N, H, out, groups, st));
+      RDM_TRY(kpconv_norm(a, b, cur, q_pts, s_pts, idx, p.index_bytes, M, N, H, p.order[s], out, groups, st));
     } else {  // ResidualBlock (modules.py:205-225)
       const float* x = cur;
       if (b.unary1.w != nullptr) {
@@ -109,7 +110,7 @@ int encoder_run(Arena& a, const rdm_block_desc* blocks, int nb, const rdm_pyrami
         x = t;
       }
       float* c = a.f((size_t)M * b.c_mid_out);
-      RDM_TRY(kpconv_norm(a, b, x, q_pts, s_pts, idx, p.index_bytes, M, N, H, c, groups, st));
+      RDM_TRY(kpconv_norm(a, b, x, q_pts, s_pts, idx, p.index_bytes, M, N, H, p.order[s], c, groups, st));
       const float* sc = cur;
       if (b.strided) {
         float* mp = a.f((size_t)M * b.c_in);
@@ -277,4 +278,120 @@ extern "C" int rdm_thdroformer_forward(const rdm_thdroformer_desc* h_desc, const
   Arena a(workspace, workspace_bytes, false);
   return thdroformer_run(a, *h_desc, ref_points, n_ref, src_points, n_src, ref_feats, ld_ref, src_feats, ld_src, out_ref, out_src,
                          stream);
+}
+
+// ------------------------------------------------------------------------------------------------ pyramid builder
+int rdm_radius_search_impl(const float* q_points, const float* s_points, const int64_t* q_lengths, const int64_t* s_lengths,
+                           int batch, int64_t nq_cap, int64_t ns_cap, int64_t ns_total_pad, float radius, int limit,
+                           void* out_indices, int index_bytes, int* out_counts, int* out_max_count, int* out_order,
+                           void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+namespace {
+// worst case: every stage keeps all n0 points
+size_t pyramid_bytes(int64_t n0, const rdm_pyramid_cfg& c) {
+  const size_t n = (size_t)n0;
+  size_t b = 4096;
+  b += align_up(sizeof(int64_t) * c.num_stages * c.batch, 256);
+  b += align_up(sizeof(int) * 64, 256);  // max counts
+  for (int s = 1; s < c.num_stages; s++) b += align_up(n * 12, 256);
+  for (int s = 0; s < c.num_stages; s++) {
+    b += align_up(n * 4, 256);                       // order
+    b += align_up(n * 4 * (size_t)c.limits[s], 256);  // neighbors
+    if (s + 1 < c.num_stages) {
+      b += align_up(n * 4 * (size_t)c.limits[s], 256);  // subsampling
+      b += align_up(n * 4 * (size_t)(c.up_nearest_only ? 1 : c.limits[s + 1]), 256);
+    }
+  }
+  return b;
+}
+size_t pyramid_ws(int64_t n0, const rdm_pyramid_cfg& c) {
+  size_t a = rdm_grid_subsample_workspace(n0, c.batch), b = rdm_radius_search_workspace(n0, c.batch);
+  return (a > b ? a : b) + 4096;
+}
+int64_t* g_pinned_lengths = nullptr;  // host staging for the one readback (process-wide; calls are serialised by the GIL)
+}  // namespace
+
+extern "C" size_t rdm_build_pyramid_bytes(int64_t n0, const rdm_pyramid_cfg* c) { return pyramid_bytes(n0, *c); }
+extern "C" size_t rdm_build_pyramid_workspace(int64_t n0, const rdm_pyramid_cfg* c) { return pyramid_ws(n0, *c); }
+
+extern "C" int rdm_build_pyramid(const float* points, const int64_t* lengths, int64_t n0, const rdm_pyramid_cfg* h_cfg,
+                                 void* out_buf, size_t out_bytes, void* workspace, size_t workspace_bytes,
+                                 rdm_pyramid_desc* h_desc, int64_t* h_lengths, const int64_t** h_d_lengths,
+                                 cudaStream_t stream) {
+  RDM_CHECK_ARG(h_cfg && h_desc && h_lengths && h_d_lengths && points && lengths, "rdm_build_pyramid: null argument");
+  const rdm_pyramid_cfg& c = *h_cfg;
+  RDM_CHECK_ARG(c.num_stages >= 1 && c.num_stages <= 8 && c.batch >= 1 && c.batch <= 16 && n0 >= 1 && n0 < (1LL << 28),
+                "rdm_build_pyramid: bad configuration");
+  if (out_bytes < pyramid_bytes(n0, c) || workspace_bytes < pyramid_ws(n0, c)) {
+    rdm_set_error("rdm_build_pyramid: output buffer or workspace too small");
+    return RDM_ERR_WORKSPACE;
+  }
+  if (g_pinned_lengths == nullptr) RDM_CUDA(cudaHostAlloc((void**)&g_pinned_lengths, sizeof(int64_t) * 8 * 16, cudaHostAllocDefault));
+  Workspace out(out_buf, out_bytes);
+  const int S = c.num_stages, B = c.batch;
+  int64_t* d_len = out.get<int64_t>((size_t)S * B);  // stage-major
+  int* d_maxc = out.get<int>(64);
+  float* pts[8];
+  pts[0] = const_cast<float*>(points);
+  for (int s = 1; s < S; s++) pts[s] = out.get<float>((size_t)n0 * 3);
+  // ---- chained subsampling: capacity launches driven by the device-side lengths, no host round trip in between
+  RDM_CUDA(cudaMemcpyAsync(d_len, lengths, sizeof(int64_t) * B, cudaMemcpyDeviceToDevice, stream));
+  float voxel = c.first_voxel;
+  for (int s = 1; s < S; s++) {
+    RDM_TRY(rdm_grid_subsample(pts[s - 1], d_len + (size_t)(s - 1) * B, B, n0, voxel, pts[s], d_len + (size_t)s * B, workspace,
+                               workspace_bytes, stream));
+    voxel *= 2.f;
+  }
+  RDM_CUDA(cudaMemcpyAsync(g_pinned_lengths, d_len, sizeof(int64_t) * S * B, cudaMemcpyDeviceToHost, stream));
+  RDM_CUDA(cudaStreamSynchronize(stream));  // the one synchronisation: stage sizes decide every later shape
+  rdm_pyramid_desc& d = *h_desc;
+  memset(&d, 0, sizeof(d));
+  d.num_stages = S;
+  d.index_bytes = 4;
+  for (int s = 0; s < S; s++) {
+    int64_t tot = 0;
+    for (int b = 0; b < B; b++) {
+      h_lengths[s * B + b] = g_pinned_lengths[s * B + b];
+      tot += g_pinned_lengths[s * B + b];
+    }
+    RDM_CHECK_ARG(tot >= 0 && tot <= n0, "rdm_build_pyramid: inconsistent stage size");
+    d.n[s] = (int)tot;
+    d.points[s] = pts[s];
+    h_d_lengths[s] = d_len + (size_t)s * B;
+  }
+  // ---- radius searches at exact sizes (utils/data.py:35-67)
+  float radius = c.first_radius;
+  int nsearch = 0;
+  for (int s = 0; s < S; s++) {
+    const int n = d.n[s];
+    int* order = out.get<int>((size_t)(n > 0 ? n : 1));
+    int* nb = out.get<int>((size_t)(n > 0 ? n : 1) * c.limits[s]);
+    d.order[s] = order;
+    d.neighbors[s] = nb;
+    d.nb_width[s] = c.limits[s];
+    RDM_TRY(rdm_radius_search_impl(pts[s], pts[s], h_d_lengths[s], h_d_lengths[s], B, n, n, n, radius, c.limits[s], nb, 4, nullptr,
+                                   d_maxc + nsearch++, order, workspace, workspace_bytes, stream));
+    if (s + 1 < S) {
+      const int m = d.n[s + 1];
+      int* sub = out.get<int>((size_t)(m > 0 ? m : 1) * c.limits[s]);
+      d.subsampling[s] = sub;
+      d.sub_width[s] = c.limits[s];
+      RDM_TRY(rdm_radius_search_impl(pts[s + 1], pts[s], h_d_lengths[s + 1], h_d_lengths[s], B, m, n, n, radius, c.limits[s], sub, 4,
+                                     nullptr, d_maxc + nsearch++, nullptr, workspace, workspace_bytes, stream));
+      if (!(c.skip_up0 && s == 0)) {
+        const int w = c.up_nearest_only ? 1 : c.limits[s + 1];
+        int* up = out.get<int>((size_t)(n > 0 ? n : 1) * w);
+        d.upsampling[s] = up;
+        d.up_width[s] = w;
+        RDM_TRY(rdm_radius_search_impl(pts[s], pts[s + 1], h_d_lengths[s], h_d_lengths[s + 1], B, n, m, m, radius * 2.f, w, up, 4,
+                                       nullptr, d_maxc + nsearch++, nullptr, workspace, workspace_bytes, stream));
+      }
+    }
+    radius *= 2.f;
+  }
+  if (!out.ok) {
+    rdm_set_error("rdm_build_pyramid: output buffer too small");
+    return RDM_ERR_WORKSPACE;
+  }
+  return RDM_OK;
 }

@@ -18,6 +18,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from . import ops
+from .modules import _Module, cache_key
 from .modules import (ConvBlock, LastUnaryBlock, LearnableLogOptimalTransport, LocalGlobalRegistration, NMS,
                       ResidualBlock, SuperPointMatching, ThDRoFormer, UnaryBlock, Vote_layer)
 
@@ -99,8 +100,74 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
     }
 
 
+class GpuPyramid:
+    """Result of rdm_build_pyramid: one device buffer + the host descriptor the C runners consume. Tensors are views
+    into the buffer, created on demand (`points(s)`, `lengths(s)`, `table(kind, s)`, `as_data_dict()`)."""
+
+    def __init__(self, buf, desc, lengths_host, d_lengths, points0, batch):
+        self.buf, self.desc, self.lengths_host, self._d_lengths, self._points0, self.batch = (
+            buf, desc, lengths_host, d_lengths, points0, batch)
+        self._base = buf.data_ptr()
+
+    def _view(self, ptr, nbytes, dtype):
+        off = ptr - self._base
+        return self.buf[off:off + nbytes].view(dtype)
+
+    def points(self, s):
+        if s == 0:
+            return self._points0
+        return self._view(self.desc.points[s], self.desc.n[s] * 12, torch.float32).view(-1, 3)
+
+    def lengths(self, s):
+        return self._view(self._d_lengths[s], 8 * self.batch, torch.int64)
+
+    def table(self, kind, s):
+        d = self.desc
+        ptr, rows, w = {"neighbors": (d.neighbors[s], d.n[s], d.nb_width[s]),
+                        "subsampling": (d.subsampling[s], d.n[s + 1], d.sub_width[s]),
+                        "upsampling": (d.upsampling[s], d.n[s], d.up_width[s]),
+                        "order": (d.order[s], d.n[s], 1)}[kind]
+        if not ptr:
+            return None
+        t = self._view(ptr, rows * w * 4, torch.int32)
+        return t if kind == "order" else t.view(rows, w)
+
+    def as_data_dict(self):
+        S = self.desc.num_stages
+        return {"points": [self.points(s) for s in range(S)], "lengths": [self.lengths(s) for s in range(S)],
+                "lengths_host": self.lengths_host,
+                "neighbors": [self.table("neighbors", s) for s in range(S)],
+                "subsampling": [self.table("subsampling", s) for s in range(S - 1)],
+                "upsampling": [self.table("upsampling", s) for s in range(S - 1)]}
+
+
+def build_pyramid_gpu(points, lengths, num_stages, voxel_size, radius, neighbor_limits, skip_unused=True,
+                      up_nearest_only=True):
+    """geotransformer/utils/data.py:13-77 through rdm_build_pyramid: one host call, one synchronisation, int32 tables of
+    fixed width = the neighbour limit, plus a cell-sorted query order per stage for the KPConv gather."""
+    points = points.contiguous()
+    n0, batch = points.shape[0], lengths.shape[0]
+    cfg = L.PyramidCfg()
+    cfg.num_stages, cfg.batch, cfg.first_voxel, cfg.first_radius = num_stages, batch, voxel_size * 2, radius
+    for i, v in enumerate(neighbor_limits):
+        cfg.limits[i] = int(v)
+    cfg.skip_up0, cfg.up_nearest_only = int(skip_unused), int(up_nearest_only)
+    lib = L.lib()
+    ob, wb = lib.rdm_build_pyramid_bytes(n0, ctypes.byref(cfg)), lib.rdm_build_pyramid_workspace(n0, ctypes.byref(cfg))
+    buf = torch.empty(int(ob), dtype=torch.uint8, device=points.device)
+    ws = torch.empty(int(wb), dtype=torch.uint8, device=points.device)
+    desc = L.PyramidDesc()
+    h_len = (ctypes.c_int64 * (num_stages * batch))()
+    h_dl = (ctypes.c_void_p * 8)()
+    with torch.cuda.device(points.device):
+        L.call("rdm_build_pyramid", L.ptr(points), L.ptr(lengths), n0, ctypes.byref(cfg), L.ptr(buf), int(ob), L.ptr(ws), int(wb),
+               ctypes.byref(desc), ctypes.cast(h_len, ctypes.c_void_p), ctypes.cast(h_dl, ctypes.c_void_p), L.stream())
+    host = [[int(h_len[s * batch + b]) for b in range(batch)] for s in range(num_stages)]
+    return GpuPyramid(buf, desc, host, [int(h_dl[s]) for s in range(num_stages)], points, batch)
+
+
 def _state_key(module):
-    return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+    return cache_key(module)
 
 
 def _p(t):
@@ -147,7 +214,7 @@ def pyramid_desc(data_dict, lengths_host):
     return d, keep
 
 
-class Encoder(nn.Module):
+class Encoder(_Module):
     """experiments/backbone.py:7-107."""
 
     def __init__(self, input_dim, init_dim, kernel_size, init_radius, init_sigma, group_norm):
@@ -233,7 +300,7 @@ class Encoder(nn.Module):
         return out
 
 
-class Decoder(nn.Module):
+class Decoder(_Module):
     """experiments/backbone.py:110-151."""
 
     def __init__(self, output_dim, init_dim, group_norm):
@@ -272,7 +339,7 @@ class Decoder(nn.Module):
         return [l2, l3, l4]
 
 
-class RDMNet(nn.Module):
+class RDMNet(_Module):
     """experiments/model_infer.py:26-354 (inference forward). Same submodule names => same checkpoint keys."""
 
     def __init__(self, cfg):
@@ -301,6 +368,14 @@ class RDMNet(nn.Module):
             num_refinement_steps=f.num_refinement_steps)
         self.optimal_transport = LearnableLogOptimalTransport(cfg.model.num_sinkhorn_iterations)
 
+    def _ones(self, n, device):
+        """Input features of the KITTI configuration: ones (N,1) (kitti/dataset.py:188-189), cached by size."""
+        c = getattr(self, "_ones_cache", None)
+        if c is None or c.shape[0] < n or c.device != device:
+            c = torch.ones((max(n, 1 << 16), 1), dtype=torch.float32, device=device)
+            self._ones_cache = c
+        return c[:n]
+
     def build_pyramid(self, points, lengths):
         b = self.cfg.backbone
         return precompute_data_stack_mode(points.contiguous(), lengths, b.num_stages, b.init_voxel_size, b.init_radius,
@@ -310,22 +385,31 @@ class RDMNet(nn.Module):
     def forward(self, data_dict):
         out = {}
         if "neighbors" not in data_dict:  # raw stacked points in: build the pyramid here, on the GPU
-            data_dict = dict(data_dict)
-            data_dict.update(self.build_pyramid(data_dict["points"], data_dict["lengths"]))
-        L_host = data_dict.get("lengths_host")
-        if L_host is None:
-            L_host = [l.tolist() for l in data_dict["lengths"]]
+            b = self.cfg.backbone
+            gp = build_pyramid_gpu(data_dict["points"], data_dict["lengths"], b.num_stages, b.init_voxel_size, b.init_radius,
+                                   self.cfg.neighbor_limits)
+            S = gp.desc.num_stages
+            L_host = gp.lengths_host
+            points_c, points_f, points = gp.points(S - 1), gp.points(1), gp.points(0)
+            lengths_c = gp.lengths(S - 1)
+            pyr = (gp.desc, [gp])
+            out["pyramid"] = gp
+        else:
+            L_host = data_dict.get("lengths_host")
+            if L_host is None:
+                L_host = [l.tolist() for l in data_dict["lengths"]]
+            points_c, points_f, points = data_dict["points"][-1], data_dict["points"][1], data_dict["points"][0]
+            lengths_c = data_dict["lengths"][-1]
+            pyr = pyramid_desc(data_dict, L_host)
         nc, nf, n0 = int(L_host[-1][0]), int(L_host[1][0]), int(L_host[0][0])
-        points_c, points_f, points = data_dict["points"][-1], data_dict["points"][1], data_dict["points"][0]
         feats = data_dict.get("features")
         if feats is None:
-            feats = torch.ones((points.shape[0], 1), dtype=torch.float32, device=points.device)
+            feats = self._ones(points.shape[0], points.device)
         out["ori_ref_points_c"], out["ori_src_points_c"] = points_c[:nc], points_c[nc:]
         ref_points_f, src_points_f = points_f[:nf].contiguous(), points_f[nf:].contiguous()
         out["ref_points_f"], out["src_points_f"] = ref_points_f, src_points_f
         out["ref_points"], out["src_points"] = points[:n0], points[n0:]
 
-        pyr = pyramid_desc(data_dict, L_host)
         feats_list = self.encoder(feats, data_dict, pyr)
         feats_c = feats_list[-1]
         ref_feats_c, src_feats_c = self.transformer(points_c[:nc].contiguous(), points_c[nc:].contiguous(),
@@ -344,10 +428,10 @@ class RDMNet(nn.Module):
             shifted, vf = self.vote(points_c, tf)
             out["shifted_ref_points_c"], out["shifted_src_points_c"] = shifted[:nc], shifted[nc:]
             n2n = ops.activation(ops.linear(vf, self.proj_n2n_score.weight, self.proj_n2n_score.bias).view(-1), 3)
-            masks = self.nms(shifted.contiguous(), data_dict["lengths"][-1])
+            masks, sel, sel_counts = self.nms(shifted.contiguous(), lengths_c, split=nc)
             out["mask"] = masks
-            ref_sel = torch.nonzero(masks[:nc], as_tuple=True)[0]  # data-dependent count: host sync
-            src_sel = torch.nonzero(masks[nc:], as_tuple=True)[0]
+            n_ref_sel, n_src_sel = sel_counts.tolist()  # data-dependent counts: the one host sync of this section
+            ref_sel, src_sel = sel[:n_ref_sel], sel[n_ref_sel:n_ref_sel + n_src_sel] - nc
             ref_points_c, src_points_c = shifted[:nc][ref_sel].contiguous(), shifted[nc:][src_sel].contiguous()
             ref_feats_c, src_feats_c = vf[:nc][ref_sel], vf[nc:][src_sel]
             out["ref_n2p_scores_c"], out["src_n2p_scores_c"] = ref_n2p[ref_sel], src_n2p[src_sel]

@@ -33,7 +33,38 @@ def default_kernel_points(radius, num_kpoints=15):
     return pts * 0.66 * radius
 
 
-class KPConv(nn.Module):
+_WEIGHTS_EPOCH = [0]
+
+
+class _Module(nn.Module):
+    """nn.Module whose device moves / dtype casts / state-dict loads / train-eval switches bump a process-wide epoch.
+    Derived data (transposed weight copies, packed layer blobs, C descriptor structs) are cached against that epoch
+    in eval mode, so the per-call cost of a cache check is one integer compare instead of a walk over ~500 tensors.
+    In training mode the caches fall back to (data_ptr, version) keys, which also see in-place optimizer updates."""
+
+    def _apply(self, fn, *args, **kwargs):
+        _WEIGHTS_EPOCH[0] += 1
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        _WEIGHTS_EPOCH[0] += 1
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def train(self, mode=True):
+        _WEIGHTS_EPOCH[0] += 1
+        return super().train(mode)
+
+
+def cache_key(module, tensors=None):
+    """Cache key for data derived from `module`'s parameters (see _Module)."""
+    if not module.training:
+        return ("eval", _WEIGHTS_EPOCH[0])
+    if tensors is None:
+        tensors = list(module.parameters()) + list(module.buffers())
+    return tuple((t.data_ptr(), t._version) for t in tensors)
+
+
+class KPConv(_Module):
     """geotransformer/modules/kpconv/kpconv.py:10-122."""
 
     def __init__(self, in_channels, out_channels, kernel_size, radius, sigma, bias=False, dimension=3, inf=1e6, eps=1e-9):
@@ -62,7 +93,7 @@ class KPConv(nn.Module):
                           self.bias)
 
 
-class GroupNorm(nn.Module):
+class GroupNorm(_Module):
     """geotransformer/modules/kpconv/modules.py:33-50 (statistics over the whole stacked (N, C/G) slab)."""
 
     def __init__(self, num_groups, num_channels):
@@ -74,7 +105,7 @@ class GroupNorm(nn.Module):
         return ops.group_norm(x, self.norm.weight, self.norm.bias, self.num_groups, residual, act, 0.1, self.norm.eps)
 
 
-class UnaryBlock(nn.Module):
+class UnaryBlock(_Module):
     """kpconv/modules.py:53-83."""
 
     def __init__(self, in_channels, out_channels, group_norm, has_relu=True, bias=True, layer_norm=False):
@@ -93,7 +124,7 @@ class UnaryBlock(nn.Module):
         return self.norm(x, residual, act)
 
 
-class LastUnaryBlock(nn.Module):
+class LastUnaryBlock(_Module):
     """kpconv/modules.py:86-101."""
 
     def __init__(self, in_channels, out_channels, bias=True):
@@ -105,7 +136,7 @@ class LastUnaryBlock(nn.Module):
         return ops.linear(x, self.mlp.weight, self.mlp.bias)
 
 
-class ConvBlock(nn.Module):
+class ConvBlock(_Module):
     """kpconv/modules.py:104-147."""
 
     def __init__(self, in_channels, out_channels, kernel_size, radius, sigma, group_norm, negative_slope=0.1, bias=True,
@@ -123,7 +154,7 @@ class ConvBlock(nn.Module):
         return self.norm(x, None, 1)
 
 
-class ResidualBlock(nn.Module):
+class ResidualBlock(_Module):
     """kpconv/modules.py:150-225."""
 
     def __init__(self, in_channels, out_channels, kernel_size, radius, sigma, group_norm, strided=False, bias=True,
@@ -154,7 +185,7 @@ class ResidualBlock(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------- transformer
-class AttentionOutput(nn.Module):
+class AttentionOutput(_Module):
     """geotransformer/modules/transformer/output_layer.py:6-21 (dropout=None)."""
 
     def __init__(self, d_model, dropout=None, activation_fn="ReLU"):
@@ -171,7 +202,7 @@ class AttentionOutput(nn.Module):
         return ops.layer_norm(h, self.norm.weight, self.norm.bias, residual=x, eps=self.norm.eps)
 
 
-class _PosEncoderBuffers(nn.Module):
+class _PosEncoderBuffers(_Module):
     """Holds the (unused) `div_term` buffer of RotaryPositionalEmbedding so that checkpoints load strictly
     (rdmnet/thdroformer/thdroformer.py:43-54)."""
 
@@ -182,7 +213,7 @@ class _PosEncoderBuffers(nn.Module):
         self.register_buffer("div_term", div.repeat_interleave(2).view(1, 1, 1, -1))
 
 
-class MultiHeadAttention(nn.Module):
+class MultiHeadAttention(_Module):
     """vanilla_transformer.py:15-70 (no masks / factors: RDMNet passes none) and, with `rotary=True`,
     RPEMultiHeadAttention (thdroformer.py:88-139, k=None)."""
 
@@ -208,7 +239,7 @@ class MultiHeadAttention(nn.Module):
         return ops.attention(q, k, v, self.num_heads)
 
 
-class AttentionLayer(nn.Module):
+class AttentionLayer(_Module):
     """vanilla_transformer.py:73-102 / RPEAttentionLayer thdroformer.py:141-172."""
 
     def __init__(self, d_model, num_heads, dropout=None, rotary=False):
@@ -223,7 +254,7 @@ class AttentionLayer(nn.Module):
         return ops.layer_norm(h, self.norm.weight, self.norm.bias, residual=input_states, eps=self.norm.eps)
 
 
-class TransformerLayer(nn.Module):
+class TransformerLayer(_Module):
     """vanilla_transformer.py:105-129 / RPETransformerLayer thdroformer.py:175-202. 2-D (N,C) states."""
 
     def __init__(self, d_model, num_heads, dropout=None, activation_fn="ReLU", rotary=False):
@@ -248,7 +279,7 @@ class TransformerLayer(nn.Module):
         params = [a.proj_q.weight, a.proj_k.weight, a.proj_v.weight, al.linear.weight, o.expand.weight, o.squeeze.weight,
                   a.proj_q.bias, a.proj_k.bias, a.proj_v.bias, al.linear.bias, o.expand.bias, o.squeeze.bias,
                   al.norm.weight, al.norm.bias, o.norm.weight, o.norm.bias]
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        key = cache_key(self, params)
         if self._blob_key != key:
             with torch.no_grad():
                 parts = [p.detach().t().contiguous().reshape(-1) for p in params[:6]] + [p.detach().reshape(-1) for p in params[6:]]
@@ -259,7 +290,7 @@ class TransformerLayer(nn.Module):
         return self._blob
 
 
-class RPEConditionalTransformer(nn.Module):
+class RPEConditionalTransformer(_Module):
     """thdroformer.py:204-251: alternating self (rotary) / cross layers; cross attention is sequential
     (feats1 attends to the already-updated feats0, :244-245)."""
 
@@ -314,7 +345,7 @@ class RPEConditionalTransformer(nn.Module):
         return f0, f1
 
 
-class posEmbedding(nn.Module):
+class posEmbedding(_Module):
     """thdroformer.py:253-263."""
 
     def __init__(self, hidden_dim, reduction_a="max"):
@@ -325,7 +356,7 @@ class posEmbedding(nn.Module):
         return ops.linear(points, self.proj.weight, self.proj.bias)
 
 
-class ThDRoFormer(nn.Module):
+class ThDRoFormer(_Module):
     """rdmnet/thdroformer/thdroformer.py:266-347. Accepts (1,N,3)/(1,N,C) like the reference (or 2-D tensors) and
     returns tensors of the same rank."""
 
@@ -362,11 +393,11 @@ class ThDRoFormer(nn.Module):
         import ctypes
         L = ops.L
         tr = self.transformer
-        blobs = [layer.fused_blob() for layer in tr.layers]
-        key = tuple(b.data_ptr() for b in blobs) + tuple((p.data_ptr(), p._version) for p in (
-            self.embedding.proj.weight, self.embedding.proj.bias, self.in_proj.weight, self.in_proj.bias,
-            self.out_proj.weight, self.out_proj.bias))
+        key = cache_key(self)
+        if key[0] != "eval":
+            key = key + tuple(layer.fused_blob().data_ptr() for layer in tr.layers)
         if getattr(self, "_desc_key", None) != key:
+            blobs = [layer.fused_blob() for layer in tr.layers]
             d = L.ThdroformerDesc()
             d.emb_w, d.emb_b = self.embedding.proj.weight.data_ptr(), self.embedding.proj.bias.data_ptr()
             d.in_w, d.in_b = self.in_proj.weight.data_ptr(), self.in_proj.bias.data_ptr()
@@ -389,7 +420,7 @@ class ThDRoFormer(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------- vote / NMS
-class Vote_layer(nn.Module):
+class Vote_layer(_Module):
     """rdmnet/vote/vote.py:43-117. `cfgs` needs MLPS, MAX_TRANSLATE_RANGE, input_feats_dim."""
 
     def __init__(self, cfgs, r):
@@ -425,7 +456,7 @@ class Vote_layer(nn.Module):
         return vote_xyz, new_features
 
 
-class NMS(nn.Module):
+class NMS(_Module):
     """rdmnet/vote/vote.py:6-40: radius search on the shifted nodes + greedy selection, both on the device."""
 
     def __init__(self, cfgs, neighbor_limits):
@@ -434,18 +465,18 @@ class NMS(nn.Module):
         self.neighbor_limits = int(neighbor_limits[-1])
 
     @torch.no_grad()
-    def forward(self, nodes_dict, length_dict=None, overlap_score=None, features=None):
+    def forward(self, nodes_dict, length_dict=None, overlap_score=None, features=None, split=None):
         nodes = nodes_dict.contiguous()
         if length_dict is None:
             length_dict = torch.tensor([nodes.shape[0]], dtype=torch.int64, device=nodes.device)
         lengths = length_dict.to(device=nodes.device, dtype=torch.int64)
         idx, _ = ops.radius_search_raw(nodes, nodes, lengths, lengths, self.NMS_radius, self.neighbor_limits,
                                        index_dtype=torch.int32)
-        return ops.nms(idx)
+        return ops.nms(idx, split)
 
 
 # ------------------------------------------------------------------------------------------------- matching
-class LearnableLogOptimalTransport(nn.Module):
+class LearnableLogOptimalTransport(_Module):
     """geotransformer/modules/sinkhorn/learnable_sinkhorn.py:5-70."""
 
     def __init__(self, num_iterations, inf=1e12):
@@ -466,7 +497,7 @@ class LearnableLogOptimalTransport(nn.Module):
         return self.__class__.__name__ + "(num_iterations={})".format(self.num_iterations)
 
 
-class SuperPointMatching(nn.Module):
+class SuperPointMatching(_Module):
     """geotransformer/modules/geotransformer/superpoint_matching.py:7-83 (without the optional n2p-score gating,
     which model.py:308-311 does not use)."""
 
@@ -487,7 +518,7 @@ class SuperPointMatching(nn.Module):
                                    self.dual_normalization)
 
 
-class WeightedProcrustes(nn.Module):
+class WeightedProcrustes(_Module):
     """geotransformer/modules/registration/procrustes.py:76-91."""
 
     def __init__(self, weight_thresh=0.0, eps=1e-5, return_transform=False):
@@ -498,7 +529,7 @@ class WeightedProcrustes(nn.Module):
         return ops.weighted_procrustes(src_points, tgt_points, weights, self.weight_thresh, self.eps, self.return_transform)
 
 
-class LocalGlobalRegistration(nn.Module):
+class LocalGlobalRegistration(_Module):
     """geotransformer/modules/geotransformer/local_global_registration.py:11-243 for the RDMNet configuration
     (k=1, mutual=False, use_dustbin=True, use_global_score=False, correspondence_limit=None)."""
 

@@ -148,7 +148,7 @@ def _host_copy(t):
     return h
 
 
-def kpconv(s_feats, q_points, s_points, neighbor_indices, weights, kernel_points, sigma, bias=None):
+def kpconv(s_feats, q_points, s_points, neighbor_indices, weights, kernel_points, sigma, bias=None, query_order=None):
     """KPConv.forward (geotransformer/modules/kpconv/kpconv.py:79-122)."""
     s_feats, neighbor_indices = s_feats.contiguous(), neighbor_indices.contiguous()
     _chk(s_feats, torch.float32, "s_feats", 2)
@@ -162,7 +162,7 @@ def kpconv(s_feats, q_points, s_points, neighbor_indices, weights, kernel_points
     rowpos = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
     L.call("rdm_kpconv_gather", L.ptr(s_feats), L.ptr(q_points), L.ptr(s_points), L.ptr(neighbor_indices),
            _idx_bytes(neighbor_indices), L.ptr(kernel_points), _host_copy(kernel_points).data_ptr(), float(sigma), m, n, h, c,
-           L.ptr(gathered), L.ptr(rowpos), L.stream())
+           L.ptr(query_order), L.ptr(gathered), L.ptr(rowpos), L.stream())
     return linear(gathered, weights.reshape(kk * c, cout), bias, weight_is_kn=True)
 
 
@@ -286,13 +286,22 @@ def tf_attend(blob, jobs):
 
 
 # ----------------------------------------------------------------------------------------------- matching
-def nms(neighbor_indices):
-    """Greedy loop of NMS.forward (rdmnet/vote/vote.py:33-40) on a radius-search table; returns a bool mask (N,)."""
+def nms(neighbor_indices, split=None):
+    """Greedy loop of NMS.forward (rdmnet/vote/vote.py:33-40) on a radius-search table; returns a bool mask (N,).
+    With `split` (number of ref nodes) also returns (selected int64 (N,) compacted ascending, counts int32 (2,) =
+    selected below / from `split`) so that the caller needs a single small readback."""
     neighbor_indices = neighbor_indices.contiguous()
     n, h = neighbor_indices.shape
-    mask = torch.empty(n, dtype=torch.uint8, device=neighbor_indices.device)
-    L.call("rdm_nms", L.ptr(neighbor_indices), _idx_bytes(neighbor_indices), n, h, L.ptr(mask), L.stream())
-    return mask.bool()
+    dev = neighbor_indices.device
+    mask = torch.empty(n, dtype=torch.uint8, device=dev)
+    if split is None:
+        L.call("rdm_nms", L.ptr(neighbor_indices), _idx_bytes(neighbor_indices), n, h, n, L.ptr(mask), None, None, L.stream())
+        return mask.bool()
+    sel = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    counts = torch.empty(2, dtype=torch.int32, device=dev)
+    L.call("rdm_nms", L.ptr(neighbor_indices), _idx_bytes(neighbor_indices), n, h, int(split), L.ptr(mask), L.ptr(sel),
+           L.ptr(counts), L.stream())
+    return mask.bool(), sel, counts
 
 
 def pairwise_distance(x, y, normalized=False, channel_first=False):

@@ -6,7 +6,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from rdmnet_b200 import ops, synthetic, _lib as L
-from rdmnet_b200.model import precompute_data_stack_mode
+from rdmnet_b200.model import build_pyramid_gpu
 
 src = sys.argv[1] if len(sys.argv) > 1 else "synthetic"
 if src == "bundled":
@@ -17,8 +17,10 @@ else:
     a, b = p["ref_points"], p["src_points"]
 pts = torch.from_numpy(np.concatenate([a, b])).cuda()
 lens = torch.tensor([len(a), len(b)]).cuda()
-pyr = precompute_data_stack_mode(pts, lens, 5, 0.3, 4.25 * 0.3, [65, 63, 69, 70, 81], index_dtype=torch.int32)
+gp = build_pyramid_gpu(pts, lens, 5, 0.3, 4.25 * 0.3, [65, 63, 69, 70, 81])
+pyr = gp.as_data_dict()
 P, NB, SUB = pyr["points"], pyr["neighbors"], pyr["subsampling"]
+ORDER = [gp.table("order", s) for s in range(5)] if os.environ.get("BG_ORDER", "1") == "1" else [None] * 5
 # (C_in, C_out, query stage, support stage, table) of the 14 KPConv calls (experiments/backbone.py:11-70)
 layers = [(1, 64, 0, 0, NB[0]), (32, 32, 0, 0, NB[0])]
 for s_ in range(1, 5):
@@ -28,7 +30,7 @@ torch.manual_seed(0)
 kp = (torch.randn(15, 3) * 0.4).cuda()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 tot_b = tot_t = 0.0
-print(f"RDM_GATHER_VEC={os.environ.get('RDM_GATHER_VEC', '4')} source={src}")
+print(f"RDM_GATHER_VEC={os.environ.get('RDM_GATHER_VEC', '4')} BG_ORDER={os.environ.get('BG_ORDER', '1')} source={src}")
 for (cin, cout, qs, ss, tab) in layers:
     m, h = tab.shape
     n = P[ss].shape[0]
@@ -40,7 +42,7 @@ for (cin, cout, qs, ss, tab) in layers:
     hk = ops._host_copy(kp)
     def run():
         L.call("rdm_kpconv_gather", L.ptr(feats), L.ptr(P[qs]), L.ptr(P[ss]), L.ptr(tab), 4, L.ptr(kp), hk.data_ptr(),
-               float(sigma), m, n, h, cin, L.ptr(out), L.ptr(rowpos), L.stream())
+               float(sigma), m, n, h, cin, L.ptr(ORDER[qs]), L.ptr(out), L.ptr(rowpos), L.stream())
     iters = int(os.environ.get('BG_ITERS', '10'))
     for _ in range(3 if iters > 1 else 0):
         run()

@@ -134,3 +134,58 @@ def test_radius_search_streaming_topk_overflow():
     ref = OP.radius_search(s, s, lens, lens, 2.5, 12, "port")
     got = ops.radius_search(cu(s), cu(s), cu(lens), cu(lens), 2.5, 12).cpu().numpy()
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("pair", [("s000000", "s000004"), ("s000000", "s000007")])
+def test_build_pyramid_single_call_equals_oracle(scans, pair):
+    """rdm_build_pyramid (one host call, one sync, int32 fixed-width tables) == the oracle's pyramid: points bit-exact,
+    tables equal over the reference width and padding beyond it, upsampling = column 0, orders are permutations."""
+    from rdmnet_b200.model import build_pyramid_gpu
+    a, b = scans[pair[0]], scans[pair[1]]
+    lim = [65, 63, 69, 70, 81]
+    ref = OP.precompute_pyramid(np.concatenate([a, b]), [len(a), len(b)], 5, 0.3, 4.25 * 0.3, lim, "port")
+    gp = build_pyramid_gpu(cu(np.concatenate([a, b])), torch.tensor([len(a), len(b)]).cuda(), 5, 0.3, 4.25 * 0.3, lim)
+    d = gp.as_data_dict()
+    for s in range(5):
+        assert gp.lengths_host[s] == [int(x) for x in ref["lengths"][s]]
+        assert np.array_equal(d["lengths"][s].cpu().numpy(), ref["lengths"][s])
+        assert np.array_equal(d["points"][s].cpu().numpy().view(np.uint32), ref["points"][s].view(np.uint32)), f"points[{s}]"
+        order = gp.table("order", s).cpu().numpy()
+        assert np.array_equal(np.sort(order), np.arange(ref["points"][s].shape[0])), f"order[{s}]"
+
+    def same(got, want, n_support, name):
+        got = got.cpu().numpy()
+        w = want.shape[1]
+        assert got.shape[0] == want.shape[0] and got.shape[1] >= w, name
+        assert np.array_equal(got[:, :w], want), name
+        assert (got[:, w:] == n_support).all(), name + " padding"
+
+    for s in range(5):
+        same(d["neighbors"][s], ref["neighbors"][s], ref["points"][s].shape[0], f"neighbors[{s}]")
+        if s < 4:
+            same(d["subsampling"][s], ref["subsampling"][s], ref["points"][s].shape[0], f"subsampling[{s}]")
+            if s == 0:
+                assert d["upsampling"][0] is None
+            else:
+                assert np.array_equal(d["upsampling"][s].cpu().numpy()[:, 0], ref["upsampling"][s][:, 0]), f"upsampling[{s}]"
+
+
+def test_nms_fixpoint_equals_sequential_rule():
+    """rdm_nms (parallel fixpoint) == the sequential greedy loop of rdmnet/vote/vote.py:33-40, incl. compaction."""
+    from rdmnet_b200 import ops
+    rng = np.random.default_rng(5)
+    for n, split, r in ((842, 431, 2.4), (3000, 1400, 3.0), (50, 20, 100.0), (1, 1, 1.0)):
+        pts = rand_cloud(rng, n, (80, 60, 4))
+        lens = np.array([split, n - split], np.int64)
+        nb = OP.radius_search(pts, pts, lens, lens, r, 81, "port")
+        sel = np.zeros(n + 1, bool)
+        for i in range(n):
+            if sel[nb[i]].sum() == 0:
+                sel[i] = True
+        mask, idx, counts = ops.nms(cu(nb), split=split)
+        assert np.array_equal(mask.cpu().numpy(), sel[:n])
+        c = counts.tolist()
+        want = np.nonzero(sel[:n])[0]
+        assert c == [int((want < split).sum()), int((want >= split).sum())]
+        assert np.array_equal(idx.cpu().numpy()[:len(want)], want)
+        assert np.array_equal(ops.nms(cu(nb.astype(np.int32))).cpu().numpy(), sel[:n])
