@@ -165,6 +165,8 @@ typedef struct {
   const float *w, *b;       /* nn.Linear weight [c_out, c_in], bias (w == NULL: identity / absent) */
   const float *gn_w, *gn_b; /* GroupNorm affine (NULL: no norm, LastUnaryBlock) */
   int c_in, c_out;
+  int ldw;                  /* row stride of w in floats (0 = c_in); a stride padded to a multiple of 4 lets a layer with
+                             * c_in % 4 != 0 (decoder4: 1281) take the TMA / tensor-core GEMM */
 } rdm_unary_desc;
 typedef struct {
   rdm_unary_desc unary1, unary2, shortcut;

@@ -82,7 +82,8 @@ class TfAttnJob(ctypes.Structure):
 
 
 class UnaryDesc(ctypes.Structure):
-    _fields_ = [("w", c_void_p), ("b", c_void_p), ("gn_w", c_void_p), ("gn_b", c_void_p), ("c_in", c_int), ("c_out", c_int)]
+    _fields_ = [("w", c_void_p), ("b", c_void_p), ("gn_w", c_void_p), ("gn_b", c_void_p), ("c_in", c_int), ("c_out", c_int),
+                ("ldw", c_int)]
 
 
 class BlockDesc(ctypes.Structure):

@@ -42,6 +42,24 @@ void rdm_prof_end(int id, cudaStream_t stream);
 #define RDM_PROF_KPCONV_GATHER 1
 #define RDM_PROF_KPCONV_GEMM 2
 
+// internal (not part of the C ABI): Linear with GroupNorm statistics fused into the epilogue (dense.cu / gemm_tc.cu),
+// the two halves of GroupNorm (dense.cu), the KPConv gather with a ready-made row-positivity table (kpconv.cu)
+int rdm_linear_gn(const float* A, int lda, const float* B, int ldb, int b_is_nk, const float* bias, float* C, int ldc, int M,
+                  int N, int K, int act, void* workspace, size_t workspace_bytes, double* gn_stats, int gn_cpg,
+                  int* stats_fused, cudaStream_t stream);
+int rdm_groupnorm_stats(const float* x, int N, int C, int groups, double* stats_zeroed, cudaStream_t stream);
+int rdm_groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta, const float* residual,
+                        float* y, int N, int C, int groups, float eps, int act, float slope, unsigned char* rowpos_out,
+                        cudaStream_t stream);
+
+int rdm_kpconv_gather_impl(const float* s_feats, const float* q_points, const float* s_points, const void* neighbor_indices,
+                           int index_bytes, const float* kernel_points, const float* h_kernel_points, float sigma, int M, int N,
+                           int H, int C_in, const int* query_order, float* out_weighted, unsigned char* rowpos_scratch,
+                           int rowpos_ready, cudaStream_t stream);
+
+int rdm_upsample_concat_ld(const float* feats, const void* upsample_indices, int index_bytes, int index_stride,
+                           const float* skip, int M, int N, int C1, int C2, float* out, int ld_out, cudaStream_t stream);
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

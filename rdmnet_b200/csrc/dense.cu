@@ -193,6 +193,51 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
   C[(size_t)m * ldc + n] = s;
 }
 
+// Split-K reduction with the GroupNorm statistics of the result fused in (N % 32 == 0, cpg a power of two).
+// Block = 8 warps on a 64-row x 32-column panel: lane = column, so the column sums accumulate in registers with no
+// shuffles; one shared-memory fold over the 8 warps, one segmented shuffle fold over the cpg columns of a group and
+// one pair of double atomics per group per block.
+__global__ void __launch_bounds__(256) splitk_reduce_stats_kernel(const float* __restrict__ part, int splits,
+                                                                  const float* __restrict__ bias, float* __restrict__ C,
+                                                                  int ldc, int M, int N, double* __restrict__ stats,
+                                                                  int cpg) {
+  __shared__ float s_s[8][32], s_q[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane, r0 = blockIdx.y * 64;
+  const float b = bias ? bias[col] : 0.f;
+  float cs = 0.f, cq = 0.f;
+  for (int r = r0 + warp; r < min(M, r0 + 64); r += 8) {
+    const size_t e = (size_t)r * N + col;
+    float v = 0.f;
+    for (int z = 0; z < splits; z++) v += part[(size_t)z * M * N + e];
+    v += b;
+    C[(size_t)r * ldc + col] = v;
+    cs += v;
+    cq = fmaf(v, v, cq);
+  }
+  s_s[warp][lane] = cs;
+  s_q[warp][lane] = cq;
+  __syncthreads();
+  if (warp == 0) {
+    cs = cq = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      cs += s_s[w][lane];
+      cq += s_q[w][lane];
+    }
+    const int span = cpg < 32 ? cpg : 32;
+    for (int o = 1; o < span; o <<= 1) {
+      cs += __shfl_xor_sync(FULL_MASK, cs, o);
+      cq += __shfl_xor_sync(FULL_MASK, cq, o);
+    }
+    if ((lane & (span - 1)) == 0) {
+      const int g = col / cpg;
+      atomicAdd(&stats[2 * g], (double)cs);
+      atomicAdd(&stats[2 * g + 1], (double)cq);
+    }
+  }
+}
+
 static inline int aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 extern "C" size_t rdm_linear_workspace(int M, int N, int K) {
@@ -201,11 +246,23 @@ extern "C" size_t rdm_linear_workspace(int M, int N, int K) {
 }
 
 int rdm_linear_tc(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N, int K,
-                  int act, void* workspace, size_t workspace_bytes, int* out_splits, cudaStream_t stream);  // gemm_tc.cu
+                  int act, void* workspace, size_t workspace_bytes, int* out_splits, double* gn_stats, int gn_cpg,
+                  int* out_stats_fused, cudaStream_t stream);  // gemm_tc.cu
 
 extern "C" int rdm_linear(const float* A, int lda, const float* B, int ldb, int b_is_nk, const float* bias, float* C,
                           int ldc, int M, int N, int K, int act, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  return rdm_linear_gn(A, lda, B, ldb, b_is_nk, bias, C, ldc, M, N, K, act, workspace, workspace_bytes, nullptr, 0, nullptr,
+                       stream);
+}
+
+// rdm_linear + optional fused GroupNorm statistics of the output: when the shape qualifies, {sum, sumsq} of every group
+// (cpg consecutive output channels) are accumulated into gn_stats (pre-zeroed doubles) by the GEMM epilogue and
+// *stats_fused = 1; otherwise *stats_fused = 0 and the caller runs the stand-alone statistics pass.
+int rdm_linear_gn(const float* A, int lda, const float* B, int ldb, int b_is_nk, const float* bias, float* C, int ldc, int M,
+                  int N, int K, int act, void* workspace, size_t workspace_bytes, double* gn_stats, int gn_cpg,
+                  int* stats_fused, cudaStream_t stream) {
   RDM_CHECK_ARG(M >= 0 && N >= 1 && K >= 1, "rdm_linear: bad shape M=%d N=%d K=%d", M, N, K);
+  if (stats_fused) *stats_fused = 0;
   if (M == 0) return RDM_OK;
   // tensor-core path (tcgen05 kind::tf32, 3-term split, fp32-level accuracy) for nn.Linear-layout weights
   static int use_tc = -1;
@@ -215,9 +272,17 @@ extern "C" int rdm_linear(const float* A, int lda, const float* B, int ldb, int 
   }
   if (use_tc && b_is_nk && M >= 64) {
     int tc_splits = 1;
-    int rc = rdm_linear_tc(A, lda, B, ldb, bias, C, ldc, M, N, K, act, workspace, workspace_bytes, &tc_splits, stream);
+    int rc = rdm_linear_tc(A, lda, B, ldb, bias, C, ldc, M, N, K, act, workspace, workspace_bytes, &tc_splits, gn_stats, gn_cpg,
+                           stats_fused, stream);
     if (rc == RDM_OK && tc_splits > 1) {
-      splitk_reduce_kernel<<<cdiv((long long)M * N, 256), 256, 0, stream>>>((const float*)workspace, tc_splits, bias, C, ldc, M, N, act);
+      const bool pow2 = gn_cpg >= 1 && (gn_cpg & (gn_cpg - 1)) == 0 && (gn_cpg <= 32 || gn_cpg % 32 == 0);
+      if (gn_stats != nullptr && act == 0 && N % 32 == 0 && pow2) {
+        splitk_reduce_stats_kernel<<<dim3(N / 32, cdiv(M, 64)), 256, 0, stream>>>((const float*)workspace, tc_splits, bias, C,
+                                                                                   ldc, M, N, gn_stats, gn_cpg);
+        if (stats_fused) *stats_fused = 1;
+      } else {
+        splitk_reduce_kernel<<<cdiv((long long)M * N, 256), 256, 0, stream>>>((const float*)workspace, tc_splits, bias, C, ldc, M, N, act);
+      }
       RDM_LAUNCH_CHECK();
     }
     if (rc != -1) return rc;
@@ -316,6 +381,102 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float* __res
   }
 }
 
+// Vectorised apply: LPR lanes own one row (LPR = C/4 for C <= 128, else 32 lanes striding 128 channels), float4 loads and
+// stores, per-channel {mean, rstd*gamma, beta} staged once per CTA in shared memory. The lanes of a row also have its
+// channel sum for free, so the kernel can emit rowpos[r] = (sum_c y[r,c] > 0): the neighbour-count predicate of the
+// KPConv that consumes y (kpconv.py:113-114) - no separate pass over the features.
+template <int LPR>
+__global__ void __launch_bounds__(256) groupnorm_apply_vec_kernel(const float* __restrict__ x, const double* __restrict__ stats,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  const float* __restrict__ res, float* __restrict__ y, int N, int C,
+                                                                  int G, float eps, int act, float slope,
+                                                                  unsigned char* __restrict__ rowpos) {
+  extern __shared__ float s_par[];  // mean[C], scale[C], beta[C]
+  float *s_mean = s_par, *s_scale = s_par + C, *s_beta = s_par + 2 * C;
+  const int tid = threadIdx.x, cpg = C / G;
+  for (int c = tid; c < C; c += 256) {
+    const int g = c / cpg;
+    const double cnt = (double)N * cpg;
+    const double mean = stats[2 * g] / cnt;
+    double var = stats[2 * g + 1] / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[c] = (float)mean;
+    s_scale[c] = (float)(1.0 / sqrt(var + (double)eps)) * gamma[c];
+    s_beta[c] = beta[c];
+  }
+  __syncthreads();
+  constexpr int RPW = 32 / LPR;  // rows per warp
+  const int lane = tid & 31, t = lane % LPR, sub = lane / LPR;
+  const int warps = (gridDim.x * 256) >> 5, gw = (blockIdx.x * 256 + tid) >> 5;
+  for (int r0 = gw * RPW; r0 < N; r0 += warps * RPW) {
+    const int r = r0 + sub;
+    float rs = 0.f;
+    if (r < N) {
+      for (int c = 4 * t; c < C; c += 4 * LPR) {
+        const size_t e = (size_t)r * C + c;
+        const float4 v = *(const float4*)(x + e);
+        const float4 m = *(const float4*)(s_mean + c), sc = *(const float4*)(s_scale + c), b = *(const float4*)(s_beta + c);
+        float4 o = make_float4((v.x - m.x) * sc.x + b.x, (v.y - m.y) * sc.y + b.y, (v.z - m.z) * sc.z + b.z,
+                               (v.w - m.w) * sc.w + b.w);
+        if (res != nullptr) {
+          const float4 q = *(const float4*)(res + e);
+          o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+        }
+        if (act == 1) {
+          o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
+          o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
+        }
+        *(float4*)(y + e) = o;
+        rs += (o.x + o.y) + (o.z + o.w);
+      }
+    }
+    if (rowpos != nullptr) {
+#pragma unroll
+      for (int o = LPR >> 1; o > 0; o >>= 1) rs += __shfl_xor_sync(FULL_MASK, rs, o);
+      if (t == 0 && r < N) rowpos[r] = rs > 0.f ? 1 : 0;
+    }
+  }
+}
+
+int rdm_groupnorm_stats(const float* x, int N, int C, int groups, double* stats_zeroed, cudaStream_t stream) {
+  if (N == 0) return RDM_OK;
+  int rows = 64;
+  while (rows > 4 && cdiv(N, rows) < 296) rows >>= 1;
+  groupnorm_stats_kernel<<<cdiv(N, rows), 256, 2 * C * sizeof(float), stream>>>(x, N, C, groups, rows, stats_zeroed);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
+
+int rdm_groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta, const float* residual,
+                        float* y, int N, int C, int groups, float eps, int act, float slope, unsigned char* rowpos_out,
+                        cudaStream_t stream) {
+  if (N == 0) return RDM_OK;
+  const bool al = (((uintptr_t)x | (uintptr_t)y | (uintptr_t)residual) & 15) == 0;
+  const int lpr = C <= 128 ? C / 4 : 32;
+  if (al && C % 4 == 0 && (lpr == 8 || lpr == 16 || lpr == 32) && (C <= 128 || C % 128 == 0) && C <= 4096) {
+    const int rpw = 32 / lpr;
+    const long long warps_needed = cdiv(N, rpw);
+    const int grid = (int)min((long long)148 * 4, (warps_needed + 7) / 8);
+    const size_t smem = 3 * (size_t)C * sizeof(float);
+#define GN_APPLY(LPRv)                                                                                               \
+  groupnorm_apply_vec_kernel<LPRv><<<grid, 256, smem, stream>>>(x, stats, gamma, beta, residual, y, N, C, groups, eps, act, \
+                                                                slope, rowpos_out)
+    if (lpr == 8) GN_APPLY(8);
+    else if (lpr == 16) GN_APPLY(16);
+    else GN_APPLY(32);
+#undef GN_APPLY
+    RDM_LAUNCH_CHECK();
+    return RDM_OK;
+  }
+  RDM_CHECK_ARG(rowpos_out == nullptr, "rdm_groupnorm_apply: row-positivity output needs the vectorised path (C=%d)", C);
+  long long total = (long long)N * C;
+  int grid = (int)min((long long)148 * 8, (total + 255) / 256);
+  groupnorm_apply_kernel<<<grid, 256, 2 * groups * sizeof(float), stream>>>(x, stats, gamma, beta, residual, y, N, C, groups, eps,
+                                                                           act, slope);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
+
 extern "C" int rdm_groupnorm(const float* x, const float* gamma, const float* beta, const float* residual, float* y,
                              int N, int C, int groups, float eps, int act, float slope, double* stats_scratch,
                              cudaStream_t stream) {
@@ -323,16 +484,8 @@ extern "C" int rdm_groupnorm(const float* x, const float* gamma, const float* be
   RDM_CHECK_ARG(groups <= 1024 && C <= 6144, "rdm_groupnorm: shape too large");
   if (N == 0) return RDM_OK;
   RDM_CUDA(cudaMemsetAsync(stats_scratch, 0, sizeof(double) * 2 * groups, stream));
-  int rows = 64;
-  while (rows > 4 && cdiv(N, rows) < 296) rows >>= 1;
-  groupnorm_stats_kernel<<<cdiv(N, rows), 256, 2 * C * sizeof(float), stream>>>(x, N, C, groups, rows, stats_scratch);
-  RDM_LAUNCH_CHECK();
-  long long total = (long long)N * C;
-  int grid = (int)min((long long)148 * 8, (total + 255) / 256);
-  groupnorm_apply_kernel<<<grid, 256, 2 * groups * sizeof(float), stream>>>(x, stats_scratch, gamma, beta, residual, y, N,
-                                                                           C, groups, eps, act, slope);
-  RDM_LAUNCH_CHECK();
-  return RDM_OK;
+  if (int rc = rdm_groupnorm_stats(x, N, C, groups, stats_scratch, stream)) return rc;
+  return rdm_groupnorm_apply(x, stats_scratch, gamma, beta, residual, y, N, C, groups, eps, act, slope, nullptr, stream);
 }
 
 // ------------------------------------------------------------------------------------------------- LayerNorm

@@ -83,6 +83,43 @@ __device__ __forceinline__ uint32_t sel32(const uint32_t (&r)[32], int j) {
   return v;
 }
 
+// GroupNorm statistics fused into a GEMM epilogue. The warp holds a 32 (rows = lanes) x 32 (columns = v[0..31]) slab
+// of the output; a 5-step butterfly (31 shuffles per quantity) leaves lane L with the sum over the 32 rows of column L,
+// a segmented shuffle reduction folds the cpg columns of a group, and one lane per group adds {sum, sumsq} to the
+// double accumulators stats[2g], stats[2g+1]. cpg is a power of two; groups never straddle a 32-column slab unless
+// cpg > 32, where the whole slab belongs to one group.
+__device__ __forceinline__ void gn_slab_stats(const float (&v)[32], bool row_valid, int col0, int cpg, int lane,
+                                              double* __restrict__ stats) {
+  float s[32], q[32];
+#pragma unroll
+  for (int j = 0; j < 32; j++) {
+    s[j] = row_valid ? v[j] : 0.f;
+    q[j] = s[j] * s[j];
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; j++) {
+      const float ks = up ? s[j + off] : s[j], ss = up ? s[j] : s[j + off];
+      const float kq = up ? q[j + off] : q[j], sq = up ? q[j] : q[j + off];
+      s[j] = ks + __shfl_xor_sync(FULL_MASK, ss, off);
+      q[j] = kq + __shfl_xor_sync(FULL_MASK, sq, off);
+    }
+  }
+  float cs = s[0], cq = q[0];  // column col0 + lane
+  const int span = cpg < 32 ? cpg : 32;
+  for (int o = 1; o < span; o <<= 1) {
+    cs += __shfl_xor_sync(FULL_MASK, cs, o);
+    cq += __shfl_xor_sync(FULL_MASK, cq, o);
+  }
+  if ((lane & (span - 1)) == 0) {
+    const int g = (col0 + lane) / cpg;
+    atomicAdd(&stats[2 * g], (double)cs);
+    atomicAdd(&stats[2 * g + 1], (double)cq);
+  }
+}
+
 template <int BN, int STAGES>
 struct TcSmem {
   // every buffer is a multiple of 1024 B: the 128-byte swizzle pattern repeats every 8 rows
@@ -99,6 +136,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const __grid
                                                                    const __grid_constant__ CUtensorMap map_b,
                                                                    const float* __restrict__ bias, float* __restrict__ C,
                                                                    int ldc, int M, int N, int K, int act, int kb_per_split,
+                                                                   double* __restrict__ gn_stats, int gn_cpg,
                                                                    long long* __restrict__ dbg) {
   extern __shared__ unsigned char smem_raw[];
   using Smem = TcSmem<BN, STAGES>;
@@ -225,36 +263,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const __grid
             "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < M) {
-        if (fast) {  // whole 32-column slab inside N, 16-byte aligned rows: float4 bias, float4 stores, no per-element checks
-          const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c0);
+      if (fast) {  // whole 32-column slab inside N, 16-byte aligned rows: float4 bias, float4 stores, no per-element checks
+        const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c0);
+        float vals[32];
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                                   __uint_as_float(r[4 * j + 3]));
-            if (bias != nullptr) {
-              const float4 b = __ldg(b4 + j);
-              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-            }
-            if (act == 1) {
-              v.x = v.x > 0.f ? v.x : 0.1f * v.x; v.y = v.y > 0.f ? v.y : 0.1f * v.y;
-              v.z = v.z > 0.f ? v.z : 0.1f * v.z; v.w = v.w > 0.f ? v.w : 0.1f * v.w;
-            } else if (act == 2) {
-              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-            }
-            *reinterpret_cast<float4*>(crow + n0 + c0 + 4 * j) = v;
+        for (int j = 0; j < 8; j++) {
+          float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                 __uint_as_float(r[4 * j + 3]));
+          if (bias != nullptr) {
+            const float4 b = __ldg(b4 + j);
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
           }
-        } else {
+          if (act == 1) {
+            v.x = v.x > 0.f ? v.x : 0.1f * v.x; v.y = v.y > 0.f ? v.y : 0.1f * v.y;
+            v.z = v.z > 0.f ? v.z : 0.1f * v.z; v.w = v.w > 0.f ? v.w : 0.1f * v.w;
+          } else if (act == 2) {
+            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+          }
+          if (row < M) *reinterpret_cast<float4*>(crow + n0 + c0 + 4 * j) = v;
+          vals[4 * j] = v.x; vals[4 * j + 1] = v.y; vals[4 * j + 2] = v.z; vals[4 * j + 3] = v.w;
+        }
+        if (gn_stats != nullptr) gn_slab_stats(vals, row < M, n0 + c0, gn_cpg, lane, gn_stats);
+      } else if (row < M) {
 #pragma unroll 1
-          for (int j = 0; j < 32; j++) {
-            const int col = n0 + c0 + j;
-            if (col >= N) break;
-            float v = __uint_as_float(sel32(r, j));
-            if (bias != nullptr) v += __ldg(bias + col);
-            if (act == 1) v = v > 0.f ? v : 0.1f * v;
-            else if (act == 2) v = fmaxf(v, 0.f);
-            crow[col] = v;
-          }
+        for (int j = 0; j < 32; j++) {
+          const int col = n0 + c0 + j;
+          if (col >= N) break;
+          float v = __uint_as_float(sel32(r, j));
+          if (bias != nullptr) v += __ldg(bias + col);
+          if (act == 1) v = v > 0.f ? v : 0.1f * v;
+          else if (act == 2) v = fmaxf(v, 0.f);
+          crow[col] = v;
         }
       }
     }
@@ -306,7 +345,7 @@ unsigned long long g_tc_launches = 0;
 
 template <int BN, int STAGES>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, float* C, int ldc, int M, int N, int K, int act,
-              int splits, int kb_per_split, cudaStream_t stream, long long* dbg = nullptr) {
+              int splits, int kb_per_split, double* gn_stats, int gn_cpg, cudaStream_t stream, long long* dbg = nullptr) {
   const size_t smem = sizeof(TcSmem<BN, STAGES>) + 1024;
   static bool attr = false;
   if (!attr) {
@@ -314,7 +353,7 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, f
     attr = true;
   }
   dim3 grid(cdiv(N, BN), cdiv(M, TC_BM), splits);
-  gemm_tf32x3_kernel<BN, STAGES><<<grid, TC_THREADS, smem, stream>>>(ma, mb, bias, C, ldc, M, N, K, act, kb_per_split, dbg);
+  gemm_tf32x3_kernel<BN, STAGES><<<grid, TC_THREADS, smem, stream>>>(ma, mb, bias, C, ldc, M, N, K, act, kb_per_split, gn_stats, gn_cpg, dbg);
   RDM_LAUNCH_CHECK();
   __atomic_fetch_add(&g_tc_launches, 1ull, __ATOMIC_RELAXED);
   return RDM_OK;
@@ -324,9 +363,13 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, f
 // Returns RDM_OK if the GEMM was launched on the tensor-core path, -1 if the shape / alignment does not qualify (the
 // caller then uses the SIMT kernel), or an error code. With a workspace, small-tile-count problems are split along K into
 // partial tiles (deterministic: `*out_splits` partials that the caller reduces with bias / activation).
+// gn_stats / gn_cpg (optional): GroupNorm {sum, sumsq} accumulation of the OUTPUT in the epilogue (N % 32 == 0, cpg a power
+// of two, aligned rows, no split-K); *out_stats_fused says whether it happened.
 int rdm_linear_tc(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N, int K,
-                  int act, void* workspace, size_t workspace_bytes, int* out_splits, cudaStream_t stream) {
+                  int act, void* workspace, size_t workspace_bytes, int* out_splits, double* gn_stats, int gn_cpg,
+                  int* out_stats_fused, cudaStream_t stream) {
   *out_splits = 1;
+  if (out_stats_fused) *out_stats_fused = 0;
   if (M < 1 || N < 8 || K < 8) return -1;
   if ((lda % 4) || (ldb % 4) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) return -1;  // TMA: 16-byte strides / base
   if (!load_encoder()) return -1;
@@ -355,8 +398,14 @@ int rdm_linear_tc(const float* A, int lda, const float* B, int ldb, const float*
   const int ldo = splits > 1 ? N : ldc;
   const float* b = splits > 1 ? nullptr : bias;
   const int a = splits > 1 ? 0 : act;
-  if (narrow) return launch_tc<64, 4>(ma, mb, b, out, ldo, M, N, K, a, splits, kps, stream);
-  return launch_tc<128, 3>(ma, mb, b, out, ldo, M, N, K, a, splits, kps, stream);
+  double* st = nullptr;
+  if (gn_stats != nullptr && splits == 1 && act == 0 && N % 32 == 0 && gn_cpg >= 1 && (gn_cpg & (gn_cpg - 1)) == 0 &&
+      (gn_cpg <= 32 || gn_cpg % 32 == 0) && ldc % 4 == 0 && (((uintptr_t)C | (uintptr_t)bias) & 15) == 0) {
+    st = gn_stats;
+    if (out_stats_fused) *out_stats_fused = 1;
+  }
+  if (narrow) return launch_tc<64, 4>(ma, mb, b, out, ldo, M, N, K, a, splits, kps, st, gn_cpg, stream);
+  return launch_tc<128, 3>(ma, mb, b, out, ldo, M, N, K, a, splits, kps, st, gn_cpg, stream);
 }
 
 extern "C" unsigned long long rdm_tc_gemm_count(void) { return __atomic_load_n(&g_tc_launches, __ATOMIC_RELAXED); }
@@ -376,7 +425,7 @@ extern "C" int rdm_debug_gemm_timeline(int M, int N, int K) {
   if (!make_map(&ma, A, M, K, K, TC_BM) || !make_map(&mb, B, N, K, K, 64)) return -1;
   for (int rep = 0; rep < 3; rep++) {
     RDM_CUDA(cudaMemset(dbg, 0, 16 * 8));
-    int rc = launch_tc<64, 4>(ma, mb, nullptr, C, N, M, N, K, 0, 1, cdiv(K, TC_BK), 0, dbg);
+    int rc = launch_tc<64, 4>(ma, mb, nullptr, C, N, M, N, K, 0, 1, cdiv(K, TC_BK), nullptr, 0, 0, dbg);
     if (rc != RDM_OK) return rc;
     RDM_CUDA(cudaDeviceSynchronize());
     long long h[16];

@@ -444,12 +444,22 @@ extern "C" int rdm_kpconv_gather(const float* s_feats, const float* q_points, co
                                  const float* h_kernel_points, float sigma,
                                  int M, int N, int H, int C_in, const int* query_order, float* out_weighted,
                                  unsigned char* rowpos_scratch, cudaStream_t stream) {
+  return rdm_kpconv_gather_impl(s_feats, q_points, s_points, neighbor_indices, index_bytes, kernel_points, h_kernel_points, sigma,
+                                M, N, H, C_in, query_order, out_weighted, rowpos_scratch, 0, stream);
+}
+
+// rowpos_ready != 0: `rowpos` already holds (sum_c s_feats[n,c] > 0) for every support row (written by the producer of
+// s_feats, rdm_groupnorm_apply), so the prepass is skipped.
+int rdm_kpconv_gather_impl(const float* s_feats, const float* q_points, const float* s_points, const void* neighbor_indices,
+                           int index_bytes, const float* kernel_points, const float* h_kernel_points, float sigma, int M, int N,
+                           int H, int C_in, const int* query_order, float* out_weighted, unsigned char* rowpos_scratch,
+                           int rowpos_ready, cudaStream_t stream) {
   RDM_CHECK_ARG(M >= 0 && N >= 0 && H >= 1 && C_in >= 1 && sigma > 0.f, "rdm_kpconv_gather: bad arguments");
   RDM_CHECK_ARG(index_bytes == 4 || index_bytes == 8, "rdm_kpconv_gather: index_bytes must be 4 or 8");
   RDM_CHECK_ARG(kernel_points != nullptr && h_kernel_points != nullptr, "rdm_kpconv_gather: kernel points missing");
   if (M == 0) return RDM_OK;
   const int prof = rdm_prof_begin(RDM_PROF_KPCONV_GATHER, M, N, H, C_in, stream);
-  if (C_in > 1 && N > 0) {
+  if (C_in > 1 && N > 0 && !rowpos_ready) {
     row_positive_kernel<<<cdiv(N, 8), 256, 0, stream>>>(s_feats, N, C_in, rowpos_scratch);
     RDM_LAUNCH_CHECK();
   }
@@ -505,11 +515,15 @@ extern "C" int rdm_maxpool(const float* feats, const void* neighbor_indices, int
 template <typename IdxT>
 __global__ void upsample_concat_kernel(const float* __restrict__ f, const IdxT* __restrict__ idx, int idx_stride,
                                        const float* __restrict__ skip, int M, int N, int C1, int C2,
-                                       float* __restrict__ out) {
+                                       float* __restrict__ out, int ld_out) {
   long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   int C = C1 + C2;
-  if (e >= (long long)M * C) return;
-  int m = (int)(e / C), c = (int)(e - (long long)m * C);
+  if (e >= (long long)M * ld_out) return;
+  int m = (int)(e / ld_out), c = (int)(e - (long long)m * ld_out);
+  if (c >= C) {  // row padding (ld_out > C): defined zeros
+    out[e] = 0.f;
+    return;
+  }
   float v;
   if (c < C1) {
     long long j = (long long)idx[(size_t)m * idx_stride];
@@ -522,15 +536,21 @@ __global__ void upsample_concat_kernel(const float* __restrict__ f, const IdxT* 
 
 extern "C" int rdm_upsample_concat(const float* feats, const void* upsample_indices, int index_bytes, int index_stride,
                                    const float* skip, int M, int N, int C1, int C2, float* out, cudaStream_t stream) {
+  return rdm_upsample_concat_ld(feats, upsample_indices, index_bytes, index_stride, skip, M, N, C1, C2, out, C1 + C2, stream);
+}
+
+int rdm_upsample_concat_ld(const float* feats, const void* upsample_indices, int index_bytes, int index_stride,
+                           const float* skip, int M, int N, int C1, int C2, float* out, int ld_out, cudaStream_t stream) {
   RDM_CHECK_ARG(index_bytes == 4 || index_bytes == 8, "rdm_upsample_concat: index_bytes must be 4 or 8");
+  RDM_CHECK_ARG(ld_out >= C1 + C2, "rdm_upsample_concat: output row stride too small");
   if (M == 0) return RDM_OK;
-  long long total = (long long)M * (C1 + C2);
+  long long total = (long long)M * ld_out;
   if (index_bytes == 8)
     upsample_concat_kernel<int64_t><<<cdiv(total, 256), 256, 0, stream>>>(feats, (const int64_t*)upsample_indices,
-                                                                         index_stride, skip, M, N, C1, C2, out);
+                                                                         index_stride, skip, M, N, C1, C2, out, ld_out);
   else
     upsample_concat_kernel<int><<<cdiv(total, 256), 256, 0, stream>>>(feats, (const int*)upsample_indices,
-                                                                     index_stride, skip, M, N, C1, C2, out);
+                                                                     index_stride, skip, M, N, C1, C2, out, ld_out);
   RDM_LAUNCH_CHECK();
   return RDM_OK;
 }

@@ -619,11 +619,161 @@ __global__ void __launch_bounds__(160) sinkhorn_kernel(const float* __restrict__
   }
 }
 
+// ---- fast path for 128 x 128 patches (num_points_in_patch = 128, experiments/config.py:100).
+// The padded score matrix is constant over the 100 iterations; only the potentials u, v change. So every thread keeps
+// its share of Z in REGISTERS, twice: as a piece of a row (for u = log_mu - LSE_j(Z + v)) and as a piece of a column
+// (for v = log_nu - LSE_i(Z + u)); shared memory only carries the two potential vectors. Masked rows / columns
+// (-1e12 entries: exp = 0 exactly, learnable_sinkhorn.py:36-47) never influence a live entry, so the live rows and
+// columns (+ the dustbin) are compacted first and the iteration runs on the compacted matrix only. Element e of a
+// compacted axis belongs to quad lane e & 3, slot e >> 2: four lanes share a row / column and fold their partial
+// (max, sum) pairs with two shuffles. Everything is kept in the log2 domain (one MUFU.EX2 per element, no multiply).
+#define SK_N 128
+#define SK_T 33   // ceil(129 / 4) slots per lane
+#define SK_LD 36  // floats between the four lanes' potential slices (16-byte aligned, conflict-free LDS.128)
+#define SK_THREADS 544
+#define SK_NEG -1.0e30f
+
+__device__ __forceinline__ float ex2f(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2f(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// running (m, s) <- fold in z[k0..k0+3] + p[0..3]   (log2 domain, online logsumexp)
+__device__ __forceinline__ void sk_fold4(const float* z, const float4 p, float& m, float& s) {
+  const float t0 = z[0] + p.x, t1 = z[1] + p.y, t2 = z[2] + p.z, t3 = z[3] + p.w;
+  const float mn = fmaxf(fmaxf(m, fmaxf(t0, t1)), fmaxf(t2, t3));
+  s = s * ex2f(m - mn) + ((ex2f(t0 - mn) + ex2f(t1 - mn)) + (ex2f(t2 - mn) + ex2f(t3 - mn)));
+  m = mn;
+}
+
+// one half-iteration: lanes (a, q) with a < n_out produce pot_out[a] = logm[a] - LSE_k(z + pot_in); kc = slots in use
+__device__ __forceinline__ void sk_phase(const float (&z)[SK_T], const float* pot_in, float* pot_out, const float* logm, int a,
+                                         int q, int n_out, int kc) {
+  float m = SK_NEG, s = 0.f;
+  if (a < n_out) {
+    const float4* p4 = (const float4*)(pot_in + q * SK_LD);
+#pragma unroll
+    for (int g = 0; g < 8; g++)
+      if (4 * g < kc) sk_fold4(&z[4 * g], p4[g], m, s);
+    if (kc > 32) {
+      const float t = z[32] + pot_in[q * SK_LD + 32];
+      const float mn = fmaxf(m, t);
+      s = s * ex2f(m - mn) + ex2f(t - mn);
+      m = mn;
+    }
+  }
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {  // fold the four lanes of the row / column
+    const float mo = __shfl_xor_sync(FULL_MASK, m, o), so = __shfl_xor_sync(FULL_MASK, s, o);
+    const float mn = fmaxf(m, mo);
+    s = s * ex2f(m - mn) + so * ex2f(mo - mn);
+    m = mn;
+  }
+  if (a < n_out && q == 0) pot_out[(a & 3) * SK_LD + (a >> 2)] = logm[a] - (m + lg2f(s));
+}
+
+__global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn128_kernel(const float* __restrict__ scores,
+                                                                   const unsigned char* __restrict__ row_masks_nodes,
+                                                                   const unsigned char* __restrict__ col_masks_nodes,
+                                                                   const int64_t* __restrict__ ridx,
+                                                                   const int64_t* __restrict__ sidx,
+                                                                   const float* __restrict__ alpha_ptr, int iters, float inf,
+                                                                   float* __restrict__ out) {
+  __shared__ __align__(16) float us[4 * SK_LD], vs[4 * SK_LD];
+  __shared__ float lmu[SK_N + 4], lnu[SK_N + 4];
+  __shared__ short liveR[SK_N + 1], liveC[SK_N + 1], posR[SK_N + 1], posC[SK_N + 1];
+  __shared__ int s_n[2];
+  const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int a = tid >> 2, q = tid & 3;
+  const unsigned char* rm = ridx ? row_masks_nodes + (size_t)ridx[p] * SK_N : row_masks_nodes + (size_t)p * SK_N;
+  const unsigned char* cm = sidx ? col_masks_nodes + (size_t)sidx[p] * SK_N : col_masks_nodes + (size_t)p * SK_N;
+  const float alpha = *alpha_ptr;
+  const float* sp = scores + (size_t)p * SK_N * SK_N;
+  const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+  if (warp < 2) {  // warp 0 compacts the rows, warp 1 the columns (ballot scan); the dustbin is the last live element
+    const unsigned char* mk = warp == 0 ? rm : cm;
+    short* live = warp == 0 ? liveR : liveC;
+    short* pos = warp == 0 ? posR : posC;
+    int base = 0;
+    for (int c = 0; c < SK_N; c += 32) {
+      const bool on = mk[c + lane] != 0;
+      const unsigned b = __ballot_sync(FULL_MASK, on);
+      const int at = base + __popc(b & ((1u << lane) - 1u));
+      if (on) live[at] = (short)(c + lane);
+      pos[c + lane] = on ? (short)at : (short)-1;
+      base += __popc(b);
+    }
+    if (lane == 0) {
+      live[base] = SK_N;
+      pos[SK_N] = (short)base;
+      s_n[warp] = base + 1;
+    }
+  }
+  for (int i = tid; i < 4 * SK_LD; i += SK_THREADS) {
+    us[i] = 0.f;
+    vs[i] = 0.f;
+  }
+  __syncthreads();
+  const int nR = s_n[0], nC = s_n[1];
+  const float nr = (float)(nR - 1), nc = (float)(nC - 1);
+  const float norm = -logf(nr + nc);  // learnable_sinkhorn.py:49
+  for (int i = tid; i < nR; i += SK_THREADS) lmu[i] = (i < nR - 1 ? norm : logf(nc) + norm) * LOG2E;
+  for (int j = tid; j < nC; j += SK_THREADS) lnu[j] = (j < nC - 1 ? norm : logf(nr) + norm) * LOG2E;
+  // register-resident shares of the compacted matrix (log2 domain); slots beyond the live extent hold SK_NEG (exp2 -> 0)
+  float zr[SK_T], zc[SK_T];
+#pragma unroll
+  for (int k = 0; k < SK_T; k++) {
+    const int e = 4 * k + q;
+    float r = SK_NEG, c = SK_NEG;
+    if (a < nR && e < nC) {
+      const int i = liveR[a], j = liveC[e];
+      r = ((i < SK_N && j < SK_N) ? __ldg(sp + i * SK_N + j) : alpha) * LOG2E;
+    }
+    if (a < nC && e < nR) {
+      const int i = liveR[e], j = liveC[a];
+      c = ((i < SK_N && j < SK_N) ? __ldg(sp + i * SK_N + j) : alpha) * LOG2E;
+    }
+    zr[k] = r;
+    zc[k] = c;
+  }
+  __syncthreads();
+  const int kcC = (nC + 3) >> 2, kcR = (nR + 3) >> 2;
+  for (int it = 0; it < iters; it++) {
+    sk_phase(zr, vs, us, lmu, a, q, nR, kcC);  // u = log_mu - logsumexp_j(Z + v)   (learnable_sinkhorn.py:24-25)
+    __syncthreads();
+    sk_phase(zc, us, vs, lnu, a, q, nC, kcR);  // v = log_nu - logsumexp_i(Z + u)
+    __syncthreads();
+  }
+  float* op = out + (size_t)p * (SK_N + 1) * (SK_N + 1);
+  for (int e = tid; e < (SK_N + 1) * (SK_N + 1); e += SK_THREADS) {
+    const int i = e / (SK_N + 1), j = e - i * (SK_N + 1);
+    const int pr = posR[i], pc = posC[j];
+    float o = -inf;  // masked rows / columns stay at -1e12 (+ finite potentials in the reference): exp() = 0 either way
+    if (pr >= 0 && pc >= 0) {
+      const float z = (i < SK_N && j < SK_N) ? __ldg(sp + i * SK_N + j) : alpha;
+      o = z + (us[(pr & 3) * SK_LD + (pr >> 2)] + vs[(pc & 3) * SK_LD + (pc >> 2)]) * LN2 - norm;
+    }
+    op[e] = o;
+  }
+}
+
 extern "C" int rdm_sinkhorn(const float* scores, int num_patches, int R, int C, const unsigned char* row_masks,
                             const unsigned char* col_masks, const int64_t* row_mask_gather, const int64_t* col_mask_gather,
                             const float* alpha, int num_iterations, float inf, float* out, cudaStream_t stream) {
   RDM_CHECK_ARG(R >= 1 && C >= 1 && R <= 159 && C <= 159, "rdm_sinkhorn: patch size must be <= 159");
   if (num_patches == 0) return RDM_OK;
+  if (R == SK_N && C == SK_N) {
+    sinkhorn128_kernel<<<num_patches, SK_THREADS, 0, stream>>>(scores, row_masks, col_masks, row_mask_gather, col_mask_gather,
+                                                               alpha, num_iterations, inf, out);
+    RDM_LAUNCH_CHECK();
+    return RDM_OK;
+  }
   int R1 = R + 1, C1 = C + 1, ld = (C1 % 2 == 0) ? C1 + 1 : C1;
   size_t smem = ((size_t)R1 * ld + 2 * R1 + 2 * C1) * sizeof(float);
   RDM_CHECK_ARG(smem <= 200 * 1024, "rdm_sinkhorn: patch too large for shared memory");

@@ -32,7 +32,7 @@ struct Arena {
   } while (0)
 
 int linear(Arena& a, const float* A, int lda, const float* W, int ldw, int nk, const float* bias, float* C, int M, int N, int K,
-           cudaStream_t st) {
+           cudaStream_t st, double* gn_stats = nullptr, int gn_cpg = 0, int* stats_fused = nullptr) {
   void* ws = nullptr;
   size_t wsb = 0;
   size_t mark = a.off;
@@ -41,45 +41,79 @@ int linear(Arena& a, const float* A, int lda, const float* W, int ldw, int nk, c
     ws = a.raw(wsb);
   }
   int rc = RDM_OK;
-  if (!a.dry) rc = rdm_linear(A, lda, W, ldw, nk, bias, C, N, M, N, K, 0, ws, wsb, st);
+  if (!a.dry) rc = rdm_linear_gn(A, lda, W, ldw, nk, bias, C, N, M, N, K, 0, ws, wsb, gn_stats, gn_cpg, stats_fused, st);
   a.off = mark;
   return rc;
 }
 
-int group_norm(Arena& a, float* x, const float* g, const float* b, const float* residual, int N, int C, int groups, int act,
-               cudaStream_t st) {
-  size_t mark = a.off;
-  double* stats = (double*)a.raw(sizeof(double) * 2 * groups);
-  int rc = RDM_OK;
-  if (!a.dry) rc = rdm_groupnorm(x, g, b, residual, x, N, C, groups, 1e-5f, act, 0.1f, stats, st);
-  a.off = mark;
-  return rc;
-}
+// GroupNorm statistics slots: one pre-zeroed array of doubles per module run (a single memset instead of one per norm)
+struct StatSlots {
+  double* base = nullptr;
+  int used = 0, cap = 0;
+  double* take(int groups) {
+    double* p = base ? base + (size_t)used * 2 * 64 : nullptr;
+    used++;
+    return p;
+  }
+};
+constexpr int kStatSlots = 96;  // >= number of GroupNorms in one module run; 64 groups max per slot
 
-// UnaryBlock (kpconv/modules.py:78-83): Linear + GroupNorm (+ residual) (+ LeakyReLU); out [M, c_out]
-int unary(Arena& a, const rdm_unary_desc& u, const float* x, int ldx, float* out, int M, int groups, const float* residual, int act,
-          cudaStream_t st) {
-  RDM_TRY(linear(a, x, ldx, u.w, u.c_in, 1, u.b, out, M, u.c_out, u.c_in, st));
-  if (u.gn_w != nullptr) RDM_TRY(group_norm(a, out, u.gn_w, u.gn_b, residual, M, u.c_out, groups, act, st));
+int stat_slots_begin(Arena& a, StatSlots& ss, cudaStream_t st) {
+  ss.base = (double*)a.raw(sizeof(double) * 2 * 64 * kStatSlots);
+  ss.cap = kStatSlots;
+  if (!a.dry) RDM_CUDA(cudaMemsetAsync(ss.base, 0, sizeof(double) * 2 * 64 * kStatSlots, st));
   return RDM_OK;
 }
 
+// out = act(GroupNorm(lin(x)) (+ residual)); the statistics ride in the GEMM epilogue when the shape allows
+int linear_group_norm(Arena& a, StatSlots& ss, const float* x, int ldx, const float* W, int ldw, int nk, const float* bias,
+                      const float* g, const float* b, const float* residual, float* out, int M, int N, int K, int groups, int act,
+                      unsigned char* rowpos_out, cudaStream_t st) {
+  RDM_CHECK_ARG(groups <= 64 && ss.used < ss.cap, "group norm: too many groups / norms in one module run");
+  double* stats = ss.take(groups);
+  int fused = 0;
+  RDM_TRY(linear(a, x, ldx, W, ldw, nk, bias, out, M, N, K, st, stats, N / groups, &fused));
+  if (a.dry) return RDM_OK;
+  if (!fused) RDM_TRY(rdm_groupnorm_stats(out, M, N, groups, stats, st));
+  return rdm_groupnorm_apply(out, stats, g, b, residual, out, M, N, groups, 1e-5f, act, 0.1f, rowpos_out, st);
+}
+
+// UnaryBlock (kpconv/modules.py:78-83): Linear + GroupNorm (+ residual) (+ LeakyReLU); out [M, c_out]
+int unary(Arena& a, StatSlots& ss, const rdm_unary_desc& u, const float* x, int ldx, float* out, int M, int groups,
+          const float* residual, int act, unsigned char* rowpos_out, cudaStream_t st) {
+  const int ldw = u.ldw > 0 ? u.ldw : u.c_in;
+  if (u.gn_w != nullptr)
+    return linear_group_norm(a, ss, x, ldx, u.w, ldw, 1, u.b, u.gn_w, u.gn_b, residual, out, M, u.c_out, u.c_in, groups, act,
+                             rowpos_out, st);
+  return linear(a, x, ldx, u.w, ldw, 1, u.b, out, M, u.c_out, u.c_in, st);
+}
+
 // KPConv.forward (kpconv.py:79-122) + norm_conv + LeakyReLU: out [M, c_mid_out]
-int kpconv_norm(Arena& a, const rdm_block_desc& b, const float* feats, const float* q_pts, const float* s_pts, const void* idx,
-                int index_bytes, int M, int N, int H, const int* order, float* out, int groups, cudaStream_t st) {
+int kpconv_norm(Arena& a, StatSlots& ss, const rdm_block_desc& b, const float* feats, const unsigned char* rowpos_ready,
+                const float* q_pts, const float* s_pts, const void* idx, int index_bytes, int M, int N, int H, const int* order,
+                float* out, int groups, cudaStream_t st) {
   size_t mark = a.off;
   float* gathered = a.f((size_t)M * 15 * b.c_mid_in);
-  unsigned char* rowpos = (unsigned char*)a.raw((size_t)(N > 0 ? N : 1));
+  unsigned char* rowpos = rowpos_ready ? const_cast<unsigned char*>(rowpos_ready) : (unsigned char*)a.raw((size_t)(N > 0 ? N : 1));
   if (!a.dry)
-    RDM_TRY(rdm_kpconv_gather(feats, q_pts, s_pts, idx, index_bytes, b.kernel_points, b.h_kernel_points, b.sigma, M, N, H,
-                              b.c_mid_in, order, gathered, rowpos, st));
+    RDM_TRY(rdm_kpconv_gather_impl(feats, q_pts, s_pts, idx, index_bytes, b.kernel_points, b.h_kernel_points, b.sigma, M, N, H,
+                                   b.c_mid_in, order, gathered, rowpos, rowpos_ready != nullptr, st));
   const int prof = a.dry ? -1 : rdm_prof_begin(RDM_PROF_KPCONV_GEMM, M, 15 * b.c_mid_in, 0, b.c_mid_out, st);
+  const int K = 15 * b.c_mid_in;
+  double* stats = ss.take(groups);
+  int fused = 0;
+  RDM_CHECK_ARG(groups <= 64 && ss.used <= ss.cap, "group norm: too many groups / norms in one module run");
   if (b.kpconv_wt != nullptr)
-    RDM_TRY(linear(a, gathered, 15 * b.c_mid_in, b.kpconv_wt, 15 * b.c_mid_in, 1, b.kpconv_b, out, M, b.c_mid_out, 15 * b.c_mid_in, st));
+    RDM_TRY(linear(a, gathered, K, b.kpconv_wt, K, 1, b.kpconv_b, out, M, b.c_mid_out, K, st, stats, b.c_mid_out / groups, &fused));
   else
-    RDM_TRY(linear(a, gathered, 15 * b.c_mid_in, b.kpconv_w, b.c_mid_out, 0, b.kpconv_b, out, M, b.c_mid_out, 15 * b.c_mid_in, st));
+    RDM_TRY(linear(a, gathered, K, b.kpconv_w, b.c_mid_out, 0, b.kpconv_b, out, M, b.c_mid_out, K, st, stats, b.c_mid_out / groups,
+                   &fused));
   rdm_prof_end(prof, st);
-  RDM_TRY(group_norm(a, out, b.norm_conv_w, b.norm_conv_b, nullptr, M, b.c_mid_out, groups, 1, st));
+  if (!a.dry) {
+    if (!fused) RDM_TRY(rdm_groupnorm_stats(out, M, b.c_mid_out, groups, stats, st));
+    RDM_TRY(rdm_groupnorm_apply(out, stats, b.norm_conv_w, b.norm_conv_b, nullptr, out, M, b.c_mid_out, groups, 1e-5f, 1, 0.1f,
+                                nullptr, st));
+  }
   a.off = mark;
   return RDM_OK;
 }
@@ -88,6 +122,8 @@ int encoder_run(Arena& a, const rdm_block_desc* blocks, int nb, const rdm_pyrami
                 float* const* out_feats, cudaStream_t st) {
   const float* cur = in_feats;
   int cur_stage = 0;
+  StatSlots ss;
+  RDM_TRY(stat_slots_begin(a, ss, st));
   for (int i = 0; i < nb; i++) {
     const rdm_block_desc& b = blocks[i];
     const int s = b.stage;
@@ -101,16 +137,21 @@ int encoder_run(Arena& a, const rdm_block_desc* blocks, int nb, const rdm_pyrami
     float* out = last_of_stage ? (a.dry ? nullptr : out_feats[s]) : a.f((size_t)M * b.c_out);
     size_t mark = a.off;
     if (b.unary2.w == nullptr) {  // ConvBlock (modules.py:143-147)
-      RDM_TRY(kpconv_norm(a, b, cur, q_pts, s_pts, idx, p.index_bytes, M, N, H, p.order[s], out, groups, st));
+      RDM_TRY(kpconv_norm(a, ss, b, cur, nullptr, q_pts, s_pts, idx, p.index_bytes, M, N, H, p.order[s], out, groups, st));
     } else {  // ResidualBlock (modules.py:205-225)
       const float* x = cur;
+      unsigned char* rowpos = nullptr;
       if (b.unary1.w != nullptr) {
         float* t = a.f((size_t)N * b.unary1.c_out);
-        RDM_TRY(unary(a, b.unary1, cur, b.c_in, t, N, groups, nullptr, 1, st));
+        // the GroupNorm apply of unary1 also emits the KPConv neighbour-count predicate of its rows (vectorised path only)
+        const int c1 = b.unary1.c_out;
+        if (b.unary1.gn_w != nullptr && (c1 == 32 || c1 == 64 || c1 == 128 || (c1 % 128 == 0 && c1 <= 4096)))
+          rowpos = (unsigned char*)a.raw((size_t)(N > 0 ? N : 1));
+        RDM_TRY(unary(a, ss, b.unary1, cur, b.c_in, t, N, groups, nullptr, 1, rowpos, st));
         x = t;
       }
       float* c = a.f((size_t)M * b.c_mid_out);
-      RDM_TRY(kpconv_norm(a, b, x, q_pts, s_pts, idx, p.index_bytes, M, N, H, p.order[s], c, groups, st));
+      RDM_TRY(kpconv_norm(a, ss, b, x, rowpos, q_pts, s_pts, idx, p.index_bytes, M, N, H, p.order[s], c, groups, st));
       const float* sc = cur;
       if (b.strided) {
         float* mp = a.f((size_t)M * b.c_in);
@@ -119,10 +160,10 @@ int encoder_run(Arena& a, const rdm_block_desc* blocks, int nb, const rdm_pyrami
       }
       if (b.shortcut.w != nullptr) {
         float* t = a.f((size_t)M * b.c_out);
-        RDM_TRY(unary(a, b.shortcut, sc, b.c_in, t, M, groups, nullptr, 0, st));
+        RDM_TRY(unary(a, ss, b.shortcut, sc, b.c_in, t, M, groups, nullptr, 0, nullptr, st));
         sc = t;
       }
-      RDM_TRY(unary(a, b.unary2, c, b.c_mid_out, out, M, groups, sc, 1, st));
+      RDM_TRY(unary(a, ss, b.unary2, c, b.c_mid_out, out, M, groups, sc, 1, nullptr, st));
     }
     a.off = mark;
     cur = out;
@@ -135,18 +176,22 @@ int decoder_run(Arena& a, const rdm_unary_desc* dec, int num, const rdm_pyramid_
                 int c_coarse, const float* const* skips, float* out, cudaStream_t st) {
   const float* x = coarse;
   int cx = c_coarse;
+  StatSlots ss;
+  RDM_TRY(stat_slots_begin(a, ss, st));
   for (int i = 0; i < num; i++) {
     const int s = top - 1 - i;  // target stage
     RDM_CHECK_ARG(s >= 0, "rdm_decoder_forward: too many levels");
     const int M = p.n[s], N = p.n[s + 1];
     const int c_skip = dec[i].c_in - cx;
     RDM_CHECK_ARG(c_skip >= 0, "rdm_decoder_forward: channel mismatch at level %d", i);
-    float* cat = a.f((size_t)M * dec[i].c_in);
+    // row stride padded to a multiple of 4 floats: 16-byte rows qualify the GEMM for the TMA / tensor-core path
+    const int ldc = (dec[i].c_in + 3) / 4 * 4;
+    float* cat = a.f((size_t)M * ldc);
     if (!a.dry)
-      RDM_TRY(rdm_upsample_concat(x, p.upsampling[s], p.index_bytes, p.up_width[s], c_skip ? skips[i] : nullptr, M, N, cx, c_skip,
-                                  cat, st));
+      RDM_TRY(rdm_upsample_concat_ld(x, p.upsampling[s], p.index_bytes, p.up_width[s], c_skip ? skips[i] : nullptr, M, N, cx,
+                                     c_skip, cat, ldc, st));
     float* y = (i + 1 == num) ? out : a.f((size_t)M * dec[i].c_out);
-    RDM_TRY(unary(a, dec[i], cat, dec[i].c_in, y, M, groups, nullptr, 1, st));
+    RDM_TRY(unary(a, ss, dec[i], cat, ldc, y, M, groups, nullptr, 1, nullptr, st));
     x = y;
     cx = dec[i].c_out;
   }

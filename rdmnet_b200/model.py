@@ -174,13 +174,22 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-def _unary_desc(u):
-    """rdm_unary_desc of a UnaryBlock / LastUnaryBlock (NULL weight for nn.Identity / None)."""
+def _unary_desc(u, keep=None):
+    """rdm_unary_desc of a UnaryBlock / LastUnaryBlock (NULL weight for nn.Identity / None). With `keep` (a list that
+    outlives the descriptor) a weight whose in_features is not a multiple of 4 is passed as a zero-padded copy with a
+    16-byte row stride, which qualifies the layer for the TMA-fed tensor-core GEMM."""
     if u is None or isinstance(u, nn.Identity):
         return L.UnaryDesc()
     norm = getattr(u, "norm", None)
-    return L.UnaryDesc(_p(u.mlp.weight), _p(u.mlp.bias), _p(norm.norm.weight) if norm is not None else None,
-                       _p(norm.norm.bias) if norm is not None else None, u.mlp.in_features, u.mlp.out_features)
+    w, ldw = u.mlp.weight, 0
+    if keep is not None and u.mlp.in_features % 4 != 0:
+        ldw = (u.mlp.in_features + 3) // 4 * 4
+        wp = torch.zeros((u.mlp.out_features, ldw), dtype=torch.float32, device=w.device)
+        wp[:, :u.mlp.in_features] = w.detach()
+        keep.append(wp)
+        w = wp
+    return L.UnaryDesc(_p(w), _p(u.mlp.bias), _p(norm.norm.weight) if norm is not None else None,
+                       _p(norm.norm.bias) if norm is not None else None, u.mlp.in_features, u.mlp.out_features, ldw)
 
 
 def pyramid_desc(data_dict, lengths_host):
@@ -313,8 +322,10 @@ class Decoder(_Module):
         """rdm_decoder_forward: three (nearest upsample || skip -> unary) levels in one host call. Returns [l2]."""
         key = _state_key(self)
         if getattr(self, "_desc_key", None) != key:
-            arr = (L.UnaryDesc * 3)(_unary_desc(self.decoder4), _unary_desc(self.decoder3), _unary_desc(self.decoder2))
-            self._descs, self._desc_key = arr, key
+            keep = []
+            arr = (L.UnaryDesc * 3)(_unary_desc(self.decoder4, keep), _unary_desc(self.decoder3, keep),
+                                    _unary_desc(self.decoder2, keep))
+            self._descs, self._desc_keep, self._desc_key = arr, keep, key
         if pyr is None:
             lh = data_dict.get("lengths_host") or [l.tolist() for l in data_dict["lengths"]]
             pyr = pyramid_desc(data_dict, lh)
