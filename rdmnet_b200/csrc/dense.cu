@@ -200,13 +200,13 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
 __global__ void __launch_bounds__(256) splitk_reduce_stats_kernel(const float* __restrict__ part, int splits,
                                                                   const float* __restrict__ bias, float* __restrict__ C,
                                                                   int ldc, int M, int N, double* __restrict__ stats,
-                                                                  int cpg) {
+                                                                  int cpg, int rows_per_block) {
   __shared__ float s_s[8][32], s_q[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int col = blockIdx.x * 32 + lane, r0 = blockIdx.y * 64;
+  const int col = blockIdx.x * 32 + lane, r0 = blockIdx.y * rows_per_block;
   const float b = bias ? bias[col] : 0.f;
   float cs = 0.f, cq = 0.f;
-  for (int r = r0 + warp; r < min(M, r0 + 64); r += 8) {
+  for (int r = r0 + warp; r < min(M, r0 + rows_per_block); r += 8) {
     const size_t e = (size_t)r * N + col;
     float v = 0.f;
     for (int z = 0; z < splits; z++) v += part[(size_t)z * M * N + e];
@@ -277,8 +277,10 @@ int rdm_linear_gn(const float* A, int lda, const float* B, int ldb, int b_is_nk,
     if (rc == RDM_OK && tc_splits > 1) {
       const bool pow2 = gn_cpg >= 1 && (gn_cpg & (gn_cpg - 1)) == 0 && (gn_cpg <= 32 || gn_cpg % 32 == 0);
       if (gn_stats != nullptr && act == 0 && N % 32 == 0 && pow2) {
-        splitk_reduce_stats_kernel<<<dim3(N / 32, cdiv(M, 64)), 256, 0, stream>>>((const float*)workspace, tc_splits, bias, C,
-                                                                                   ldc, M, N, gn_stats, gn_cpg);
+        int rpb = 64;  // rows per block: small problems get more, shorter blocks (the pass is latency-bound)
+        while (rpb > 8 && (long long)(N / 32) * cdiv(M, rpb) < 296) rpb >>= 1;
+        splitk_reduce_stats_kernel<<<dim3(N / 32, cdiv(M, rpb)), 256, 0, stream>>>((const float*)workspace, tc_splits, bias, C,
+                                                                                    ldc, M, N, gn_stats, gn_cpg, rpb);
         if (stats_fused) *stats_fused = 1;
       } else {
         splitk_reduce_kernel<<<cdiv((long long)M * N, 256), 256, 0, stream>>>((const float*)workspace, tc_splits, bias, C, ldc, M, N, act);

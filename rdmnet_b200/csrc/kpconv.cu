@@ -357,6 +357,191 @@ __global__ void __launch_bounds__(128, VEC == 4 ? 4 : 7) kpconv_gather_v3_kernel
   }
 }
 
+// ---------------------------------------------------------------------------------------------- gather, v4
+// Same warp-autonomous mapping as v3, with the two Blackwell-specific changes that the ncu captures of v3 asked for
+// (long-scoreboard stalls at 25 % occupancy, FMA pipe the next limiter):
+//   * neighbour rows are STAGED IN SHARED MEMORY with cp.async (LDGSTS): the 32 rows of a chunk land in a per-warp
+//     buffer while the previous half-chunk is being multiplied, so 16 rows per warp are in flight without holding a
+//     single register (v3: 4 per lane group, each pinning a float4);
+//   * the 15 x 4 accumulators of a lane are 30 packed pairs updated with FFMA2 (fma.rn.f32x2, scalar-broadcast
+//     influence operand): half the issue slots and register-operand traffic per row.
+// Shared memory per warp: 32 rows x L x 16 B + the 32 x 20 influence tile (L = 8: 6.5 KB, 16: 10.5 KB, 32: 18.5 KB).
+__device__ __forceinline__ float2 ffma2(const float w, const float2 f, const float2 c) {
+  unsigned long long rw, rf, rc, rd;
+  const float2 w2 = make_float2(w, w);
+  rw = *reinterpret_cast<const unsigned long long*>(&w2);
+  rf = *reinterpret_cast<const unsigned long long*>(&f);
+  rc = *reinterpret_cast<const unsigned long long*>(&c);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(rw), "l"(rf), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ void gather_cp16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void gather_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void gather_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int L, bool SPLIT, typename IdxT>
+__global__ void __launch_bounds__(128, 4) kpconv_gather_v4_kernel(const float* __restrict__ feats,
+                                                                  const unsigned char* __restrict__ rowpos,
+                                                                  const float* __restrict__ q_pts,
+                                                                  const float* __restrict__ s_pts,
+                                                                  const IdxT* __restrict__ idx, const KPts kp,
+                                                                  float inv_sigma, int M, int N, int H, int C, int NS,
+                                                                  const int* __restrict__ order,
+                                                                  float* __restrict__ out) {
+  constexpr int G = 32 / L;
+  constexpr int STEP = SPLIT ? 32 : L;  // neighbour slots per chunk (per query)
+  constexpr int HALF = L / 2;
+  constexpr int WARP_F4 = 32 * L + 32 * KP_WS / 4;  // float4 per warp: row buffer + influence tile
+  extern __shared__ float4 s_dyn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane / L, t = lane % L;
+  const int gw = blockIdx.x * 4 + warp;
+  int m, slice;
+  if (SPLIT || L == 32) {
+    m = gw / NS;
+    slice = gw - m * NS;
+  } else {
+    m = gw * G + g;
+    slice = 0;
+  }
+  const bool qvalid = m < M;
+  if (__all_sync(FULL_MASK, !qvalid)) return;
+  if (qvalid && order != nullptr) m = order[m];
+  const int mm = qvalid ? m : M - 1;
+  const float qx = q_pts[3 * (size_t)mm], qy = q_pts[3 * (size_t)mm + 1], qz = q_pts[3 * (size_t)mm + 2];
+  const IdxT* row = idx + (size_t)mm * H;
+  const float* fbase = feats + slice * (4 * L) + 4 * t;
+  float4* rowbuf = s_dyn + (size_t)warp * WARP_F4;           // [32 rows][L] float4; row (g, u) at (g * L + u) * L
+  float* wtile = reinterpret_cast<float*>(rowbuf + 32 * L);  // [32][KP_WS]
+  float2 acc[KP_K][2];
+#pragma unroll
+  for (int k = 0; k < KP_K; k++) acc[k][0] = acc[k][1] = make_float2(0.f, 0.f);
+  int npos = 0;
+  float4* wrow = (float4*)(wtile + (t * G + g) * KP_WS);  // rows interleaved over groups: (u, g) -> u*G + g
+  const int myslot = SPLIT ? lane : t;
+  auto load_j = [&](int h) -> int {
+    if (qvalid && h < H) {
+      long long jj = (long long)row[h];
+      if (jj < N) return (int)jj;
+    }
+    return -1;
+  };
+  // asynchronous copy of rows [u0, u0 + HALF) of every group for the chunk whose slot indices are `jc`; one commit group
+  auto issue_half = [&](int jc, int u0) {
+#pragma unroll
+    for (int u = u0; u < u0 + HALF; u++) {
+      const int ju = __shfl_sync(FULL_MASK, jc, g * L + u);
+      if (ju >= 0) gather_cp16(rowbuf + (g * L + u) * L + t, fbase + (size_t)ju * C);
+    }
+    gather_commit();
+  };
+  int j = load_j(myslot);
+  int jn = load_j(STEP + myslot);
+  issue_half(j, 0);
+  issue_half(j, HALF);
+  for (int h0 = 0; h0 < H; h0 += STEP) {
+    if (!__any_sync(FULL_MASK, j >= 0)) break;  // rows are valid-first: nothing but padding from here on
+    const int jn2 = load_j(h0 + 2 * STEP + myslot);
+    // ---- (A) influences of this lane's slot
+    float w[16];
+    if (j >= 0) {
+      const float dx = s_pts[3 * (size_t)j] - qx, dy = s_pts[3 * (size_t)j + 1] - qy, dz = s_pts[3 * (size_t)j + 2] - qz;
+#pragma unroll
+      for (int k = 0; k < KP_K; k++) {
+        const float ex = dx - kp.x[k], ey = dy - kp.y[k], ez = dz - kp.z[k];
+        const float d = sqrt_approx(fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
+        w[k] = fmaxf(0.f, fmaf(-d, inv_sigma, 1.f));  // kpconv.py:98-99
+      }
+      npos += rowpos[j];
+    } else {
+#pragma unroll
+      for (int k = 0; k < KP_K; k++) w[k] = 0.f;
+    }
+    w[15] = 0.f;
+    wrow[0] = make_float4(w[0], w[1], w[2], w[3]);
+    wrow[1] = make_float4(w[4], w[5], w[6], w[7]);
+    wrow[2] = make_float4(w[8], w[9], w[10], w[11]);
+    wrow[3] = make_float4(w[12], w[13], w[14], w[15]);
+    const unsigned vb = __ballot_sync(FULL_MASK, j >= 0);
+    int nu = 0;
+#pragma unroll
+    for (int gg = 0; gg < G; gg++) {
+      const unsigned mg = (L == 32) ? vb : ((vb >> (gg * L)) & ((1u << (L & 31)) - 1u));
+      nu = max(nu, 32 - __clz(mg));
+    }
+    // ---- (B) two halves: multiply the landed rows, then refill their slots with the next chunk's rows
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      gather_wait<1>();  // this half's rows (the older of the two pending groups) have landed for this lane ...
+      __syncwarp();      // ... and for the whole warp; also orders the influence tile stores above
+      const int ue = min(nu, (half + 1) * HALF);
+#pragma unroll 4
+      for (int u = half * HALF; u < ue; u++) {
+        const int ju = __shfl_sync(FULL_MASK, j, g * L + u);
+        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ju >= 0) f = rowbuf[(g * L + u) * L + t];
+        const float4* wp = (const float4*)(wtile + (u * G + g) * KP_WS);
+        const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+        const float ww[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+        const float2 fa = make_float2(f.x, f.y), fb = make_float2(f.z, f.w);
+#pragma unroll
+        for (int k = 0; k < KP_K; k++) {
+          acc[k][0] = ffma2(ww[k], fa, acc[k][0]);
+          acc[k][1] = ffma2(ww[k], fb, acc[k][1]);
+        }
+      }
+      __syncwarp();  // every lane is done with this half's rows (and, after the second half, with the influence tile)
+      issue_half(jn, half * HALF);
+    }
+    j = jn;
+    jn = jn2;
+  }
+  gather_wait<0>();
+  if (SPLIT) {
+    npos = warp_sum_i(npos);
+#pragma unroll
+    for (int o = L; o < 32; o <<= 1)
+#pragma unroll
+      for (int k = 0; k < KP_K; k++) {
+        acc[k][0].x += __shfl_xor_sync(FULL_MASK, acc[k][0].x, o);
+        acc[k][0].y += __shfl_xor_sync(FULL_MASK, acc[k][0].y, o);
+        acc[k][1].x += __shfl_xor_sync(FULL_MASK, acc[k][1].x, o);
+        acc[k][1].y += __shfl_xor_sync(FULL_MASK, acc[k][1].y, o);
+      }
+    if (g != 0) return;
+  } else {
+#pragma unroll
+    for (int o = L >> 1; o > 0; o >>= 1) npos += __shfl_xor_sync(FULL_MASK, npos, o);
+  }
+  if (!qvalid) return;
+  const float inv = 1.f / (float)max(npos, 1);
+  float* op = out + (size_t)m * KP_K * C + slice * (4 * L) + 4 * t;
+#pragma unroll
+  for (int k = 0; k < KP_K; k++)
+    *(float4*)(op + (size_t)k * C) = make_float4(acc[k][0].x * inv, acc[k][0].y * inv, acc[k][1].x * inv, acc[k][1].y * inv);
+}
+
+template <int L, bool SPLIT, typename IdxT>
+static int launch_v4(long long warps, const float* feats, const unsigned char* rowpos, const float* q, const float* s,
+                     const IdxT* idx, const KPts& kp, float inv_sigma, int M, int N, int H, int C, int NS, const int* order,
+                     float* out, cudaStream_t stream) {
+  const size_t smem = 4 * (size_t)(32 * L + 32 * KP_WS / 4) * sizeof(float4);
+  static bool attr = false;
+  if (!attr && smem > 48 * 1024) {
+    RDM_CUDA(cudaFuncSetAttribute(kpconv_gather_v4_kernel<L, SPLIT, IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  kpconv_gather_v4_kernel<L, SPLIT, IdxT><<<cdiv(warps, 4), 128, smem, stream>>>(feats, rowpos, q, s, idx, kp, inv_sigma, M, N, H,
+                                                                                 C, NS, order, out);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
+
 template <typename IdxT>
 static int launch_gather(const float* feats, const unsigned char* rowpos, const float* q, const float* s,
                          const IdxT* idx, const float* kpts, const float* h_kpts, float sigma, int M, int N, int H, int C,
@@ -384,6 +569,28 @@ static int launch_gather(const float* feats, const unsigned char* rowpos, const 
       vec = (e && e[0] == '2') ? 2 : 4;
     }
     const long long want = 148LL * 16;
+    static int ver = 0;
+    if (ver == 0) {
+      const char* e = getenv("RDM_GATHER_V");  // debug knob: RDM_GATHER_V=3 selects the register-staged v3 kernels
+      ver = (e && e[0] == '3') ? 3 : 4;
+    }
+    if (ver == 4 && vec == 4) {
+#define GATHER4(Lv, SPLITv, warps, NSv) \
+  return launch_v4<Lv, SPLITv, IdxT>((warps), feats, rowpos, q, s, idx, kp, inv_sigma, M, N, H, C, (NSv), order, out, stream)
+      if (C == 32) {
+        if (cdiv(M, 4) >= want) GATHER4(8, false, cdiv(M, 4), 1);
+        GATHER4(8, true, M, 1);
+      } else if (C == 64) {
+        if (cdiv(M, 2) >= want) GATHER4(16, false, cdiv(M, 2), 1);
+        if (M >= want) GATHER4(16, true, M, 1);
+        GATHER4(8, true, 2LL * M, 2);
+      } else {
+        if ((long long)M * (C / 128) >= want) GATHER4(32, false, (long long)M * (C / 128), C / 128);
+        if ((long long)M * (C / 64) >= want) GATHER4(16, true, (long long)M * (C / 64), C / 64);
+        GATHER4(8, true, (long long)M * (C / 32), C / 32);
+      }
+#undef GATHER4
+    }
 #define GATHER(Lv, SPLITv, VECv, warps, NSv)                                                                        \
   do {                                                                                                              \
     kpconv_gather_v3_kernel<Lv, SPLITv, VECv, IdxT><<<cdiv((long long)(warps), 4), 128, 0, stream>>>(               \

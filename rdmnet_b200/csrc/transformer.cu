@@ -120,6 +120,7 @@ extern "C" int rdm_tf_project(const rdm_tf_proj_job* h_jobs, int num_jobs, cudaS
 }
 
 // ------------------------------------------------------------------------------------------------ attention + post
+#define TF_WBUF 16384  // floats per weight staging buffer (64 KB)
 struct AttnSmem {
   float Ks[TF_D * TF_KT];       // [channel][key]: lane-per-key reads and float4 tile stores are both conflict free
   float Vs[TF_KT * TF_D];       // [key][channel]
@@ -129,7 +130,35 @@ struct AttnSmem {
   float Y[TF_R * TF_D];         // row-major scratch for LayerNorm
   float X1[TF_R * TF_D];        // x1 row-major (residual of the FFN)
   float Ft[TF_F * TF_R];        // FFN hidden, transposed
+  float W0[TF_WBUF];            // weight staging ring (cp.async): the 320 KB of out-proj / FFN weights stream through these
+  float W1[TF_WBUF];            //   two buffers in six 64 KB chunks, each chunk landing while the previous one is consumed
 };
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// all 256 threads: asynchronous copy of one 64 KB weight chunk (16 x 16 B per thread) + commit
+__device__ __forceinline__ void stage_chunk(float* dst, const float* __restrict__ src, int tid) {
+#pragma unroll
+  for (int i = 0; i < TF_WBUF / 4 / 256; i++) cp_async16(dst + 4 * (tid + i * 256), src + 4 * (tid + i * 256));
+  cp_async_commit();
+}
+
+// acc[i] += sum_{k < K} Ws[k][o] * xt[k][r0 + i], i < 4; Ws is a staged weight chunk in shared memory (row stride ldw)
+template <int K>
+__device__ __forceinline__ void rowblock_gemv4_s(const float* Ws, int ldw, int o, const float* xt, int r0, float acc[4]) {
+#pragma unroll 8
+  for (int k = 0; k < K; k++) {
+    const float w = Ws[k * ldw + o];
+    const float4 x = *(const float4*)(xt + k * TF_R + r0);
+    acc[0] = fmaf(w, x.x, acc[0]); acc[1] = fmaf(w, x.y, acc[1]); acc[2] = fmaf(w, x.z, acc[2]); acc[3] = fmaf(w, x.w, acc[3]);
+  }
+}
 
 // LayerNorm of the 8 rows in sm.Y (one warp per row): writes row-major to dst_rm (shared or global, stride ld) and,
 // if dst_t != nullptr, transposed to dst_t[c*8 + row].
@@ -154,6 +183,9 @@ __device__ __forceinline__ void layernorm_rows(const float* Y, const float* __re
 }
 
 // grid (ceil(maxNq/8), num_jobs), 256 threads = 8 warps; warp w -> head w & 3, queries (w >> 2) * 4 .. + 3.
+// Latency plan: K/V tile t+1 is prefetched into registers while tile t is consumed; the out-projection and the first
+// half of the FFN-expand weights are copied to shared memory with cp.async during the whole attention phase, and every
+// later 64 KB weight chunk lands while the previous one is being multiplied.
 __global__ void __launch_bounds__(256) tf_attend_kernel(const AttnJobs jobs) {
   const rdm_tf_attn_job jb = blockIdx.y == 0 ? jobs.j[0] : jobs.j[1];
   const int n0 = blockIdx.x * TF_R;
@@ -164,6 +196,9 @@ __global__ void __launch_bounds__(256) tf_attend_kernel(const AttnJobs jobs) {
   const int head = warp & 3, qh = warp >> 2;
   const int nvalid = min(TF_R, jb.nq - n0);
   const float scale = 0.17677669529663687f;  // 1/sqrt(32)
+  const float* B = jb.blob;
+  stage_chunk(sm.W0, B + TFB_WO, tid);  // group 0: out-projection [128][128]
+  stage_chunk(sm.W1, B + TFB_W1, tid);  // group 1: FFN expand, k = 0..63 of [128][256]
   for (int e = tid; e < TF_R * TF_D; e += 256) {
     int r = e >> 7, c = e & 127;
     sm.Qt[c * TF_R + r] = (r < nvalid) ? jb.q[(size_t)(n0 + r) * TF_D + c] * scale : 0.f;
@@ -177,22 +212,30 @@ __global__ void __launch_bounds__(256) tf_attend_kernel(const AttnJobs jobs) {
   }
   const int hoff = head * TF_HD;
   float* Pw = sm.Ps[warp];
+  float4 kreg[8], vreg[8];
+  auto load_tile = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int e = tid + i * 256;
+      const int c = e >> 4, j4 = (e & 15) * 4;  // K tile: channel-major in global (ld = ldk_t) and in smem
+      kreg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + j4 + 3 < jb.ldk_t) kreg[i] = __ldg((const float4*)(jb.k + (size_t)c * jb.ldk_t + k0 + j4));  // cols >= nk: masked below
+      const int j = e >> 5, c4 = (e & 31) * 4;
+      vreg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + j < jb.nk) vreg[i] = __ldg((const float4*)(jb.v + (size_t)(k0 + j) * TF_D + c4));
+    }
+  };
+  load_tile(0);
   for (int k0 = 0; k0 < jb.nk; k0 += TF_KT) {
     __syncthreads();  // previous tile fully consumed (and Qt visible on the first pass)
-    for (int e = tid; e < TF_D * (TF_KT / 4); e += 256) {  // K tile: channel-major in global (ld = ldk_t) and in smem
-      const int c = e >> 4, j4 = (e & 15) * 4;
-      const float* src = jb.k + (size_t)c * jb.ldk_t + k0 + j4;
-      float4 kk = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 + j4 + 3 < jb.ldk_t) kk = __ldg((const float4*)src);  // columns >= nk hold padding: masked below
-      *(float4*)(sm.Ks + c * TF_KT + j4) = kk;
-    }
-    for (int e = tid; e < TF_KT * (TF_D / 4); e += 256) {
-      const int j = e >> 5, c4 = (e & 31) * 4;
-      float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 + j < jb.nk) vv = __ldg((const float4*)(jb.v + (size_t)(k0 + j) * TF_D + c4));
-      *(float4*)(sm.Vs + j * TF_D + c4) = vv;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int e = tid + i * 256;
+      *(float4*)(sm.Ks + (e >> 4) * TF_KT + (e & 15) * 4) = kreg[i];
+      *(float4*)(sm.Vs + (e >> 5) * TF_D + (e & 31) * 4) = vreg[i];
     }
     __syncthreads();
+    if (k0 + TF_KT < jb.nk) load_tile(k0 + TF_KT);  // in flight during this tile's math
     // scores of keys (lane, lane+32) against the warp's 4 queries
     float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
     const float* ka = sm.Ks + hoff * TF_KT + lane;
@@ -233,13 +276,13 @@ __global__ void __launch_bounds__(256) tf_attend_kernel(const AttnJobs jobs) {
   // attention output, transposed: At[channel][row]
   *(float4*)(sm.At + (hoff + lane) * TF_R + qh * 4) =
       make_float4(acc[0] / l[0], acc[1] / l[1], acc[2] / l[2], acc[3] / l[3]);
-  __syncthreads();
-  const float* B = jb.blob;
+  cp_async_wait<1>();  // group 0 (out-projection weights) has landed for this thread ...
+  __syncthreads();     // ... and for everyone; At complete
   const int o = tid & 127, rh = tid >> 7;
   // out-projection + bias + residual(input rows) -> Y
   {
     float a4[4] = {0.f, 0.f, 0.f, 0.f};
-    rowblock_gemv4<TF_D>(B + TFB_WO, TF_D, o, sm.At, rh * 4, a4);
+    rowblock_gemv4_s<TF_D>(sm.W0, TF_D, o, sm.At, rh * 4, a4);
     const float b = B[TFB_BO + o];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -248,28 +291,42 @@ __global__ void __launch_bounds__(256) tf_attend_kernel(const AttnJobs jobs) {
       sm.Y[r * TF_D + o] = a4[i] + b + res;
     }
   }
-  __syncthreads();
+  __syncthreads();                                        // W0 free, Y complete
+  stage_chunk(sm.W0, B + TFB_W1 + TF_WBUF, tid);          // group 2: FFN expand, k = 64..127
   layernorm_rows(sm.Y, B + TFB_G1, B + TFB_E1, sm.X1, TF_D, sm.At, TF_R, warp, lane);  // x1 (row-major + transposed)
+  cp_async_wait<1>();                                     // group 1
   __syncthreads();
-  // FFN expand 128 -> 256, ReLU: thread (o2 = tid, all 8 rows as two groups of 4)
+  // FFN expand 128 -> 256, ReLU: thread tid -> hidden unit tid, all 8 rows as two groups of 4; k split over two chunks
+  float a4[4] = {0.f, 0.f, 0.f, 0.f}, c4[4] = {0.f, 0.f, 0.f, 0.f};
+  rowblock_gemv4_s<64>(sm.W1, TF_F, tid, sm.At, 0, a4);
+  rowblock_gemv4_s<64>(sm.W1, TF_F, tid, sm.At, 4, c4);
+  __syncthreads();                                        // W1 free
+  stage_chunk(sm.W1, B + TFB_W2, tid);                    // group 3: FFN squeeze, k = 0..127 of [256][128]
+  cp_async_wait<1>();                                     // group 2
+  __syncthreads();
+  rowblock_gemv4_s<64>(sm.W0, TF_F, tid, sm.At + 64 * TF_R, 0, a4);
+  rowblock_gemv4_s<64>(sm.W0, TF_F, tid, sm.At + 64 * TF_R, 4, c4);
   {
-    float a4[4] = {0.f, 0.f, 0.f, 0.f}, c4[4] = {0.f, 0.f, 0.f, 0.f};
-    rowblock_gemv4<TF_D>(B + TFB_W1, TF_F, tid, sm.At, 0, a4);
-    rowblock_gemv4<TF_D>(B + TFB_W1, TF_F, tid, sm.At, 4, c4);
     const float b = B[TFB_B1 + tid];
     *(float4*)(sm.Ft + tid * TF_R) = make_float4(fmaxf(a4[0] + b, 0.f), fmaxf(a4[1] + b, 0.f), fmaxf(a4[2] + b, 0.f), fmaxf(a4[3] + b, 0.f));
     *(float4*)(sm.Ft + tid * TF_R + 4) = make_float4(fmaxf(c4[0] + b, 0.f), fmaxf(c4[1] + b, 0.f), fmaxf(c4[2] + b, 0.f), fmaxf(c4[3] + b, 0.f));
   }
+  __syncthreads();                                        // W0 free, Ft complete
+  stage_chunk(sm.W0, B + TFB_W2 + TF_WBUF, tid);          // group 4: FFN squeeze, k = 128..255
+  cp_async_wait<1>();                                     // group 3
   __syncthreads();
   // FFN squeeze 256 -> 128 + bias + residual(x1) -> Y
   {
-    float a4[4] = {0.f, 0.f, 0.f, 0.f};
-    rowblock_gemv4<TF_F>(B + TFB_W2, TF_D, o, sm.Ft, rh * 4, a4);
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+    rowblock_gemv4_s<128>(sm.W1, TF_D, o, sm.Ft, rh * 4, s4);
+    cp_async_wait<0>();                                   // group 4
+    __syncthreads();
+    rowblock_gemv4_s<128>(sm.W0, TF_D, o, sm.Ft + 128 * TF_R, rh * 4, s4);
     const float b = B[TFB_B2 + o];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const int r = rh * 4 + i;
-      sm.Y[r * TF_D + o] = a4[i] + b + sm.X1[r * TF_D + o];
+      sm.Y[r * TF_D + o] = s4[i] + b + sm.X1[r * TF_D + o];
     }
   }
   __syncthreads();
