@@ -221,8 +221,8 @@ int rdm_encoder_forward(const rdm_block_desc* h_blocks, int num_blocks, const rd
  * coarse [n[top], c_coarse]; h_skips[i] = encoder output of stage top-1-i; out = last result [n[top-num], c_out]. */
 size_t rdm_decoder_workspace(const rdm_unary_desc* h_dec, int num, const rdm_pyramid_desc* h_pyr, int top_stage, int groups);
 int rdm_decoder_forward(const rdm_unary_desc* h_dec, int num, const rdm_pyramid_desc* h_pyr, int top_stage, int groups,
-                        const float* coarse, int c_coarse, const float* const* h_skips, float* out, void* workspace,
-                        size_t workspace_bytes, rdm_stream_t stream);
+                        const float* coarse, int c_coarse, const float* const* h_skips, float* out, int ld_out,
+                        void* workspace, size_t workspace_bytes, rdm_stream_t stream);
 /* rdm_thdroformer_forward = ThDRoFormer.forward (rdmnet/thdroformer/thdroformer.py:304-347) for hidden 128 / 4 heads:
  * embedding Linear(3,64), in_proj, 2*L fused layers (h_layer_blobs[i], h_is_self[i]), out_proj. */
 typedef struct {
@@ -258,8 +258,9 @@ int rdm_coarse_matching(float* xy_scores, int M, int N, const unsigned char* ref
                         int64_t* out_src_indices, float* out_scores, int* out_count, float* sums_scratch,
                         rdm_stream_t stream);
 
-/* ---- patch gather + einsum('bnd,bmd->bnm') * scale (experiments/model.py:323-343); point_limit must be 128. */
-int rdm_patch_scores(const float* ref_feats, int Nr, const float* src_feats, int Ns, int C,
+/* ---- patch gather + einsum('bnd,bmd->bnm') * scale (experiments/model.py:323-343); point_limit must be 128.
+ * ld_feats = row stride of both feature tables in floats (multiple of 4; the decoder output keeps its 257th column). */
+int rdm_patch_scores(const float* ref_feats, int Nr, const float* src_feats, int Ns, int C, int ld_feats,
                      const int64_t* ref_knn_indices, const int64_t* src_knn_indices, const int64_t* ref_corr_indices,
                      const int64_t* src_corr_indices, int num_patches, int point_limit, float scale, float* out_scores,
                      rdm_stream_t stream);
@@ -286,6 +287,71 @@ int rdm_lgr(const float* matching_scores, int num_patches, int K, const float* r
             float acceptance_radius, int correspondence_threshold, int num_refinement_steps, float* out_ref_corr_points,
             float* out_src_corr_points, float* out_corr_scores, int* out_corr_bij, float* out_transform, int* out_meta,
             void* workspace, size_t workspace_bytes, rdm_stream_t stream);
+
+/* ---- rdm_match_forward: everything RDMNet.forward does after the decoder (experiments/model_infer.py:180-354) in ONE
+ * host call - Vote_layer + n2n score head, NMS (radius search + greedy rule), node selection, second ThDRoFormer,
+ * L2 normalisation, both point_to_node partitions, SuperPointMatching, patch scores, Sinkhorn and
+ * LocalGlobalRegistration. Two internal stream synchronisations (the NMS survivor counts decide the shapes of the
+ * second half; the final counts / pose are read back through pinned memory). All pointers in the descriptor are
+ * device pointers except h_*; outputs are caller-allocated at the capacities given below. */
+typedef struct {
+  /* Vote_layer (rdmnet/vote/vote.py:43-117): two (Linear, LayerNorm, ReLU) stages, ctr_reg, out_proj LayerNorm */
+  const float *v_w0, *v_b0, *v_g0, *v_e0; /* [h0, c], [h0] x3 */
+  const float *v_w1, *v_b1, *v_g1, *v_e1; /* [h1, h0], [h1] x3 */
+  const float *v_wr, *v_br;               /* [3 + c, h1] */
+  const float *v_go, *v_eo;               /* [c] */
+  float max_offset[3];
+  int c, h0, h1;
+  const float *n2n_w, *n2n_b;             /* proj_n2n_score [1, c] */
+  const rdm_thdroformer_desc* h_transformer2;
+  const float* ot_alpha;
+  float nms_radius, acceptance_radius, sinkhorn_inf;
+  int nms_limit, point_limit, num_correspondences, dual_normalization, sinkhorn_iterations, correspondence_threshold,
+      refinement_steps;
+} rdm_match_desc;
+typedef struct {
+  /* inputs */
+  const float* points_c;        /* [nc, 3] stage-5 points, ref rows first */
+  const int64_t* lengths_c;     /* [2] device */
+  int nc, nc_ref;
+  const float* feats_c;         /* [nc, c] first-transformer output */
+  const float* n2p_scores;      /* [nc] */
+  const float* points_f;        /* [nf, 3] */
+  int nf, nf_ref;
+  const float* feats_f;         /* [nf, c] with row stride ld_feats_f */
+  int ld_feats_f;
+  /* outputs, capacity in brackets */
+  float* shifted_points;        /* [nc, 3] */
+  float* vote_feats;            /* [nc, c] */
+  float* n2n_scores;            /* [nc] */
+  unsigned char* nms_mask;      /* [nc] */
+  int64_t* selected;            /* [nc] */
+  float* sel_points;            /* [nc, 3]   selected nodes, ref first */
+  float* sel_feats_norm;        /* [nc, c]   L2-normalised second-transformer output */
+  float* sel_n2p;               /* [nc] */
+  float* sel_n2n;               /* [nc] */
+  unsigned char* node_masks;    /* [nc] */
+  int64_t* knn_indices;         /* [nc, point_limit] */
+  unsigned char* knn_masks;     /* [nc, point_limit] */
+  int64_t* corr_ref;            /* [num_correspondences] */
+  int64_t* corr_src;            /* [num_correspondences] */
+  float* corr_node_scores;      /* [num_correspondences] */
+  float* matching_scores;       /* [num_correspondences, point_limit + 1, point_limit + 1] */
+  float* ref_corr_points;       /* [num_correspondences * 2 * point_limit, 3] */
+  float* src_corr_points;       /* same */
+  float* corr_scores;           /* [num_correspondences * 2 * point_limit] */
+  int* corr_bij;                /* [num_correspondences * 2 * point_limit, 3] */
+  float* transform;             /* [16] */
+} rdm_match_io;
+typedef struct {
+  int n_ref_sel, n_src_sel;     /* NMS survivors */
+  int num_patches;              /* coarse correspondences actually produced (<= num_correspondences) */
+  int num_corr;                 /* fine correspondences */
+  float transform[16];
+} rdm_match_result;
+size_t rdm_match_workspace(const rdm_match_desc* h_desc, int nc, int nc_ref, int nf, int nf_ref);
+int rdm_match_forward(const rdm_match_desc* h_desc, const rdm_match_io* h_io, rdm_match_result* h_result, void* workspace,
+                      size_t workspace_bytes, rdm_stream_t stream);
 
 #ifdef __cplusplus
 }

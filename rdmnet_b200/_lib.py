@@ -48,8 +48,8 @@ SIGNATURES = {
     "rdm_encoder_workspace": (c_size_t, [c_void_p, c_int, c_void_p, c_int]),
     "rdm_encoder_forward": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "rdm_decoder_workspace": (c_size_t, [c_void_p, c_int, c_void_p, c_int, c_int]),
-    "rdm_decoder_forward": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
-                                    c_size_t, c_void_p]),
+    "rdm_decoder_forward": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                    c_void_p, c_size_t, c_void_p]),
     "rdm_thdroformer_workspace": (c_size_t, [c_int, c_int, c_int]),
     "rdm_thdroformer_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                         c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -59,10 +59,12 @@ SIGNATURES = {
                                   c_size_t, c_void_p]),
     "rdm_coarse_matching": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p]),
-    "rdm_patch_scores": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+    "rdm_patch_scores": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                  c_int, c_float, c_void_p, c_void_p]),
     "rdm_sinkhorn": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                              c_float, c_void_p, c_void_p]),
+    "rdm_match_workspace": (c_size_t, [c_void_p, c_int, c_int, c_int, c_int]),
+    "rdm_match_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "rdm_weighted_procrustes": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
     "rdm_lgr_workspace": (c_size_t, [c_int, c_int]),
     "rdm_lgr": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -108,6 +110,34 @@ class ThdroformerDesc(ctypes.Structure):
     _fields_ = [("emb_w", c_void_p), ("emb_b", c_void_p), ("in_w", c_void_p), ("in_b", c_void_p), ("out_w", c_void_p),
                 ("out_b", c_void_p), ("layer_blobs", c_void_p * 32), ("is_self", c_int * 32), ("num_layers", c_int),
                 ("c_in", c_int), ("c_out", c_int)]
+
+
+class MatchDesc(ctypes.Structure):
+    _fields_ = [("v_w0", c_void_p), ("v_b0", c_void_p), ("v_g0", c_void_p), ("v_e0", c_void_p),
+                ("v_w1", c_void_p), ("v_b1", c_void_p), ("v_g1", c_void_p), ("v_e1", c_void_p),
+                ("v_wr", c_void_p), ("v_br", c_void_p), ("v_go", c_void_p), ("v_eo", c_void_p),
+                ("max_offset", c_float * 3), ("c", c_int), ("h0", c_int), ("h1", c_int),
+                ("n2n_w", c_void_p), ("n2n_b", c_void_p), ("h_transformer2", c_void_p), ("ot_alpha", c_void_p),
+                ("nms_radius", c_float), ("acceptance_radius", c_float), ("sinkhorn_inf", c_float),
+                ("nms_limit", c_int), ("point_limit", c_int), ("num_correspondences", c_int), ("dual_normalization", c_int),
+                ("sinkhorn_iterations", c_int), ("correspondence_threshold", c_int), ("refinement_steps", c_int)]
+
+
+class MatchIO(ctypes.Structure):
+    _fields_ = [("points_c", c_void_p), ("lengths_c", c_void_p), ("nc", c_int), ("nc_ref", c_int), ("feats_c", c_void_p),
+                ("n2p_scores", c_void_p), ("points_f", c_void_p), ("nf", c_int), ("nf_ref", c_int), ("feats_f", c_void_p),
+                ("ld_feats_f", c_int),
+                ("shifted_points", c_void_p), ("vote_feats", c_void_p), ("n2n_scores", c_void_p), ("nms_mask", c_void_p),
+                ("selected", c_void_p), ("sel_points", c_void_p), ("sel_feats_norm", c_void_p), ("sel_n2p", c_void_p),
+                ("sel_n2n", c_void_p), ("node_masks", c_void_p), ("knn_indices", c_void_p), ("knn_masks", c_void_p),
+                ("corr_ref", c_void_p), ("corr_src", c_void_p), ("corr_node_scores", c_void_p), ("matching_scores", c_void_p),
+                ("ref_corr_points", c_void_p), ("src_corr_points", c_void_p), ("corr_scores", c_void_p), ("corr_bij", c_void_p),
+                ("transform", c_void_p)]
+
+
+class MatchResult(ctypes.Structure):
+    _fields_ = [("n_ref_sel", c_int), ("n_src_sel", c_int), ("num_patches", c_int), ("num_corr", c_int),
+                ("transform", c_float * 16)]
 
 
 def lib():

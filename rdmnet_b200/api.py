@@ -33,7 +33,12 @@ class PairRegistrar:
         lens = self.h_lengths.to(self.device, non_blocking=True)
         self.h2d_bytes = pts.numel() * 4 + lens.numel() * 8
         out = self.model({"points": pts, "lengths": lens})
-        res = {k: out[k].cpu().numpy() for k in keys}  # D2H (synchronises)
+        res = {}
+        for k in keys:  # D2H (synchronises); the pose already came back through pinned memory inside rdm_match_forward
+            if k == "estimated_transform" and "estimated_transform_host" in out:
+                res[k] = out["estimated_transform_host"].numpy()
+            else:
+                res[k] = out[k].cpu().numpy()
         self.d2h_bytes = int(sum(v.nbytes for v in res.values()))
         return res
 

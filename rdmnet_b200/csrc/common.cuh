@@ -60,6 +60,13 @@ int rdm_kpconv_gather_impl(const float* s_feats, const float* q_points, const fl
 int rdm_upsample_concat_ld(const float* feats, const void* upsample_indices, int index_bytes, int index_stride,
                            const float* skip, int M, int N, int C1, int C2, float* out, int ld_out, cudaStream_t stream);
 
+int rdm_vote_finish(const float* off, int ld_off, const float* xyz, const float* feats, int ld_f, const float* gamma,
+                    const float* beta, const float* h_limit3, float eps, int N, int C, float* xyz_out, float* feat_out,
+                    cudaStream_t stream);
+int rdm_gather_rows(const float* const* h_src, float* const* h_dst, const int* h_c, const int* h_ld, int num_jobs,
+                    const int64_t* sel, int count, cudaStream_t stream);
+int rdm_l2_normalize(const float* x, float* y, int N, int C, cudaStream_t stream);
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -53,17 +53,37 @@ __global__ void __launch_bounds__(256) kpconv_gather_c1_kernel(const float* __re
 #pragma unroll
   for (int k = 0; k < KP_K; k++) acc[k] = 0.f;
   int cnt = 0;
-  for (int h = t; h < H; h += 8) {
-    long long j = qvalid ? (long long)idx[(size_t)mm * H + h] : (long long)N;
-    if (j >= N) continue;
-    const float f = feats[j];
-    cnt += f > 0.f;
-    const float dx = s_pts[3 * j] - qx, dy = s_pts[3 * j + 1] - qy, dz = s_pts[3 * j + 2] - qz;
+  // batches of 4 slots per lane: all index loads, then all point / feature loads, then the math - two dependent
+  // memory round trips per batch instead of per slot
+  for (int hb = t; hb < H; hb += 32) {
+    long long jj[4];
+    float px[4], py[4], pz[4], ff[4];
 #pragma unroll
-    for (int k = 0; k < KP_K; k++) {
-      const float ex = dx - kp.x[k], ey = dy - kp.y[k], ez = dz - kp.z[k];
-      const float w = fmaxf(0.f, fmaf(-sqrt_approx(fmaf(ez, ez, fmaf(ey, ey, ex * ex))), inv_sigma, 1.f));
-      acc[k] = fmaf(w, f, acc[k]);
+    for (int i = 0; i < 4; i++) {
+      const int h = hb + 8 * i;
+      jj[i] = (qvalid && h < H) ? (long long)idx[(size_t)mm * H + h] : (long long)N;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const bool ok = jj[i] < N;
+      const long long j = ok ? jj[i] : 0;
+      px[i] = s_pts[3 * j];
+      py[i] = s_pts[3 * j + 1];
+      pz[i] = s_pts[3 * j + 2];
+      ff[i] = ok ? feats[j] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (jj[i] >= N) continue;
+      const float f = ff[i];
+      cnt += f > 0.f;
+      const float dx = px[i] - qx, dy = py[i] - qy, dz = pz[i] - qz;
+#pragma unroll
+      for (int k = 0; k < KP_K; k++) {
+        const float ex = dx - kp.x[k], ey = dy - kp.y[k], ez = dz - kp.z[k];
+        const float w = fmaxf(0.f, fmaf(-sqrt_approx(fmaf(ez, ez, fmaf(ey, ey, ex * ex))), inv_sigma, 1.f));
+        acc[k] = fmaf(w, f, acc[k]);
+      }
     }
   }
 #pragma unroll
@@ -568,7 +588,12 @@ static int launch_gather(const float* feats, const unsigned char* rowpos, const 
       const char* e = getenv("RDM_GATHER_VEC");
       vec = (e && e[0] == '2') ? 2 : 4;
     }
-    const long long want = 148LL * 16;
+    static int wps = 0;
+    if (wps == 0) {
+      const char* e = getenv("RDM_GATHER_WPS");  // tuning knob: warps per SM a mapping must reach before it is taken
+      wps = (e && atoi(e) > 0) ? atoi(e) : 16;
+    }
+    const long long want = 148LL * wps;
     static int ver = 0;
     if (ver == 0) {
       const char* e = getenv("RDM_GATHER_V");  // debug knob: RDM_GATHER_V=3 selects the register-staged v3 kernels
@@ -665,6 +690,10 @@ int rdm_kpconv_gather_impl(const float* s_feats, const float* q_points, const fl
   RDM_CHECK_ARG(index_bytes == 4 || index_bytes == 8, "rdm_kpconv_gather: index_bytes must be 4 or 8");
   RDM_CHECK_ARG(kernel_points != nullptr && h_kernel_points != nullptr, "rdm_kpconv_gather: kernel points missing");
   if (M == 0) return RDM_OK;
+  if (N == 0) {  // no supports: every slot is padding
+    RDM_CUDA(cudaMemsetAsync(out_weighted, 0, (size_t)M * KP_K * C_in * sizeof(float), stream));
+    return RDM_OK;
+  }
   const int prof = rdm_prof_begin(RDM_PROF_KPCONV_GATHER, M, N, H, C_in, stream);
   if (C_in > 1 && N > 0 && !rowpos_ready) {
     row_positive_kernel<<<cdiv(N, 8), 256, 0, stream>>>(s_feats, N, C_in, rowpos_scratch);

@@ -453,7 +453,7 @@ extern "C" int rdm_coarse_matching(float* xy_scores, int M, int N, const unsigne
 // One CTA per patch; K x K tile with K = 128 (point limit), 256 threads x (8x8), BK = 16.
 #define PS_K 128
 __global__ void __launch_bounds__(256) patch_scores_kernel(const float* __restrict__ Fr, int Nr,
-                                                           const float* __restrict__ Fs, int Ns, int C,
+                                                           const float* __restrict__ Fs, int Ns, int C, int ld,
                                                            const int64_t* __restrict__ rknn,
                                                            const int64_t* __restrict__ sknn,
                                                            const int64_t* __restrict__ ridx,
@@ -475,8 +475,8 @@ __global__ void __launch_bounds__(256) patch_scores_kernel(const float* __restri
     for (int q = 0; q < 2; q++) {
       int row = (tid >> 2) + q * 64, kq = (tid & 3) * 4;
       int ia = s_ra[row], ib = s_rb[row];
-      ra[q] = ia >= 0 ? *(const float4*)(Fr + (size_t)ia * C + k0 + kq) : make_float4(0.f, 0.f, 0.f, 0.f);
-      rb[q] = ib >= 0 ? *(const float4*)(Fs + (size_t)ib * C + k0 + kq) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ra[q] = ia >= 0 ? *(const float4*)(Fr + (size_t)ia * ld + k0 + kq) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rb[q] = ib >= 0 ? *(const float4*)(Fs + (size_t)ib * ld + k0 + kq) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
   auto store = [&](int buf) {
@@ -526,15 +526,16 @@ __global__ void __launch_bounds__(256) patch_scores_kernel(const float* __restri
   }
 }
 
-extern "C" int rdm_patch_scores(const float* ref_feats, int Nr, const float* src_feats, int Ns, int C,
+extern "C" int rdm_patch_scores(const float* ref_feats, int Nr, const float* src_feats, int Ns, int C, int ld_feats,
                                 const int64_t* ref_knn_indices, const int64_t* src_knn_indices,
                                 const int64_t* ref_corr_indices, const int64_t* src_corr_indices, int num_patches,
                                 int point_limit, float scale, float* out_scores, cudaStream_t stream) {
   RDM_CHECK_ARG(point_limit == PS_K, "rdm_patch_scores: num_points_in_patch must be 128");
   RDM_CHECK_ARG(C % 16 == 0 && C >= 16, "rdm_patch_scores: C must be a multiple of 16");
+  RDM_CHECK_ARG(ld_feats >= C && ld_feats % 4 == 0, "rdm_patch_scores: feature row stride must be a multiple of 4 floats");
   RDM_CHECK_ARG(((uintptr_t)ref_feats & 15) == 0 && ((uintptr_t)src_feats & 15) == 0, "rdm_patch_scores: unaligned features");
   if (num_patches == 0) return RDM_OK;
-  patch_scores_kernel<<<num_patches, 256, 0, stream>>>(ref_feats, Nr, src_feats, Ns, C, ref_knn_indices, src_knn_indices,
+  patch_scores_kernel<<<num_patches, 256, 0, stream>>>(ref_feats, Nr, src_feats, Ns, C, ld_feats, ref_knn_indices, src_knn_indices,
                                                       ref_corr_indices, src_corr_indices, scale, out_scores);
   RDM_LAUNCH_CHECK();
   return RDM_OK;
@@ -781,6 +782,103 @@ extern "C" int rdm_sinkhorn(const float* scores, int num_patches, int R, int C, 
     RDM_CUDA(cudaFuncSetAttribute(sinkhorn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   sinkhorn_kernel<<<num_patches, 160, smem, stream>>>(scores, R, C, row_masks, col_masks, row_mask_gather,
                                                      col_mask_gather, alpha, num_iterations, inf, out);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------- tail helpers
+// Vote_layer epilogue (rdmnet/vote/vote.py:101-116): off = ctr_reg(h) is [N, 3 + C]; xyz_out = xyz + clamp(off[:, :3],
+// -limit, +limit); feat_out = LayerNorm(features + off[:, 3:]). One warp per row.
+__global__ void __launch_bounds__(256) vote_finish_kernel(const float* __restrict__ off, int ld_off, const float* __restrict__ xyz,
+                                                          const float* __restrict__ feats, int ld_f, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float lx, float ly, float lz, float eps,
+                                                          int N, int C, float* __restrict__ xyz_out, float* __restrict__ feat_out) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= N) return;
+  const float* o = off + (size_t)r * ld_off;
+  if (lane < 3) {
+    const float lim = lane == 0 ? lx : (lane == 1 ? ly : lz);
+    xyz_out[3 * r + lane] = xyz[3 * r + lane] + fminf(fmaxf(o[lane], -lim), lim);
+  }
+  float v[32];  // C <= 1024
+  float s = 0.f;
+  const int per = (C + 31) / 32;
+  for (int i = 0; i < per; i++) {
+    const int c = lane + 32 * i;
+    v[i] = c < C ? feats[(size_t)r * ld_f + c] + o[3 + c] : 0.f;
+    s += v[i];
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+  for (int i = 0; i < per; i++) {
+    const int c = lane + 32 * i;
+    const float d = c < C ? v[i] - mean : 0.f;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  for (int i = 0; i < per; i++) {
+    const int c = lane + 32 * i;
+    if (c < C) feat_out[(size_t)r * C + c] = (v[i] - mean) * rstd * gamma[c] + beta[c];
+  }
+}
+
+int rdm_vote_finish(const float* off, int ld_off, const float* xyz, const float* feats, int ld_f, const float* gamma,
+                    const float* beta, const float* h_limit3, float eps, int N, int C, float* xyz_out, float* feat_out,
+                    cudaStream_t stream) {
+  RDM_CHECK_ARG(C >= 1 && C <= 1024, "rdm_vote_finish: C must be <= 1024");
+  if (N == 0) return RDM_OK;
+  vote_finish_kernel<<<cdiv(N, 8), 256, 0, stream>>>(off, ld_off, xyz, feats, ld_f, gamma, beta, h_limit3[0], h_limit3[1],
+                                                     h_limit3[2], eps, N, C, xyz_out, feat_out);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
+
+// Row selection after NMS (experiments/model.py:233-246): up to 4 (src, dst, C) jobs gathered by the same index list;
+// `normalize` L2-normalises job 1's rows into dst_norm (F.normalize(p=2, dim=1), eps 1e-12; model.py:261-264) - used
+// AFTER the second transformer, so it is a separate flag on its own launch.
+struct GatherJobs {
+  const float* src[4];
+  float* dst[4];
+  int c[4], ld[4], n;
+};
+__global__ void __launch_bounds__(256) gather_rows_kernel(const GatherJobs jobs, const int64_t* __restrict__ sel, int count) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= count) return;
+  const long long s = sel[r];
+  for (int j = 0; j < jobs.n; j++)
+    for (int c = lane; c < jobs.c[j]; c += 32) jobs.dst[j][(size_t)r * jobs.c[j] + c] = jobs.src[j][(size_t)s * jobs.ld[j] + c];
+}
+int rdm_gather_rows(const float* const* h_src, float* const* h_dst, const int* h_c, const int* h_ld, int num_jobs,
+                    const int64_t* sel, int count, cudaStream_t stream) {
+  RDM_CHECK_ARG(num_jobs >= 1 && num_jobs <= 4, "rdm_gather_rows: 1..4 jobs");
+  if (count == 0) return RDM_OK;
+  GatherJobs g;
+  g.n = num_jobs;
+  for (int i = 0; i < num_jobs; i++) {
+    g.src[i] = h_src[i];
+    g.dst[i] = h_dst[i];
+    g.c[i] = h_c[i];
+    g.ld[i] = h_ld[i];
+  }
+  gather_rows_kernel<<<cdiv(count, 8), 256, 0, stream>>>(g, sel, count);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
+
+__global__ void __launch_bounds__(256) l2_normalize_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int C) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= N) return;
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float v = x[(size_t)r * C + c];
+    q = fmaf(v, v, q);
+  }
+  const float inv = 1.f / fmaxf(sqrtf(warp_sum(q)), 1e-12f);
+  for (int c = lane; c < C; c += 32) y[(size_t)r * C + c] = x[(size_t)r * C + c] * inv;
+}
+int rdm_l2_normalize(const float* x, float* y, int N, int C, cudaStream_t stream) {
+  if (N == 0) return RDM_OK;
+  l2_normalize_kernel<<<cdiv(N, 8), 256, 0, stream>>>(x, y, N, C);
   RDM_LAUNCH_CHECK();
   return RDM_OK;
 }

@@ -32,7 +32,7 @@ struct Arena {
   } while (0)
 
 int linear(Arena& a, const float* A, int lda, const float* W, int ldw, int nk, const float* bias, float* C, int M, int N, int K,
-           cudaStream_t st, double* gn_stats = nullptr, int gn_cpg = 0, int* stats_fused = nullptr) {
+           cudaStream_t st, double* gn_stats = nullptr, int gn_cpg = 0, int* stats_fused = nullptr, int ldc = 0) {
   void* ws = nullptr;
   size_t wsb = 0;
   size_t mark = a.off;
@@ -41,7 +41,7 @@ int linear(Arena& a, const float* A, int lda, const float* W, int ldw, int nk, c
     ws = a.raw(wsb);
   }
   int rc = RDM_OK;
-  if (!a.dry) rc = rdm_linear_gn(A, lda, W, ldw, nk, bias, C, N, M, N, K, 0, ws, wsb, gn_stats, gn_cpg, stats_fused, st);
+  if (!a.dry) rc = rdm_linear_gn(A, lda, W, ldw, nk, bias, C, ldc > 0 ? ldc : N, M, N, K, 0, ws, wsb, gn_stats, gn_cpg, stats_fused, st);
   a.off = mark;
   return rc;
 }
@@ -80,12 +80,14 @@ int linear_group_norm(Arena& a, StatSlots& ss, const float* x, int ldx, const fl
 
 // UnaryBlock (kpconv/modules.py:78-83): Linear + GroupNorm (+ residual) (+ LeakyReLU); out [M, c_out]
 int unary(Arena& a, StatSlots& ss, const rdm_unary_desc& u, const float* x, int ldx, float* out, int M, int groups,
-          const float* residual, int act, unsigned char* rowpos_out, cudaStream_t st) {
+          const float* residual, int act, unsigned char* rowpos_out, cudaStream_t st, int ld_out = 0) {
   const int ldw = u.ldw > 0 ? u.ldw : u.c_in;
-  if (u.gn_w != nullptr)
+  if (u.gn_w != nullptr) {
+    RDM_CHECK_ARG(ld_out == 0 || ld_out == u.c_out, "unary: a normalised block writes dense rows");
     return linear_group_norm(a, ss, x, ldx, u.w, ldw, 1, u.b, u.gn_w, u.gn_b, residual, out, M, u.c_out, u.c_in, groups, act,
                              rowpos_out, st);
-  return linear(a, x, ldx, u.w, ldw, 1, u.b, out, M, u.c_out, u.c_in, st);
+  }
+  return linear(a, x, ldx, u.w, ldw, 1, u.b, out, M, u.c_out, u.c_in, st, nullptr, 0, nullptr, ld_out);
 }
 
 // KPConv.forward (kpconv.py:79-122) + norm_conv + LeakyReLU: out [M, c_mid_out]
@@ -173,7 +175,7 @@ int encoder_run(Arena& a, const rdm_block_desc* blocks, int nb, const rdm_pyrami
 }
 
 int decoder_run(Arena& a, const rdm_unary_desc* dec, int num, const rdm_pyramid_desc& p, int top, int groups, const float* coarse,
-                int c_coarse, const float* const* skips, float* out, cudaStream_t st) {
+                int c_coarse, const float* const* skips, float* out, int ld_out, cudaStream_t st) {
   const float* x = coarse;
   int cx = c_coarse;
   StatSlots ss;
@@ -191,7 +193,7 @@ int decoder_run(Arena& a, const rdm_unary_desc* dec, int num, const rdm_pyramid_
       RDM_TRY(rdm_upsample_concat_ld(x, p.upsampling[s], p.index_bytes, p.up_width[s], c_skip ? skips[i] : nullptr, M, N, cx,
                                      c_skip, cat, ldc, st));
     float* y = (i + 1 == num) ? out : a.f((size_t)M * dec[i].c_out);
-    RDM_TRY(unary(a, ss, dec[i], cat, ldc, y, M, groups, nullptr, 1, nullptr, st));
+    RDM_TRY(unary(a, ss, dec[i], cat, ldc, y, M, groups, nullptr, 1, nullptr, st, (i + 1 == num) ? ld_out : 0));
     x = y;
     cx = dec[i].c_out;
   }
@@ -279,26 +281,26 @@ extern "C" size_t rdm_decoder_workspace(const rdm_unary_desc* h_dec, int num, co
   Arena a(nullptr, 0, true);
   const float* skips[8] = {nullptr};
   int cc = h_dec[0].c_in;  // dry run: channel split does not change the sizes
-  if (decoder_run(a, h_dec, num, *h_pyr, top_stage, groups, nullptr, cc, skips, nullptr, 0) != RDM_OK) return 0;
+  if (decoder_run(a, h_dec, num, *h_pyr, top_stage, groups, nullptr, cc, skips, nullptr, 0, 0) != RDM_OK) return 0;
   return a.peak + 4096;
 }
 
 extern "C" int rdm_decoder_forward(const rdm_unary_desc* h_dec, int num, const rdm_pyramid_desc* h_pyr, int top_stage, int groups,
-                                   const float* coarse, int c_coarse, const float* const* h_skips, float* out, void* workspace,
-                                   size_t workspace_bytes, cudaStream_t stream) {
+                                   const float* coarse, int c_coarse, const float* const* h_skips, float* out, int ld_out,
+                                   void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   RDM_CHECK_ARG(h_dec && h_pyr && h_skips && num >= 1 && num <= 7, "rdm_decoder_forward: bad arguments");
   Arena a(workspace, workspace_bytes, false);
   // size check first: the arena hands out pointers past the end otherwise
   {
     Arena d(nullptr, 0, true);
-    int rc = decoder_run(d, h_dec, num, *h_pyr, top_stage, groups, nullptr, c_coarse, h_skips, nullptr, 0);
+    int rc = decoder_run(d, h_dec, num, *h_pyr, top_stage, groups, nullptr, c_coarse, h_skips, nullptr, 0, 0);
     if (rc != RDM_OK) return rc;
     if (d.peak > workspace_bytes) {
       rdm_set_error("rdm_decoder_forward: workspace too small (%zu needed)", d.peak);
       return RDM_ERR_WORKSPACE;
     }
   }
-  return decoder_run(a, h_dec, num, *h_pyr, top_stage, groups, coarse, c_coarse, h_skips, out, stream);
+  return decoder_run(a, h_dec, num, *h_pyr, top_stage, groups, coarse, c_coarse, h_skips, out, ld_out, stream);
 }
 
 extern "C" size_t rdm_thdroformer_workspace(int n_ref, int n_src, int c_out) {
@@ -438,5 +440,187 @@ extern "C" int rdm_build_pyramid(const float* points, const int64_t* lengths, in
     rdm_set_error("rdm_build_pyramid: output buffer too small");
     return RDM_ERR_WORKSPACE;
   }
+  return RDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ matching tail
+namespace {
+struct MatchPinned {
+  int counts[2];
+  int coarse_count;
+  int meta[4];
+  float T[16];
+};
+MatchPinned* g_match_pinned = nullptr;
+
+// phase 1: vote + NMS (sizes known). Returns through `io` buffers; sel counts land in pinned memory.
+int match_phase1(Arena& a, const rdm_match_desc& d, const rdm_match_io& io, int* d_counts, cudaStream_t st) {
+  const int nc = io.nc, c = d.c;
+  size_t mark = a.off;
+  float* h0 = a.f((size_t)nc * d.h0);
+  float* h1 = a.f((size_t)nc * d.h1);
+  float* off = a.f((size_t)nc * (3 + c));
+  float* n2n_logit = a.f((size_t)nc);
+  RDM_TRY(linear(a, io.feats_c, c, d.v_w0, c, 1, d.v_b0, h0, nc, d.h0, c, st));
+  if (!a.dry) RDM_TRY(rdm_layernorm(h0, nullptr, d.v_g0, d.v_e0, h0, nc, d.h0, 1e-5f, 2, st));
+  RDM_TRY(linear(a, h0, d.h0, d.v_w1, d.h0, 1, d.v_b1, h1, nc, d.h1, d.h0, st));
+  if (!a.dry) RDM_TRY(rdm_layernorm(h1, nullptr, d.v_g1, d.v_e1, h1, nc, d.h1, 1e-5f, 2, st));
+  RDM_TRY(linear(a, h1, d.h1, d.v_wr, d.h1, 1, d.v_br, off, nc, 3 + c, d.h1, st));
+  if (!a.dry)
+    RDM_TRY(rdm_vote_finish(off, 3 + c, io.points_c, io.feats_c, c, d.v_go, d.v_eo, d.max_offset, 1e-5f, nc, c, io.shifted_points,
+                            io.vote_feats, st));
+  // n2n score head (model.py:209-212): sigmoid + clamp
+  RDM_TRY(linear(a, io.vote_feats, c, d.n2n_w, c, 1, d.n2n_b, n2n_logit, nc, 1, c, st));
+  if (!a.dry) RDM_TRY(rdm_activation(n2n_logit, io.n2n_scores, nc, 3, 0.f, st));
+  // NMS (vote.py:14-40): radius search on the shifted nodes, greedy rule, compaction
+  int* table = (int*)a.raw((size_t)nc * d.nms_limit * sizeof(int));
+  int* maxc = (int*)a.raw(sizeof(int));
+  const size_t wsb = rdm_radius_search_workspace(nc, 2);
+  void* ws = a.raw(wsb);
+  if (!a.dry) {
+    RDM_TRY(rdm_radius_search_impl(io.shifted_points, io.shifted_points, io.lengths_c, io.lengths_c, 2, nc, nc, nc, d.nms_radius,
+                                   d.nms_limit, table, 4, nullptr, maxc, nullptr, ws, wsb, st));
+    RDM_TRY(rdm_nms(table, 4, nc, d.nms_limit, io.nc_ref, io.nms_mask, io.selected, d_counts, st));
+  }
+  a.off = mark;
+  return RDM_OK;
+}
+
+// patch scores + Sinkhorn + LGR on the first P coarse correspondences (model.py:323-361)
+int match_patches(Arena& a, const rdm_match_desc& d, const rdm_match_io& io, int n0, int P, int* d_meta, cudaStream_t st) {
+  const int c = d.c, K = d.point_limit;
+  size_t mark = a.off;
+  float* scores = a.f((size_t)P * K * K);
+  const size_t wsb = rdm_lgr_workspace(P, K);
+  void* ws = a.raw(wsb);
+  if (!a.dry) {
+    const float* ff_ref = io.feats_f;
+    const float* ff_src = io.feats_f + (size_t)io.nf_ref * io.ld_feats_f;
+    const int64_t* knn_src = io.knn_indices + (size_t)n0 * K;
+    const unsigned char* km_src = io.knn_masks + (size_t)n0 * K;
+    RDM_TRY(rdm_patch_scores(ff_ref, io.nf_ref, ff_src, io.nf - io.nf_ref, c, io.ld_feats_f, io.knn_indices, knn_src, io.corr_ref,
+                             io.corr_src, P, K, 1.0f / sqrtf((float)c), scores, st));
+    RDM_TRY(rdm_sinkhorn(scores, P, K, K, io.knn_masks, km_src, io.corr_ref, io.corr_src, d.ot_alpha, d.sinkhorn_iterations,
+                         d.sinkhorn_inf, io.matching_scores, st));
+    RDM_TRY(rdm_lgr(io.matching_scores, P, K, io.points_f, io.points_f + 3 * (size_t)io.nf_ref, io.knn_indices, knn_src,
+                    io.knn_masks, km_src, io.corr_ref, io.corr_src, d.acceptance_radius, d.correspondence_threshold,
+                    d.refinement_steps, io.ref_corr_points, io.src_corr_points, io.corr_scores, io.corr_bij, io.transform, d_meta, ws,
+                    wsb, st));
+  }
+  a.off = mark;
+  return RDM_OK;
+}
+
+// phase 2: everything after the node selection, for n0 ref / n1 src survivors (capacities when dry)
+int match_phase2(Arena& a, const rdm_match_desc& d, const rdm_match_io& io, int n0, int n1, int* d_coarse_count, int* d_meta,
+                 cudaStream_t st) {
+  const int c = d.c, K = d.point_limit, P = d.num_correspondences;
+  const int ns = n0 + n1;
+  size_t mark = a.off;
+  float* sel_feats = a.f((size_t)ns * c);
+  float* t2 = a.f((size_t)ns * c);
+  if (!a.dry) {
+    const float* src[4] = {io.shifted_points, io.vote_feats, io.n2p_scores, io.n2n_scores};
+    float* dst[4] = {io.sel_points, sel_feats, io.sel_n2p, io.sel_n2n};
+    const int cc[4] = {3, c, 1, 1}, ld[4] = {3, c, 1, 1};
+    RDM_TRY(rdm_gather_rows(src, dst, cc, ld, 4, io.selected, ns, st));
+  }
+  {
+    const size_t wsb = rdm_thdroformer_workspace(n0 > 0 ? n0 : 1, n1 > 0 ? n1 : 1, c);
+    void* ws = a.raw(wsb);
+    if (!a.dry)
+      RDM_TRY(rdm_thdroformer_forward(d.h_transformer2, io.sel_points, n0, io.sel_points + 3 * (size_t)n0, n1, sel_feats, c,
+                                      sel_feats + (size_t)n0 * c, c, t2, t2 + (size_t)n0 * c, ws, wsb, st));
+  }
+  if (!a.dry) RDM_TRY(rdm_l2_normalize(t2, io.sel_feats_norm, ns, c, st));
+  // point_to_node_partition x2 (model.py:267-272)
+  {
+    int* p2n = (int*)a.raw(sizeof(int) * (size_t)io.nf);
+    const size_t w0 = rdm_point_to_node_workspace(io.nf_ref, n0 > 0 ? n0 : 1), w1 = rdm_point_to_node_workspace(io.nf - io.nf_ref, n1 > 0 ? n1 : 1);
+    void* ws = a.raw(w0 > w1 ? w0 : w1);
+    if (!a.dry) {
+      RDM_TRY(rdm_point_to_node(io.points_f, io.nf_ref, io.sel_points, n0, K, p2n, io.node_masks, io.knn_indices, io.knn_masks, ws,
+                                w0, st));
+      RDM_TRY(rdm_point_to_node(io.points_f + 3 * (size_t)io.nf_ref, io.nf - io.nf_ref, io.sel_points + 3 * (size_t)n0, n1, K,
+                                p2n + io.nf_ref, io.node_masks + n0, io.knn_indices + (size_t)n0 * K, io.knn_masks + (size_t)n0 * K,
+                                ws, w1, st));
+    }
+  }
+  // SuperPointMatching (model.py:308-311)
+  {
+    float* xy = a.f((size_t)(n0 > 0 ? n0 : 1) * (n1 > 0 ? n1 : 1));
+    float* sums = a.f((size_t)ns + 2);
+    RDM_TRY(linear(a, io.sel_feats_norm, c, io.sel_feats_norm + (size_t)n0 * c, c, 1, nullptr, xy, n0, n1, c, st));
+    if (!a.dry) {  // slots beyond the produced count stay at pair (0, 0): in range for the speculative patch pass below
+      RDM_CUDA(cudaMemsetAsync(io.corr_ref, 0, sizeof(int64_t) * P, st));
+      RDM_CUDA(cudaMemsetAsync(io.corr_src, 0, sizeof(int64_t) * P, st));
+    }
+    if (!a.dry)
+      RDM_TRY(rdm_coarse_matching(xy, n0, n1, io.node_masks, io.node_masks + n0, P, d.dual_normalization, io.corr_ref, io.corr_src,
+                                  io.corr_node_scores, d_coarse_count, sums, st));
+  }
+  RDM_TRY(match_patches(a, d, io, n0, P, d_meta, st));
+  a.off = mark;
+  return RDM_OK;
+}
+
+size_t match_ws(const rdm_match_desc& d, int nc, int nc_ref, int nf, int nf_ref) {
+  Arena a(nullptr, 0, true);
+  rdm_match_io io = {};
+  io.nc = nc; io.nc_ref = nc_ref; io.nf = nf; io.nf_ref = nf_ref;
+  a.raw(256);  // device counters
+  if (match_phase1(a, d, io, nullptr, 0) != RDM_OK) return 0;
+  if (match_phase2(a, d, io, nc_ref, nc - nc_ref, nullptr, nullptr, 0) != RDM_OK) return 0;
+  return a.peak + 4096;
+}
+}  // namespace
+
+extern "C" size_t rdm_match_workspace(const rdm_match_desc* h_desc, int nc, int nc_ref, int nf, int nf_ref) {
+  return match_ws(*h_desc, nc, nc_ref, nf, nf_ref);
+}
+
+extern "C" int rdm_match_forward(const rdm_match_desc* h_desc, const rdm_match_io* h_io, rdm_match_result* h_result, void* workspace,
+                                 size_t workspace_bytes, cudaStream_t stream) {
+  RDM_CHECK_ARG(h_desc && h_io && h_result && h_desc->h_transformer2, "rdm_match_forward: null argument");
+  const rdm_match_desc& d = *h_desc;
+  const rdm_match_io& io = *h_io;
+  RDM_CHECK_ARG(io.nc >= 1 && io.nc_ref >= 0 && io.nc_ref <= io.nc && io.nf >= 1 && io.nf_ref >= 0 && io.nf_ref <= io.nf &&
+                    d.point_limit == 128 && d.num_correspondences >= 1 && d.num_correspondences <= 1024 && d.c >= 16,
+                "rdm_match_forward: bad sizes");
+  if (workspace_bytes < match_ws(d, io.nc, io.nc_ref, io.nf, io.nf_ref)) {
+    rdm_set_error("rdm_match_forward: workspace too small");
+    return RDM_ERR_WORKSPACE;
+  }
+  if (g_match_pinned == nullptr) RDM_CUDA(cudaHostAlloc((void**)&g_match_pinned, sizeof(MatchPinned), cudaHostAllocDefault));
+  Arena a(workspace, workspace_bytes, false);
+  int* d_cnt = (int*)a.raw(256);  // [0,1] NMS counts, [2] coarse count, [4..7] LGR meta
+  RDM_TRY(match_phase1(a, d, io, d_cnt, stream));
+  RDM_CUDA(cudaMemcpyAsync(g_match_pinned->counts, d_cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+  RDM_CUDA(cudaStreamSynchronize(stream));  // sync 1: survivor counts = the shapes of everything below
+  const int n0 = g_match_pinned->counts[0], n1 = g_match_pinned->counts[1];
+  RDM_CHECK_ARG(n0 >= 0 && n1 >= 0 && n0 <= io.nc_ref && n1 <= io.nc - io.nc_ref, "rdm_match_forward: inconsistent NMS counts");
+  h_result->n_ref_sel = n0;
+  h_result->n_src_sel = n1;
+  h_result->num_patches = 0;
+  h_result->num_corr = 0;
+  RDM_CHECK_ARG(n0 >= 1 && n1 >= 1, "rdm_match_forward: no superpoint survived NMS in one of the clouds");
+  RDM_TRY(match_phase2(a, d, io, n0, n1, d_cnt + 2, d_cnt + 4, stream));
+  RDM_CUDA(cudaMemcpyAsync(&g_match_pinned->coarse_count, d_cnt + 2, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  RDM_CUDA(cudaMemcpyAsync(g_match_pinned->meta, d_cnt + 4, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+  RDM_CUDA(cudaMemcpyAsync(g_match_pinned->T, io.transform, 16 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+  RDM_CUDA(cudaStreamSynchronize(stream));  // sync 2: result counts + pose
+  if (g_match_pinned->coarse_count < d.num_correspondences) {
+    // fewer valid node pairs than requested (tiny clouds): the speculative pass saw padding patches; redo it at the
+    // exact count. superpoint_matching.py:52-53 takes min(num_correspondences, #pairs).
+    const int P = g_match_pinned->coarse_count;
+    RDM_CHECK_ARG(P >= 1, "rdm_match_forward: no coarse correspondence");
+    RDM_TRY(match_patches(a, d, io, n0, P, d_cnt + 4, stream));
+    RDM_CUDA(cudaMemcpyAsync(g_match_pinned->meta, d_cnt + 4, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    RDM_CUDA(cudaMemcpyAsync(g_match_pinned->T, io.transform, 16 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    RDM_CUDA(cudaStreamSynchronize(stream));
+  }
+  h_result->num_patches = g_match_pinned->coarse_count;
+  h_result->num_corr = g_match_pinned->meta[0];
+  memcpy(h_result->transform, g_match_pinned->T, sizeof(float) * 16);
   return RDM_OK;
 }

@@ -333,13 +333,18 @@ class Decoder(_Module):
         coarse = feats[4].contiguous()
         skips = [feats[3].contiguous(), feats[2].contiguous(), feats[1].contiguous()]
         skip_ptrs = (ctypes.c_void_p * 8)(*[t.data_ptr() for t in skips])
-        out = torch.empty((desc.n[1], self.decoder2.out_channels), dtype=torch.float32, device=coarse.device)
+        # rows padded to a multiple of 4 floats (257 -> 260): 16-byte rows for the GEMM epilogue and for the consumers of
+        # the feature columns (rdm_patch_scores); the returned tensor is the [:, :out_channels] view
+        c_out = self.decoder2.out_channels
+        ld_out = (c_out + 3) // 4 * 4
+        out_full = torch.empty((desc.n[1], ld_out), dtype=torch.float32, device=coarse.device)
+        out = out_full[:, :c_out]
         lib = L.lib()
         wsb = lib.rdm_decoder_workspace(ctypes.cast(self._descs, ctypes.c_void_p), 3, ctypes.byref(desc), 4, 32)
         ws = torch.empty(max(int(wsb), 1), dtype=torch.uint8, device=coarse.device)
         L.call("rdm_decoder_forward", ctypes.cast(self._descs, ctypes.c_void_p), 3, ctypes.byref(desc), 4,
                self.decoder4.norm.num_groups, L.ptr(coarse), coarse.shape[1], ctypes.cast(skip_ptrs, ctypes.c_void_p),
-               L.ptr(out), L.ptr(ws), int(wsb), L.stream())
+               L.ptr(out_full), ld_out, L.ptr(ws), int(wsb), L.stream())
         return [out]
 
     def forward_modules(self, feats, data_dict):
@@ -392,6 +397,86 @@ class RDMNet(_Module):
         return precompute_data_stack_mode(points.contiguous(), lengths, b.num_stages, b.init_voxel_size, b.init_radius,
                                           self.cfg.neighbor_limits, index_dtype=torch.int32, skip_unused=True)
 
+    def _match_desc(self):
+        """rdm_match_desc over this model's vote / score / transformer2 / matching parameters (cached; see _Module)."""
+        key = cache_key(self)
+        if getattr(self, "_mdesc_key", None) != key:
+            v, cfg = self.vote, self.cfg
+            mods = list(v.mlp_modules)
+            if len(mods) != 6 or v.max_offset_limit is None:
+                raise RuntimeError("rdm_match_forward expects the RDMNet vote head: two (Linear, LayerNorm, ReLU) stages")
+            d = L.MatchDesc()
+            d.v_w0, d.v_b0, d.v_g0, d.v_e0 = _p(mods[0].weight), _p(mods[0].bias), _p(mods[1].weight), _p(mods[1].bias)
+            d.v_w1, d.v_b1, d.v_g1, d.v_e1 = _p(mods[3].weight), _p(mods[3].bias), _p(mods[4].weight), _p(mods[4].bias)
+            d.v_wr, d.v_br = _p(v.ctr_reg.weight), _p(v.ctr_reg.bias)
+            d.v_go, d.v_eo = _p(v.out_proj[0].weight), _p(v.out_proj[0].bias)
+            for i, x in enumerate(v.max_offset_limit.tolist()):
+                d.max_offset[i] = float(x)
+            d.c, d.h0, d.h1 = mods[0].in_features, mods[0].out_features, mods[3].out_features
+            d.n2n_w, d.n2n_b = _p(self.proj_n2n_score.weight), _p(self.proj_n2n_score.bias)
+            t2 = self.transformer2.runner_desc()
+            d.h_transformer2 = ctypes.addressof(t2)
+            alpha = self.optimal_transport.alpha.detach().reshape(1).float().contiguous()
+            d.ot_alpha = alpha.data_ptr()
+            fm, ot = self.fine_matching, self.optimal_transport
+            d.nms_radius, d.acceptance_radius, d.sinkhorn_inf = float(self.nms.NMS_radius), float(fm.acceptance_radius), float(ot.inf)
+            d.nms_limit, d.point_limit = int(self.nms.neighbor_limits), int(self.num_points_in_patch)
+            d.num_correspondences = int(self.coarse_matching.num_correspondences)
+            d.dual_normalization = 1 if self.coarse_matching.dual_normalization else 0
+            d.sinkhorn_iterations, d.correspondence_threshold = int(ot.num_iterations), int(fm.correspondence_threshold)
+            d.refinement_steps = int(fm.num_refinement_steps)
+            self._mdesc, self._mdesc_keep, self._mdesc_key = d, (t2, alpha), key
+        return self._mdesc
+
+    def _match_tail(self, out, points_c, lengths_c, nc_ref, tf, n2p, points_f, nf_ref, feats_f):
+        """model_infer.py:180-354 through rdm_match_forward (one host call, two internal synchronisations)."""
+        d = self._match_desc()
+        dev = tf.device
+        nc, nf, c, K, P = points_c.shape[0], points_f.shape[0], d.c, d.point_limit, d.num_correspondences
+        f32, i64, u8 = torch.float32, torch.int64, torch.uint8
+        E = lambda shape, dt=f32: torch.empty(shape, dtype=dt, device=dev)
+        cap = P * 2 * K
+        B = dict(shifted=E((nc, 3)), vote_feats=E((nc, c)), n2n=E(nc), mask=E(nc, u8), sel=E(nc, i64), sel_points=E((nc, 3)),
+                 sel_feats=E((nc, c)), sel_n2p=E(nc), sel_n2n=E(nc), node_masks=E(nc, u8), knn=E((nc, K), i64),
+                 knn_masks=E((nc, K), u8), corr_ref=E(P, i64), corr_src=E(P, i64), corr_sc=E(P), ms=E((P, K + 1, K + 1)),
+                 rcp=E((cap, 3)), scp=E((cap, 3)), cs=E(cap), bij=E((cap, 3), torch.int32), T=E((4, 4)))
+        io = L.MatchIO()
+        io.points_c, io.lengths_c, io.nc, io.nc_ref = L.ptr(points_c), L.ptr(lengths_c), nc, nc_ref
+        io.feats_c, io.n2p_scores = L.ptr(tf), L.ptr(n2p)
+        io.points_f, io.nf, io.nf_ref = L.ptr(points_f), nf, nf_ref
+        if feats_f.stride(1) != 1 or feats_f.stride(0) % 4 != 0:
+            feats_f = feats_f.contiguous()
+        io.feats_f, io.ld_feats_f = feats_f.data_ptr(), feats_f.stride(0)
+        (io.shifted_points, io.vote_feats, io.n2n_scores, io.nms_mask, io.selected, io.sel_points, io.sel_feats_norm, io.sel_n2p,
+         io.sel_n2n, io.node_masks, io.knn_indices, io.knn_masks, io.corr_ref, io.corr_src, io.corr_node_scores,
+         io.matching_scores, io.ref_corr_points, io.src_corr_points, io.corr_scores, io.corr_bij, io.transform) = [
+            B[k].data_ptr() for k in ("shifted", "vote_feats", "n2n", "mask", "sel", "sel_points", "sel_feats", "sel_n2p", "sel_n2n",
+                                      "node_masks", "knn", "knn_masks", "corr_ref", "corr_src", "corr_sc", "ms", "rcp", "scp", "cs",
+                                      "bij", "T")]
+        lib = L.lib()
+        wsb = int(lib.rdm_match_workspace(ctypes.byref(d), nc, nc_ref, nf, nf_ref))
+        ws = torch.empty(max(wsb, 1), dtype=u8, device=dev)
+        res = L.MatchResult()
+        with torch.cuda.device(dev):
+            L.call("rdm_match_forward", ctypes.byref(d), ctypes.byref(io), ctypes.byref(res), L.ptr(ws), wsb, L.stream())
+        n0, n1, k, ncorr = res.n_ref_sel, res.n_src_sel, res.num_patches, res.num_corr
+        out["shifted_ref_points_c"], out["shifted_src_points_c"] = B["shifted"][:nc_ref], B["shifted"][nc_ref:]
+        out["mask"] = B["mask"].bool()
+        out["ref_points_c"], out["src_points_c"] = B["sel_points"][:n0], B["sel_points"][n0:n0 + n1]
+        out["ref_feats_c"], out["src_feats_c"] = B["sel_feats"][:n0], B["sel_feats"][n0:n0 + n1]
+        out["ref_n2p_scores_c"], out["src_n2p_scores_c"] = B["sel_n2p"][:n0], B["sel_n2p"][n0:n0 + n1]
+        out["ref_n2n_scores_c"], out["src_n2n_scores_c"] = B["sel_n2n"][:n0], B["sel_n2n"][n0:n0 + n1]
+        out["ref_node_corr_indices"], out["src_node_corr_indices"] = B["corr_ref"][:k], B["corr_src"][:k]
+        out["node_corr_scores"] = B["corr_sc"][:k]
+        out["ref_node_knn_indices"], out["src_node_knn_indices"] = B["knn"][:n0], B["knn"][n0:n0 + n1]
+        out["ref_node_knn_masks"], out["src_node_knn_masks"] = B["knn_masks"][:n0].bool(), B["knn_masks"][n0:n0 + n1].bool()
+        out["matching_scores"] = B["ms"][:k]
+        out["ref_corr_points"], out["src_corr_points"], out["corr_scores"] = B["rcp"][:ncorr], B["scp"][:ncorr], B["cs"][:ncorr]
+        out["corr_patch_ij"] = B["bij"][:ncorr]
+        out["estimated_transform"] = B["T"]
+        out["estimated_transform_host"] = torch.tensor(list(res.transform), dtype=f32).view(4, 4)
+        return out
+
     @torch.no_grad()
     def forward(self, data_dict):
         out = {}
@@ -430,11 +515,14 @@ class RDMNet(_Module):
         n2p = ops.activation(n2p_logit.view(-1), 3)
         feats_list[-1] = torch.cat([tf, n2p_logit], 1)
         dec = self.decoder(feats_list, data_dict, pyr)[0]
-        feats_f = dec[:, :-1].contiguous()
+        feats_f = dec[:, :-1]  # strided view (row stride 260): no copy of the 16 MB feature table
         p2p = ops.activation(dec[:, -1].contiguous(), 3)
         out["ref_p2p_scores_c"], out["src_p2p_scores_c"] = p2p[:nf], p2p[nf:]
         ref_n2p, src_n2p = n2p[:nc], n2p[nc:]
+        out["ref_feats_f"], out["src_feats_f"] = feats_f[:nf], feats_f[nf:]
 
+        if self.use_vote and not data_dict.get("stepwise", False):
+            return self._match_tail(out, points_c.contiguous(), lengths_c, nc, tf, n2p, points_f.contiguous(), nf, feats_f)
         if self.use_vote:
             shifted, vf = self.vote(points_c, tf)
             out["shifted_ref_points_c"], out["shifted_src_points_c"] = shifted[:nc], shifted[nc:]
@@ -459,7 +547,7 @@ class RDMNet(_Module):
         k = self.num_points_in_patch
         _, ref_node_masks, ref_knn, ref_knn_masks = ops.point_to_node_partition(ref_points_f, ref_points_c, k)
         _, src_node_masks, src_knn, src_knn_masks = ops.point_to_node_partition(src_points_f, src_points_c, k)
-        ref_feats_f, src_feats_f = feats_f[:nf].contiguous(), feats_f[nf:].contiguous()
+        ref_feats_f, src_feats_f = feats_f[:nf], feats_f[nf:]
         out["ref_feats_f"], out["src_feats_f"] = ref_feats_f, src_feats_f
 
         ref_ci, src_ci, node_corr_scores = self.coarse_matching(ref_feats_c_norm, src_feats_c_norm, ref_node_masks,

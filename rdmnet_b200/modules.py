@@ -388,9 +388,8 @@ class ThDRoFormer(_Module):
         return (f0[None], f1[None]) if batched else (f0, f1)
 
 
-    def _forward_runner(self, rp, sp, rf, sf):
-        """rdm_thdroformer_forward: embedding, in_proj, all fused layers and out_proj in one host call."""
-        import ctypes
+    def runner_desc(self):
+        """The rdm_thdroformer_desc of this module (cached; see _Module)."""
         L = ops.L
         tr = self.transformer
         key = cache_key(self)
@@ -406,7 +405,13 @@ class ThDRoFormer(_Module):
                 d.layer_blobs[i], d.is_self[i] = b.data_ptr(), 1 if kind == "self" else 0
             d.num_layers, d.c_in, d.c_out = len(blobs), self.in_proj.in_features, self.out_proj.out_features
             self._desc, self._desc_key = d, key
-        d = self._desc
+        return self._desc
+
+    def _forward_runner(self, rp, sp, rf, sf):
+        """rdm_thdroformer_forward: embedding, in_proj, all fused layers and out_proj in one host call."""
+        import ctypes
+        L = ops.L
+        d = self.runner_desc()
         if rf.stride(1) != 1 or sf.stride(1) != 1 or rf.shape[1] != d.c_in:
             raise RuntimeError("ThDRoFormer: feature tensors must be (N, input_dim) with contiguous channels")
         n0, n1, dev = rf.shape[0], sf.shape[0], rf.device

@@ -360,8 +360,11 @@ def patch_scores(ref_feats_f, src_feats_f, ref_knn_indices, src_knn_indices, ref
     """index_select + einsum('bnd,bmd->bnm') / sqrt(C) (experiments/model.py:323-343) without the gathered copies."""
     p, k = ref_corr_indices.shape[0], ref_knn_indices.shape[1]
     c = ref_feats_f.shape[1]
+    ld = ref_feats_f.stride(0)
+    if ref_feats_f.stride(1) != 1 or src_feats_f.stride(1) != 1 or src_feats_f.stride(0) != ld:
+        raise RuntimeError("patch_scores: feature tables need contiguous channels and a common row stride")
     out = torch.empty((p, k, k), dtype=torch.float32, device=ref_feats_f.device)
-    L.call("rdm_patch_scores", L.ptr(ref_feats_f), ref_feats_f.shape[0], L.ptr(src_feats_f), src_feats_f.shape[0], c,
+    L.call("rdm_patch_scores", ref_feats_f.data_ptr(), ref_feats_f.shape[0], src_feats_f.data_ptr(), src_feats_f.shape[0], c, ld,
            L.ptr(ref_knn_indices), L.ptr(src_knn_indices), L.ptr(ref_corr_indices), L.ptr(src_corr_indices), p, k,
            1.0 / c ** 0.5, L.ptr(out), L.stream())
     return out

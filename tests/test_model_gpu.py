@@ -139,3 +139,21 @@ def test_gpu_pyramid_equals_reference_tables(scans):
         for i, (x, y) in enumerate(zip(got[k], ref[k])):
             assert np.array_equal(x.cpu().numpy(), y), f"{k}[{i}]"
     assert got["lengths_host"][-1] == [431, 390]
+
+
+def test_match_tail_runner_equals_stepwise_path(model, scans):
+    """rdm_match_forward (one host call after the decoder) == the per-operator Python wiring of the same kernels."""
+    a, b = scans["s000000"], scans["s000007"]
+    pts = torch.from_numpy(np.concatenate([a, b])).cuda()
+    lens = torch.tensor([len(a), len(b)], dtype=torch.int64).cuda()
+    fast = model({"points": pts, "lengths": lens})
+    slow = model({"points": pts, "lengths": lens, "stepwise": True})
+    for k in ("mask", "ref_node_corr_indices", "src_node_corr_indices", "ref_node_knn_indices", "src_node_knn_indices",
+              "ref_node_knn_masks", "src_node_knn_masks"):
+        assert torch.equal(fast[k], slow[k]), k
+    for k, tol in (("shifted_ref_points_c", 1e-5), ("ref_points_c", 1e-5), ("src_points_c", 1e-5), ("ref_feats_c", 1e-5),
+                   ("src_feats_c", 1e-5), ("ref_n2n_scores_c", 1e-5), ("src_n2p_scores_c", 1e-6), ("node_corr_scores", 1e-5),
+                   ("corr_scores", 1e-4), ("estimated_transform", 1e-5)):
+        close(fast[k], slow[k], tol, k)
+    assert torch.equal(fast["ref_corr_points"], slow["ref_corr_points"]) and torch.equal(fast["src_corr_points"], slow["src_corr_points"])
+    close(fast["estimated_transform_host"], fast["estimated_transform"].cpu(), 0.0, "pinned pose readback")
