@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=4, help="distinct synthetic pairs per rank (cycled)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="one pair at a time (model(data_dict) / PairRegistrar.register) instead of the pair pipeline")
     ap.add_argument("--cpu-pairs", type=int, default=3, help="pairs in the bounded cpu_baseline sample")
     return ap.parse_args()
 
@@ -174,7 +176,8 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from rdmnet_b200 import _lib as L
-    from rdmnet_b200.api import PairRegistrar
+    from rdmnet_b200.api import PairRegistrar, PairStreamRegistrar
+    from rdmnet_b200.model import PairPipeline
     from rdmnet_b200.ops import kpconv_gather_bytes as ops_kpconv_gather_bytes
     from rdmnet_b200.model import create_model
 
@@ -203,6 +206,9 @@ def run_ours(args, rank, world, local_rank):
         d_pairs.append((pts, lens))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    pipelined = not args.no_pipeline
+    pipe = PairPipeline(model, dev)
+
     def step(i):
         pts, lens = d_pairs[i % len(d_pairs)]
         return model({"points": pts, "lengths": lens})
@@ -212,11 +218,18 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step(i)
+    if pipelined:
+        for _ in pipe.run(d_pairs[i % len(d_pairs)] for i in range(args.warmup)):
+            pass
+    else:
+        for i in range(args.warmup):
+            step(i)
     barrier()
 
-    # ---- timed region 1: device-resident inputs; per-step CUDA events, L2 flush (untimed) between steps
+    # ---- timed region 1: device-resident inputs; per-step CUDA events, L2 flush (untimed) between steps.
+    # Pipelined: while step i is in the network the pyramid of step i+1 is built on a side stream, so every timed step
+    # contains exactly one pyramid build and one network pass; the events live on the main stream, which also waits
+    # (inside the bracket) for the pyramid it consumes.
     clocks = ClockSampler(local_rank)
     clocks.start()
     L.prof_enable(True)
@@ -224,31 +237,61 @@ def run_ours(args, rank, world, local_rank):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t_wall0 = time.perf_counter()
-    rre_ok = 0
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)
-        ev[i][0].record()
-        out = step(i)
-        ev[i][1].record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    launches = L.launch_count() - launches0
+    if pipelined:
+        def before(i):
+            if i < args.steps:
+                flush.fill_(i & 0xFF)
+                ev[i][0].record()
+        gen = pipe.run((d_pairs[i % len(d_pairs)] for i in range(args.steps + 1)), before_step=before)
+        for i in range(args.steps):
+            out = next(gen)
+            ev[i][1].record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        launches = L.launch_count() - launches0
+        for _ in gen:  # the look-ahead pair: untimed
+            pass
+    else:
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)
+            ev[i][0].record()
+            out = step(i)
+            ev[i][1].record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        launches = L.launch_count() - launches0
     prof = L.prof_read()
     L.prof_enable(False)
+    torch.cuda.synchronize()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))
     clk = clocks.stop()
 
     # ---- timed region 2: end to end through the host-buffer API (pinned H2D of the points, D2H of the results)
-    reg = PairRegistrar(model, max_points=max(p[0].shape[0] for p in d_pairs), device=dev)
-    for i in range(min(args.warmup, 3)):
-        reg.register(pairs[i % len(pairs)]["ref_points"], pairs[i % len(pairs)]["src_points"])
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        res = reg.register(pairs[i % len(pairs)]["ref_points"], pairs[i % len(pairs)]["src_points"])
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    maxp = max(p[0].shape[0] for p in d_pairs)
+    host_pairs = [(pairs[i % len(pairs)]["ref_points"], pairs[i % len(pairs)]["src_points"]) for i in range(max(args.steps, 3))]
+    if pipelined:
+        reg = PairStreamRegistrar(model, max_points=maxp, device=dev)
+        for res in reg.register_stream(host_pairs[:min(args.warmup, 3)]):
+            pass
+        barrier()
+        t0 = time.perf_counter()
+        for res in reg.register_stream(host_pairs[:args.steps]):
+            pass
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        api_name = "rdmnet_b200.api.PairStreamRegistrar.register_stream (host numpy in, host numpy out, pair i+1 staged while pair i runs)"
+    else:
+        reg = PairRegistrar(model, max_points=maxp, device=dev)
+        for i in range(min(args.warmup, 3)):
+            reg.register(*host_pairs[i])
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            res = reg.register(*host_pairs[i])
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        api_name = "rdmnet_b200.api.PairRegistrar.register (host numpy in, host numpy out)"
 
     # max over ranks
     tm = torch.tensor([total_ms, e2e_s * 1e3, t_wall * 1e3], dtype=torch.float64, device=dev)
@@ -291,11 +334,13 @@ def run_ours(args, rank, world, local_rank):
                        "points_per_pair": [int(p[0].shape[0]) for p in d_pairs], "neighbor_limits": LIMITS,
                        "weights": wdesc, "l2": "256 MiB flush write between timed steps (untimed)",
                        "timing": "CUDA events per step on the launch stream, summed; max over ranks; kernel events recorded inside the library around the launches",
-                       "sharding": "pairs round-robin over ranks, no data-path collective"},
+                       "sharding": "pairs round-robin over ranks, no data-path collective",
+                       "pipeline": ("pair pipeline: pyramid of pair i+1 on a side stream during the network pass of pair i"
+                                    if pipelined else "off: one pair at a time")},
             "wall_ms_per_step_incl_flush": wall_ms / args.steps,
             "e2e": {"value": world * args.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": reg.h2d_bytes,
                     "d2h_bytes_per_step": reg.d2h_bytes, "ms_per_step": e2e_ms / args.steps,
-                    "api": "rdmnet_b200.api.PairRegistrar.register (host numpy in, host numpy out)"},
+                    "api": api_name},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "kpconv_gather_kernel (+row_positive prepass), 14 launches/step", "bound": "hbm",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,

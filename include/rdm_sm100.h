@@ -212,6 +212,15 @@ size_t rdm_build_pyramid_workspace(int64_t n0, const rdm_pyramid_cfg* h_cfg);
 int rdm_build_pyramid(const float* points, const int64_t* lengths, int64_t n0, const rdm_pyramid_cfg* h_cfg, void* out_buf,
                       size_t out_bytes, void* workspace, size_t workspace_bytes, rdm_pyramid_desc* h_desc,
                       int64_t* h_lengths, const int64_t** h_d_lengths, rdm_stream_t stream);
+/* two-phase form for pipelining pairs: _begin queues the subsampling chain + the size readback and returns at once;
+ * _finish waits for that readback (host), then queues every radius search. A job handle carries the state (one
+ * pyramid in flight per handle; out_buf / workspace must stay alive until _finish's work has run). */
+void* rdm_pyramid_job_create(void);
+void rdm_pyramid_job_destroy(void* job);
+int rdm_build_pyramid_begin(void* job, const float* points, const int64_t* lengths, int64_t n0, const rdm_pyramid_cfg* h_cfg,
+                            void* out_buf, size_t out_bytes, void* workspace, size_t workspace_bytes, rdm_stream_t stream);
+int rdm_build_pyramid_finish(void* job, rdm_pyramid_desc* h_desc, int64_t* h_lengths, const int64_t** h_d_lengths,
+                             rdm_stream_t stream);
 size_t rdm_encoder_workspace(const rdm_block_desc* h_blocks, int num_blocks, const rdm_pyramid_desc* h_pyr, int groups);
 int rdm_encoder_forward(const rdm_block_desc* h_blocks, int num_blocks, const rdm_pyramid_desc* h_pyr, int groups,
                         const float* in_feats, float* const* h_out_feats, void* workspace, size_t workspace_bytes,

@@ -28,6 +28,11 @@ SIGNATURES = {
     "rdm_build_pyramid_workspace": (c_size_t, [c_i64, c_void_p]),
     "rdm_build_pyramid": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p,
                                   c_void_p, c_void_p, c_void_p]),
+    "rdm_pyramid_job_create": (c_void_p, []),
+    "rdm_pyramid_job_destroy": (None, [c_void_p]),
+    "rdm_build_pyramid_begin": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t,
+                                        c_void_p]),
+    "rdm_build_pyramid_finish": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdm_kpconv_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_int,
                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdm_maxpool": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

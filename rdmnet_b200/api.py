@@ -43,6 +43,47 @@ class PairRegistrar:
         return res
 
 
+class PairStreamRegistrar(PairRegistrar):
+    """Throughput form of PairRegistrar: ``register_stream(pairs)`` takes an iterable of (ref_points, src_points) host
+    arrays and yields one result dict per pair, in order. Pair i+1 is staged (pinned copy + H2D) and its voxel pyramid
+    built on a side stream while pair i is in the network (rdmnet_b200.model.PairPipeline) - the role the reference gives
+    to its DataLoader workers. Same results as register() pair by pair."""
+
+    def __init__(self, model, max_points=1 << 18, device=None):
+        super().__init__(model, max_points, device)
+        from .model import PairPipeline
+        self.pipe = PairPipeline(model, self.device)
+        self.h_pts = [self.h_points, torch.empty_like(self.h_points).pin_memory()]
+        self.h_len = [self.h_lengths, torch.empty_like(self.h_lengths).pin_memory()]
+
+    def _stager(self, ref_points, src_points, slot):
+        def stage():  # runs under the pipeline's side stream
+            nr, ns = ref_points.shape[0], src_points.shape[0]
+            if nr + ns > self.h_pts[slot].shape[0]:
+                raise RuntimeError("PairStreamRegistrar: pair larger than the staging buffer")
+            hp, hl = self.h_pts[slot], self.h_len[slot]
+            hp[:nr] = torch.as_tensor(ref_points)
+            hp[nr:nr + ns] = torch.as_tensor(src_points)
+            hl[0], hl[1] = nr, ns
+            pts = hp[:nr + ns].to(self.device, non_blocking=True)
+            lens = hl.to(self.device, non_blocking=True)
+            self.h2d_bytes = pts.numel() * 4 + lens.numel() * 8
+            return pts, lens
+        return stage
+
+    def register_stream(self, pairs, keys=RESULT_KEYS):
+        items = (self._stager(r, s, i & 1) for i, (r, s) in enumerate(pairs))
+        for out in self.pipe.run(items):
+            res = {}
+            for k in keys:
+                if k == "estimated_transform" and "estimated_transform_host" in out:
+                    res[k] = out["estimated_transform_host"].numpy()
+                else:
+                    res[k] = out[k].cpu().numpy()
+            self.d2h_bytes = int(sum(v.nbytes for v in res.values()))
+            yield res
+
+
 def register_pair(model, ref_points, src_points):
     return PairRegistrar(model, max_points=ref_points.shape[0] + src_points.shape[0]).register(
         np.ascontiguousarray(ref_points, np.float32), np.ascontiguousarray(src_points, np.float32))

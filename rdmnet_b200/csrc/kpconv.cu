@@ -25,13 +25,51 @@ __global__ void row_positive_kernel(const float* __restrict__ f, int n, int c, u
 }
 
 struct KPts {
-  float x[KP_K], y[KP_K], z[KP_K];
+  float x[16], y[16], z[16];  // 15 kernel points + one far-away dummy (influence 0): pairs feed the packed f32x2 math
 };
 
 __device__ __forceinline__ float sqrt_approx(float x) {
   float r;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+}
+
+// ---- packed fp32x2 helpers (sm_100: add / mul / fma .f32x2 take two lanes' worth of fp32 per instruction)
+__device__ __forceinline__ unsigned long long pk2(float a, float b) {
+  const float2 t = make_float2(a, b);
+  return *reinterpret_cast<const unsigned long long*>(&t);
+}
+__device__ __forceinline__ float2 up2(unsigned long long v) { return *reinterpret_cast<float2*>(&v); }
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// w[k] = max(0, 1 - |d - kp_k| / sigma), k = 0..15 (w[15] = 0 through the dummy point), two kernel points per instruction.
+// Same roundings as the scalar form: every packed op is two IEEE round-to-nearest ops (kpconv.py:98-99).
+__device__ __forceinline__ void influences16(float dx, float dy, float dz, const KPts& kp, float inv_sigma, float (&w)[16]) {
+  const unsigned long long dx2 = pk2(dx, dx), dy2 = pk2(dy, dy), dz2 = pk2(dz, dz), one2 = pk2(1.f, 1.f),
+                           ninv2 = pk2(-inv_sigma, -inv_sigma);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const unsigned long long ex = add2(dx2, pk2(-kp.x[2 * k], -kp.x[2 * k + 1]));
+    const unsigned long long ey = add2(dy2, pk2(-kp.y[2 * k], -kp.y[2 * k + 1]));
+    const unsigned long long ez = add2(dz2, pk2(-kp.z[2 * k], -kp.z[2 * k + 1]));
+    const float2 dd = up2(fma2(ez, ez, fma2(ey, ey, mul2(ex, ex))));
+    const float2 ww = up2(fma2(pk2(sqrt_approx(dd.x), sqrt_approx(dd.y)), ninv2, one2));
+    w[2 * k] = fmaxf(ww.x, 0.f);
+    w[2 * k + 1] = fmaxf(ww.y, 0.f);
+  }
 }
 
 // C_in == 1 (encoder1_1): 8 lanes per query (4 queries per warp), lanes stride over the neighbour list; the 15
@@ -77,13 +115,10 @@ __global__ void __launch_bounds__(256) kpconv_gather_c1_kernel(const float* __re
       if (jj[i] >= N) continue;
       const float f = ff[i];
       cnt += f > 0.f;
-      const float dx = px[i] - qx, dy = py[i] - qy, dz = pz[i] - qz;
+      float w[16];
+      influences16(px[i] - qx, py[i] - qy, pz[i] - qz, kp, inv_sigma, w);
 #pragma unroll
-      for (int k = 0; k < KP_K; k++) {
-        const float ex = dx - kp.x[k], ey = dy - kp.y[k], ez = dz - kp.z[k];
-        const float w = fmaxf(0.f, fmaf(-sqrt_approx(fmaf(ez, ez, fmaf(ey, ey, ex * ex))), inv_sigma, 1.f));
-        acc[k] = fmaf(w, f, acc[k]);
-      }
+      for (int k = 0; k < KP_K; k++) acc[k] = fmaf(w[k], f, acc[k]);
     }
   }
 #pragma unroll
@@ -470,19 +505,12 @@ __global__ void __launch_bounds__(128, 4) kpconv_gather_v4_kernel(const float* _
     // ---- (A) influences of this lane's slot
     float w[16];
     if (j >= 0) {
-      const float dx = s_pts[3 * (size_t)j] - qx, dy = s_pts[3 * (size_t)j + 1] - qy, dz = s_pts[3 * (size_t)j + 2] - qz;
-#pragma unroll
-      for (int k = 0; k < KP_K; k++) {
-        const float ex = dx - kp.x[k], ey = dy - kp.y[k], ez = dz - kp.z[k];
-        const float d = sqrt_approx(fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
-        w[k] = fmaxf(0.f, fmaf(-d, inv_sigma, 1.f));  // kpconv.py:98-99
-      }
+      influences16(s_pts[3 * (size_t)j] - qx, s_pts[3 * (size_t)j + 1] - qy, s_pts[3 * (size_t)j + 2] - qz, kp, inv_sigma, w);
       npos += rowpos[j];
     } else {
 #pragma unroll
-      for (int k = 0; k < KP_K; k++) w[k] = 0.f;
+      for (int k = 0; k < 16; k++) w[k] = 0.f;
     }
-    w[15] = 0.f;
     wrow[0] = make_float4(w[0], w[1], w[2], w[3]);
     wrow[1] = make_float4(w[4], w[5], w[6], w[7]);
     wrow[2] = make_float4(w[8], w[9], w[10], w[11]);
@@ -573,6 +601,7 @@ static int launch_gather(const float* feats, const unsigned char* rowpos, const 
     kp.y[k] = h_kpts[3 * k + 1];
     kp.z[k] = h_kpts[3 * k + 2];
   }
+  kp.x[15] = kp.y[15] = kp.z[15] = 1.0e6f;  // dummy 16th point: |d - kp| / sigma >> 1 -> influence exactly 0
   const float inv_sigma = 1.f / sigma;
   if (C == 1) {
     kpconv_gather_c1_kernel<IdxT><<<cdiv(M, 32), 256, 0, stream>>>(feats, q, s, idx, kp, inv_sigma, M, N, H, order, out);
@@ -591,7 +620,7 @@ static int launch_gather(const float* feats, const unsigned char* rowpos, const 
     static int wps = 0;
     if (wps == 0) {
       const char* e = getenv("RDM_GATHER_WPS");  // tuning knob: warps per SM a mapping must reach before it is taken
-      wps = (e && atoi(e) > 0) ? atoi(e) : 16;
+      wps = (e && atoi(e) > 0) ? atoi(e) : 8;  // measured (profiles/r01e): 8 beats 16 on the strided / deep layers
     }
     const long long want = 148LL * wps;
     static int ver = 0;

@@ -355,17 +355,53 @@ size_t pyramid_ws(int64_t n0, const rdm_pyramid_cfg& c) {
   size_t a = rdm_grid_subsample_workspace(n0, c.batch), b = rdm_radius_search_workspace(n0, c.batch);
   return (a > b ? a : b) + 4096;
 }
-int64_t* g_pinned_lengths = nullptr;  // host staging for the one readback (process-wide; calls are serialised by the GIL)
 }  // namespace
 
 extern "C" size_t rdm_build_pyramid_bytes(int64_t n0, const rdm_pyramid_cfg* c) { return pyramid_bytes(n0, *c); }
 extern "C" size_t rdm_build_pyramid_workspace(int64_t n0, const rdm_pyramid_cfg* c) { return pyramid_ws(n0, *c); }
 
-extern "C" int rdm_build_pyramid(const float* points, const int64_t* lengths, int64_t n0, const rdm_pyramid_cfg* h_cfg,
-                                 void* out_buf, size_t out_bytes, void* workspace, size_t workspace_bytes,
-                                 rdm_pyramid_desc* h_desc, int64_t* h_lengths, const int64_t** h_d_lengths,
-                                 cudaStream_t stream) {
-  RDM_CHECK_ARG(h_cfg && h_desc && h_lengths && h_d_lengths && points && lengths, "rdm_build_pyramid: null argument");
+// Two-phase form (used by the pair pipeline: the subsampling chain of pair i+1 runs on a side stream while pair i is in
+// the network): begin = chained subsamplings + asynchronous readback of the stage sizes + event; finish = wait for that
+// event (host), then every radius search at its exact size. rdm_build_pyramid = begin + finish.
+struct PyramidJob {
+  cudaEvent_t ev = nullptr;
+  int64_t* pinned = nullptr;  // [8 * 16]
+  const float* points = nullptr;
+  int64_t n0 = 0;
+  rdm_pyramid_cfg cfg;
+  void *out_buf = nullptr, *ws = nullptr;
+  size_t out_bytes = 0, ws_bytes = 0;
+  int64_t* d_len = nullptr;
+  int* d_maxc = nullptr;
+  float* pts[8];
+  size_t out_off = 0;
+  bool pending = false;
+};
+
+extern "C" void* rdm_pyramid_job_create(void) {
+  PyramidJob* j = new PyramidJob();
+  if (cudaEventCreateWithFlags(&j->ev, cudaEventDisableTiming) != cudaSuccess ||
+      cudaHostAlloc((void**)&j->pinned, sizeof(int64_t) * 8 * 16, cudaHostAllocDefault) != cudaSuccess) {
+    rdm_set_error("rdm_pyramid_job_create: CUDA allocation failed");
+    delete j;
+    return nullptr;
+  }
+  return j;
+}
+
+extern "C" void rdm_pyramid_job_destroy(void* job) {
+  PyramidJob* j = (PyramidJob*)job;
+  if (j == nullptr) return;
+  if (j->ev) cudaEventDestroy(j->ev);
+  if (j->pinned) cudaFreeHost(j->pinned);
+  delete j;
+}
+
+extern "C" int rdm_build_pyramid_begin(void* job, const float* points, const int64_t* lengths, int64_t n0,
+                                       const rdm_pyramid_cfg* h_cfg, void* out_buf, size_t out_bytes, void* workspace,
+                                       size_t workspace_bytes, cudaStream_t stream) {
+  PyramidJob* j = (PyramidJob*)job;
+  RDM_CHECK_ARG(j && h_cfg && points && lengths, "rdm_build_pyramid_begin: null argument");
   const rdm_pyramid_cfg& c = *h_cfg;
   RDM_CHECK_ARG(c.num_stages >= 1 && c.num_stages <= 8 && c.batch >= 1 && c.batch <= 16 && n0 >= 1 && n0 < (1LL << 28),
                 "rdm_build_pyramid: bad configuration");
@@ -373,24 +409,45 @@ extern "C" int rdm_build_pyramid(const float* points, const int64_t* lengths, in
     rdm_set_error("rdm_build_pyramid: output buffer or workspace too small");
     return RDM_ERR_WORKSPACE;
   }
-  if (g_pinned_lengths == nullptr) RDM_CUDA(cudaHostAlloc((void**)&g_pinned_lengths, sizeof(int64_t) * 8 * 16, cudaHostAllocDefault));
+  j->points = points; j->n0 = n0; j->cfg = c; j->out_buf = out_buf; j->out_bytes = out_bytes; j->ws = workspace;
+  j->ws_bytes = workspace_bytes;
   Workspace out(out_buf, out_bytes);
   const int S = c.num_stages, B = c.batch;
-  int64_t* d_len = out.get<int64_t>((size_t)S * B);  // stage-major
-  int* d_maxc = out.get<int>(64);
-  float* pts[8];
-  pts[0] = const_cast<float*>(points);
-  for (int s = 1; s < S; s++) pts[s] = out.get<float>((size_t)n0 * 3);
+  j->d_len = out.get<int64_t>((size_t)S * B);  // stage-major
+  j->d_maxc = out.get<int>(64);
+  j->pts[0] = const_cast<float*>(points);
+  for (int s = 1; s < S; s++) j->pts[s] = out.get<float>((size_t)n0 * 3);
+  j->out_off = out.off;
   // ---- chained subsampling: capacity launches driven by the device-side lengths, no host round trip in between
-  RDM_CUDA(cudaMemcpyAsync(d_len, lengths, sizeof(int64_t) * B, cudaMemcpyDeviceToDevice, stream));
+  RDM_CUDA(cudaMemcpyAsync(j->d_len, lengths, sizeof(int64_t) * B, cudaMemcpyDeviceToDevice, stream));
   float voxel = c.first_voxel;
   for (int s = 1; s < S; s++) {
-    RDM_TRY(rdm_grid_subsample(pts[s - 1], d_len + (size_t)(s - 1) * B, B, n0, voxel, pts[s], d_len + (size_t)s * B, workspace,
-                               workspace_bytes, stream));
+    RDM_TRY(rdm_grid_subsample(j->pts[s - 1], j->d_len + (size_t)(s - 1) * B, B, n0, voxel, j->pts[s], j->d_len + (size_t)s * B,
+                               workspace, workspace_bytes, stream));
     voxel *= 2.f;
   }
-  RDM_CUDA(cudaMemcpyAsync(g_pinned_lengths, d_len, sizeof(int64_t) * S * B, cudaMemcpyDeviceToHost, stream));
-  RDM_CUDA(cudaStreamSynchronize(stream));  // the one synchronisation: stage sizes decide every later shape
+  RDM_CUDA(cudaMemcpyAsync(j->pinned, j->d_len, sizeof(int64_t) * S * B, cudaMemcpyDeviceToHost, stream));
+  RDM_CUDA(cudaEventRecord(j->ev, stream));
+  j->pending = true;
+  return RDM_OK;
+}
+
+extern "C" int rdm_build_pyramid_finish(void* job, rdm_pyramid_desc* h_desc, int64_t* h_lengths, const int64_t** h_d_lengths,
+                                        cudaStream_t stream) {
+  PyramidJob* j = (PyramidJob*)job;
+  RDM_CHECK_ARG(j && j->pending && h_desc && h_lengths && h_d_lengths, "rdm_build_pyramid_finish: no pyramid in flight");
+  j->pending = false;
+  RDM_CUDA(cudaEventSynchronize(j->ev));  // the one synchronisation: stage sizes decide every later shape
+  const rdm_pyramid_cfg& c = j->cfg;
+  const int S = c.num_stages, B = c.batch;
+  const int64_t n0 = j->n0;
+  Workspace out(j->out_buf, j->out_bytes);
+  out.off = j->out_off;
+  void* workspace = j->ws;
+  const size_t workspace_bytes = j->ws_bytes;
+  float** pts = j->pts;
+  int64_t* d_len = j->d_len;
+  int* d_maxc = j->d_maxc;
   rdm_pyramid_desc& d = *h_desc;
   memset(&d, 0, sizeof(d));
   d.num_stages = S;
@@ -398,8 +455,8 @@ extern "C" int rdm_build_pyramid(const float* points, const int64_t* lengths, in
   for (int s = 0; s < S; s++) {
     int64_t tot = 0;
     for (int b = 0; b < B; b++) {
-      h_lengths[s * B + b] = g_pinned_lengths[s * B + b];
-      tot += g_pinned_lengths[s * B + b];
+      h_lengths[s * B + b] = j->pinned[s * B + b];
+      tot += j->pinned[s * B + b];
     }
     RDM_CHECK_ARG(tot >= 0 && tot <= n0, "rdm_build_pyramid: inconsistent stage size");
     d.n[s] = (int)tot;
@@ -441,6 +498,17 @@ extern "C" int rdm_build_pyramid(const float* points, const int64_t* lengths, in
     return RDM_ERR_WORKSPACE;
   }
   return RDM_OK;
+}
+
+extern "C" int rdm_build_pyramid(const float* points, const int64_t* lengths, int64_t n0, const rdm_pyramid_cfg* h_cfg,
+                                 void* out_buf, size_t out_bytes, void* workspace, size_t workspace_bytes,
+                                 rdm_pyramid_desc* h_desc, int64_t* h_lengths, const int64_t** h_d_lengths,
+                                 cudaStream_t stream) {
+  static void* job = nullptr;  // calls are serialised by the caller (GIL)
+  if (job == nullptr) job = rdm_pyramid_job_create();
+  if (job == nullptr) return RDM_ERR_CUDA;
+  RDM_TRY(rdm_build_pyramid_begin(job, points, lengths, n0, h_cfg, out_buf, out_bytes, workspace, workspace_bytes, stream));
+  return rdm_build_pyramid_finish(job, h_desc, h_lengths, h_d_lengths, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ matching tail

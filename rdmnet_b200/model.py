@@ -141,29 +141,122 @@ class GpuPyramid:
                 "upsampling": [self.table("upsampling", s) for s in range(S - 1)]}
 
 
+class PyramidJob:
+    """One pyramid in flight through rdm_build_pyramid_begin / _finish (the two-phase form of rdm_build_pyramid)."""
+
+    def __init__(self):
+        self.handle = L.lib().rdm_pyramid_job_create()
+        if not self.handle:
+            raise RuntimeError("rdm_pyramid_job_create failed: " + L.lib().rdm_last_error().decode())
+        self._live = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                L.lib().rdm_pyramid_job_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def begin(self, points, lengths, num_stages, voxel_size, radius, neighbor_limits, skip_unused=True, up_nearest_only=True):
+        """Queues the chained subsamplings + the size readback on the current stream; returns immediately."""
+        points = points.contiguous()
+        n0, batch = points.shape[0], lengths.shape[0]
+        cfg = L.PyramidCfg()
+        cfg.num_stages, cfg.batch, cfg.first_voxel, cfg.first_radius = num_stages, batch, voxel_size * 2, radius
+        for i, v in enumerate(neighbor_limits):
+            cfg.limits[i] = int(v)
+        cfg.skip_up0, cfg.up_nearest_only = int(skip_unused), int(up_nearest_only)
+        lib = L.lib()
+        ob, wb = lib.rdm_build_pyramid_bytes(n0, ctypes.byref(cfg)), lib.rdm_build_pyramid_workspace(n0, ctypes.byref(cfg))
+        buf = torch.empty(int(ob), dtype=torch.uint8, device=points.device)
+        ws = torch.empty(int(wb), dtype=torch.uint8, device=points.device)
+        with torch.cuda.device(points.device):
+            L.call("rdm_build_pyramid_begin", self.handle, L.ptr(points), L.ptr(lengths), n0, ctypes.byref(cfg), L.ptr(buf), int(ob),
+                   L.ptr(ws), int(wb), L.stream())
+        self._live = (points, lengths, buf, ws, num_stages, batch)
+
+    def finish(self):
+        """Waits (host) for the stage sizes, queues every radius search on the current stream -> GpuPyramid."""
+        points, lengths, buf, ws, num_stages, batch = self._live
+        self._live = None
+        desc = L.PyramidDesc()
+        h_len = (ctypes.c_int64 * (num_stages * batch))()
+        h_dl = (ctypes.c_void_p * 8)()
+        with torch.cuda.device(points.device):
+            L.call("rdm_build_pyramid_finish", self.handle, ctypes.byref(desc), ctypes.cast(h_len, ctypes.c_void_p),
+                   ctypes.cast(h_dl, ctypes.c_void_p), L.stream())
+        host = [[int(h_len[s * batch + b]) for b in range(batch)] for s in range(num_stages)]
+        gp = GpuPyramid(buf, desc, host, [int(h_dl[s]) for s in range(num_stages)], points, batch)
+        gp._keep = (lengths, ws)
+        return gp
+
+
+_DEFAULT_JOB = None
+
+
 def build_pyramid_gpu(points, lengths, num_stages, voxel_size, radius, neighbor_limits, skip_unused=True,
                       up_nearest_only=True):
-    """geotransformer/utils/data.py:13-77 through rdm_build_pyramid: one host call, one synchronisation, int32 tables of
-    fixed width = the neighbour limit, plus a cell-sorted query order per stage for the KPConv gather."""
-    points = points.contiguous()
-    n0, batch = points.shape[0], lengths.shape[0]
-    cfg = L.PyramidCfg()
-    cfg.num_stages, cfg.batch, cfg.first_voxel, cfg.first_radius = num_stages, batch, voxel_size * 2, radius
-    for i, v in enumerate(neighbor_limits):
-        cfg.limits[i] = int(v)
-    cfg.skip_up0, cfg.up_nearest_only = int(skip_unused), int(up_nearest_only)
-    lib = L.lib()
-    ob, wb = lib.rdm_build_pyramid_bytes(n0, ctypes.byref(cfg)), lib.rdm_build_pyramid_workspace(n0, ctypes.byref(cfg))
-    buf = torch.empty(int(ob), dtype=torch.uint8, device=points.device)
-    ws = torch.empty(int(wb), dtype=torch.uint8, device=points.device)
-    desc = L.PyramidDesc()
-    h_len = (ctypes.c_int64 * (num_stages * batch))()
-    h_dl = (ctypes.c_void_p * 8)()
-    with torch.cuda.device(points.device):
-        L.call("rdm_build_pyramid", L.ptr(points), L.ptr(lengths), n0, ctypes.byref(cfg), L.ptr(buf), int(ob), L.ptr(ws), int(wb),
-               ctypes.byref(desc), ctypes.cast(h_len, ctypes.c_void_p), ctypes.cast(h_dl, ctypes.c_void_p), L.stream())
-    host = [[int(h_len[s * batch + b]) for b in range(batch)] for s in range(num_stages)]
-    return GpuPyramid(buf, desc, host, [int(h_dl[s]) for s in range(num_stages)], points, batch)
+    """geotransformer/utils/data.py:13-77 through rdm_build_pyramid: one synchronisation, int32 tables of fixed
+    width = the neighbour limit, plus a cell-sorted query order per stage for the KPConv gather."""
+    global _DEFAULT_JOB
+    if _DEFAULT_JOB is None:
+        _DEFAULT_JOB = PyramidJob()
+    _DEFAULT_JOB.begin(points, lengths, num_stages, voxel_size, radius, neighbor_limits, skip_unused, up_nearest_only)
+    return _DEFAULT_JOB.finish()
+
+
+class PairPipeline:
+    """Software pipeline over a stream of scan pairs: while pair i runs through the network on the main stream, the
+    voxel pyramid of pair i+1 is built on a side stream (what the reference's DataLoader workers do on CPU cores,
+    geotransformer/utils/data.py:223-253 with num_workers=8). Single host thread; results come out in input order and
+    are identical to model(data_dict) pair by pair."""
+
+    def __init__(self, model, device=None):
+        self.model = model
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.side = torch.cuda.Stream(self.device)
+        self.jobs = [PyramidJob(), PyramidJob()]
+
+    def _begin(self, item, slot):
+        points, lengths = item() if callable(item) else item  # a callable may stage host data (runs on the side stream)
+        b, cfg = self.model.cfg.backbone, self.model.cfg
+        self.jobs[slot].begin(points, lengths, b.num_stages, b.init_voxel_size, b.init_radius, cfg.neighbor_limits)
+
+    def _finish(self, slot):
+        gp = self.jobs[slot].finish()
+        ev = torch.cuda.Event()
+        ev.record(self.side)
+        return gp, ev
+
+    def run(self, items, before_step=None):
+        """items: iterable of (points (N,3) f32 cuda, lengths (2,) i64 cuda) or of callables returning such a tuple
+        (called under the side stream). Yields the model's output dict per pair. before_step(i), if given, runs on the
+        main stream right before pair i enters the network (bench.py: L2 flush + event record)."""
+        main = torch.cuda.current_stream(self.device)
+        it = iter(items)
+        first = next(it, None)
+        if first is None:
+            return
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            self._begin(first, 0)
+            cur = self._finish(0)
+        i = 0
+        while cur is not None:
+            gp, ready = cur
+            nxt_item = next(it, None)
+            if before_step is not None:
+                before_step(i)
+            main.wait_event(ready)
+            state = self.model.forward_head(None, gp=gp)  # asynchronous launches on the main stream
+            cur = None
+            if nxt_item is not None:
+                with torch.cuda.stream(self.side):
+                    self._begin(nxt_item, (i + 1) & 1)
+                    cur = self._finish((i + 1) & 1)  # host waits for the (short) subsampling chain only
+            yield self.model.forward_tail(state)
+            i += 1
 
 
 def _state_key(module):
@@ -478,12 +571,16 @@ class RDMNet(_Module):
         return out
 
     @torch.no_grad()
-    def forward(self, data_dict):
+    def forward_head(self, data_dict, gp=None):
+        """Pyramid (unless `gp`, a ready GpuPyramid, or a reference-style data_dict is given) + encoder + first
+        transformer + decoder: asynchronous launches only once the pyramid exists. Returns the state forward_tail needs."""
         out = {}
-        if "neighbors" not in data_dict:  # raw stacked points in: build the pyramid here, on the GPU
-            b = self.cfg.backbone
-            gp = build_pyramid_gpu(data_dict["points"], data_dict["lengths"], b.num_stages, b.init_voxel_size, b.init_radius,
-                                   self.cfg.neighbor_limits)
+        data_dict = data_dict if data_dict is not None else {}
+        if gp is not None or "neighbors" not in data_dict:  # raw stacked points in: build the pyramid here, on the GPU
+            if gp is None:
+                b = self.cfg.backbone
+                gp = build_pyramid_gpu(data_dict["points"], data_dict["lengths"], b.num_stages, b.init_voxel_size,
+                                       b.init_radius, self.cfg.neighbor_limits)
             S = gp.desc.num_stages
             L_host = gp.lengths_host
             points_c, points_f, points = gp.points(S - 1), gp.points(1), gp.points(0)
@@ -521,6 +618,14 @@ class RDMNet(_Module):
         ref_n2p, src_n2p = n2p[:nc], n2p[nc:]
         out["ref_feats_f"], out["src_feats_f"] = feats_f[:nf], feats_f[nf:]
 
+        return (out, data_dict, points_c, lengths_c, nc, tf, n2p, points_f, nf, feats_f, ref_points_f, src_points_f, ref_n2p,
+                src_n2p)
+
+    @torch.no_grad()
+    def forward_tail(self, state):
+        """Everything after the decoder (model_infer.py:180-354)."""
+        (out, data_dict, points_c, lengths_c, nc, tf, n2p, points_f, nf, feats_f, ref_points_f, src_points_f, ref_n2p,
+         src_n2p) = state
         if self.use_vote and not data_dict.get("stepwise", False):
             return self._match_tail(out, points_c.contiguous(), lengths_c, nc, tf, n2p, points_f.contiguous(), nf, feats_f)
         if self.use_vote:
@@ -571,6 +676,10 @@ class RDMNet(_Module):
         out["estimated_transform"] = T
         out["corr_patch_ij"] = bij
         return out
+
+
+    def forward(self, data_dict):
+        return self.forward_tail(self.forward_head(data_dict))
 
 
 def create_model(cfg=None):

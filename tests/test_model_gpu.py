@@ -157,3 +157,29 @@ def test_match_tail_runner_equals_stepwise_path(model, scans):
         close(fast[k], slow[k], tol, k)
     assert torch.equal(fast["ref_corr_points"], slow["ref_corr_points"]) and torch.equal(fast["src_corr_points"], slow["src_corr_points"])
     close(fast["estimated_transform_host"], fast["estimated_transform"].cpu(), 0.0, "pinned pose readback")
+
+
+def test_pair_pipeline_equals_sequential(model, scans):
+    """PairPipeline (pyramid of pair i+1 on a side stream during pair i) yields, in order, exactly model(data_dict)."""
+    from rdmnet_b200.model import PairPipeline
+    from rdmnet_b200.api import PairStreamRegistrar, PairRegistrar
+    names = [("s000000", "s000004"), ("s000000", "s000007"), ("s000004", "s000007"), ("s000007", "s000000")]
+    items = []
+    for a, b in names:
+        pts = torch.from_numpy(np.concatenate([scans[a], scans[b]])).cuda()
+        items.append((pts, torch.tensor([len(scans[a]), len(scans[b])], dtype=torch.int64).cuda()))
+    seq = [model({"points": p, "lengths": l}) for p, l in items]
+    outs = list(PairPipeline(model).run(items))
+    assert len(outs) == len(seq)
+    for o, s in zip(outs, seq):
+        for k in ("mask", "ref_node_corr_indices", "src_node_corr_indices", "ref_corr_points", "src_corr_points", "corr_scores",
+                  "estimated_transform", "ref_feats_c"):
+            assert torch.equal(o[k], s[k]), k
+    # host-buffer API: streaming form == one-pair form
+    host = [(scans[a], scans[b]) for a, b in names]
+    one = PairRegistrar(model, max_points=1 << 16)
+    want = [one.register(r, s) for r, s in host]
+    got = list(PairStreamRegistrar(model, max_points=1 << 16).register_stream(host))
+    for g, w in zip(got, want):
+        for k in w:
+            assert np.array_equal(g[k], w[k]), k
