@@ -297,6 +297,29 @@ int rdm_lgr(const float* matching_scores, int num_patches, int K, const float* r
             float* out_src_corr_points, float* out_corr_scores, int* out_corr_bij, float* out_transform, int* out_meta,
             void* workspace, size_t workspace_bytes, rdm_stream_t stream);
 
+/* ---- rdm_backbone_forward: Encoder + first ThDRoFormer + n2p score head + Decoder + p2p score head
+ * (experiments/model_infer.py:147-174) in ONE asynchronous host call; the encoder stage outputs live in the workspace.
+ * feats_c [n[top], c]: transformer output, ref rows first; feats_f [n[top - num_dec], ld_feats_f]: decoder output (its
+ * last real column is the p2p logit); n2p_scores [n[top]], p2p_scores [n[top - num_dec]]: clamp(sigmoid(logit), 0, 1). */
+typedef struct {
+  const rdm_block_desc* h_blocks;
+  int num_blocks, groups;
+  const rdm_thdroformer_desc* h_transformer1;
+  const float *n2p_w, *n2p_b; /* proj_n2p_score [1, c] */
+  const rdm_unary_desc* h_dec;
+  int num_dec;
+} rdm_backbone_desc;
+typedef struct {
+  float* feats_c;
+  float* n2p_scores;
+  float* feats_f;
+  int ld_feats_f;
+  float* p2p_scores;
+} rdm_backbone_out;
+size_t rdm_backbone_workspace(const rdm_backbone_desc* h_desc, const rdm_pyramid_desc* h_pyr, int nc_ref);
+int rdm_backbone_forward(const rdm_backbone_desc* h_desc, const rdm_pyramid_desc* h_pyr, int nc_ref, const float* in_feats,
+                         const rdm_backbone_out* h_out, void* workspace, size_t workspace_bytes, rdm_stream_t stream);
+
 /* ---- rdm_match_forward: everything RDMNet.forward does after the decoder (experiments/model_infer.py:180-354) in ONE
  * host call - Vote_layer + n2n score head, NMS (radius search + greedy rule), node selection, second ThDRoFormer,
  * L2 normalisation, both point_to_node partitions, SuperPointMatching, patch scores, Sinkhorn and

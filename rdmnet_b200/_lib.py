@@ -68,6 +68,8 @@ SIGNATURES = {
                                  c_int, c_float, c_void_p, c_void_p]),
     "rdm_sinkhorn": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                              c_float, c_void_p, c_void_p]),
+    "rdm_backbone_workspace": (c_size_t, [c_void_p, c_void_p, c_int]),
+    "rdm_backbone_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "rdm_match_workspace": (c_size_t, [c_void_p, c_int, c_int, c_int, c_int]),
     "rdm_match_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "rdm_weighted_procrustes": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
@@ -115,6 +117,16 @@ class ThdroformerDesc(ctypes.Structure):
     _fields_ = [("emb_w", c_void_p), ("emb_b", c_void_p), ("in_w", c_void_p), ("in_b", c_void_p), ("out_w", c_void_p),
                 ("out_b", c_void_p), ("layer_blobs", c_void_p * 32), ("is_self", c_int * 32), ("num_layers", c_int),
                 ("c_in", c_int), ("c_out", c_int)]
+
+
+class BackboneDesc(ctypes.Structure):
+    _fields_ = [("h_blocks", c_void_p), ("num_blocks", c_int), ("groups", c_int), ("h_transformer1", c_void_p),
+                ("n2p_w", c_void_p), ("n2p_b", c_void_p), ("h_dec", c_void_p), ("num_dec", c_int)]
+
+
+class BackboneOut(ctypes.Structure):
+    _fields_ = [("feats_c", c_void_p), ("n2p_scores", c_void_p), ("feats_f", c_void_p), ("ld_feats_f", c_int),
+                ("p2p_scores", c_void_p)]
 
 
 class MatchDesc(ctypes.Structure):

@@ -67,6 +67,9 @@ int rdm_gather_rows(const float* const* h_src, float* const* h_dst, const int* h
                     const int64_t* sel, int count, cudaStream_t stream);
 int rdm_l2_normalize(const float* x, float* y, int N, int C, cudaStream_t stream);
 
+int rdm_append_column(const float* x, const float* col, int N, int C, float* out, cudaStream_t stream);
+int rdm_sigmoid_column(const float* x, int ld, int N, float* y, cudaStream_t stream);
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -55,21 +55,18 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
-// w[k] = max(0, 1 - |d - kp_k| / sigma), k = 0..15 (w[15] = 0 through the dummy point), two kernel points per instruction.
-// Same roundings as the scalar form: every packed op is two IEEE round-to-nearest ops (kpconv.py:98-99).
+// w[k] = max(0, 1 - |d - kp_k| / sigma), k = 0..14, w[15] = 0 (kpconv.py:98-99). Scalar on purpose: the packed form
+// (add/mul/fma.rn.f32x2 over kernel-point pairs, 30 % fewer instructions) measured 7-15 % SLOWER on B200
+// (gpurun s4h vs s4g: C_in = 32 layer 64.3 -> 70.4 us) - the f32x2 ops with constant-bank operands need register
+// staging moves and run at half rate, and this phase is latency- not issue-bound.
 __device__ __forceinline__ void influences16(float dx, float dy, float dz, const KPts& kp, float inv_sigma, float (&w)[16]) {
-  const unsigned long long dx2 = pk2(dx, dx), dy2 = pk2(dy, dy), dz2 = pk2(dz, dz), one2 = pk2(1.f, 1.f),
-                           ninv2 = pk2(-inv_sigma, -inv_sigma);
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    const unsigned long long ex = add2(dx2, pk2(-kp.x[2 * k], -kp.x[2 * k + 1]));
-    const unsigned long long ey = add2(dy2, pk2(-kp.y[2 * k], -kp.y[2 * k + 1]));
-    const unsigned long long ez = add2(dz2, pk2(-kp.z[2 * k], -kp.z[2 * k + 1]));
-    const float2 dd = up2(fma2(ez, ez, fma2(ey, ey, mul2(ex, ex))));
-    const float2 ww = up2(fma2(pk2(sqrt_approx(dd.x), sqrt_approx(dd.y)), ninv2, one2));
-    w[2 * k] = fmaxf(ww.x, 0.f);
-    w[2 * k + 1] = fmaxf(ww.y, 0.f);
+  for (int k = 0; k < KP_K; k++) {
+    const float ex = dx - kp.x[k], ey = dy - kp.y[k], ez = dz - kp.z[k];
+    const float d = sqrt_approx(fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
+    w[k] = fmaxf(0.f, fmaf(-d, inv_sigma, 1.f));
   }
+  w[15] = 0.f;
 }
 
 // C_in == 1 (encoder1_1): 8 lanes per query (4 queries per warp), lanes stride over the neighbour list; the 15

@@ -882,3 +882,31 @@ int rdm_l2_normalize(const float* x, float* y, int N, int C, cudaStream_t stream
   RDM_LAUNCH_CHECK();
   return RDM_OK;
 }
+
+// out[r, :C] = x[r, :C]; out[r, C] = col[r]   (torch.cat([feats_c, n2p_logit], 1), experiments/model.py:166-167)
+__global__ void append_column_kernel(const float* __restrict__ x, const float* __restrict__ col, int N, int C,
+                                     float* __restrict__ out) {
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= (long long)N * (C + 1)) return;
+  const int r = (int)(e / (C + 1)), c = (int)(e - (long long)r * (C + 1));
+  out[e] = c < C ? x[(size_t)r * C + c] : col[r];
+}
+int rdm_append_column(const float* x, const float* col, int N, int C, float* out, cudaStream_t stream) {
+  if (N == 0) return RDM_OK;
+  append_column_kernel<<<cdiv((long long)N * (C + 1), 256), 256, 0, stream>>>(x, col, N, C, out);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
+// y[r] = clamp(sigmoid(x[r * ld]), 0, 1): score head on a strided column (the p2p logit = last decoder column)
+__global__ void sigmoid_column_kernel(const float* __restrict__ x, int ld, int N, float* __restrict__ y) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const float v = 1.f / (1.f + expf(-x[(size_t)r * ld]));
+  y[r] = fminf(fmaxf(v, 0.f), 1.f);
+}
+int rdm_sigmoid_column(const float* x, int ld, int N, float* y, cudaStream_t stream) {
+  if (N == 0) return RDM_OK;
+  sigmoid_column_kernel<<<cdiv(N, 256), 256, 0, stream>>>(x, ld, N, y);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}

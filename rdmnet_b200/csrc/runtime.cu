@@ -511,6 +511,62 @@ extern "C" int rdm_build_pyramid(const float* points, const int64_t* lengths, in
   return rdm_build_pyramid_finish(job, h_desc, h_lengths, h_d_lengths, stream);
 }
 
+// ------------------------------------------------------------------------------------------------ backbone runner
+namespace {
+int backbone_run(Arena& a, const rdm_backbone_desc& d, const rdm_pyramid_desc& p, int nc_ref, const float* in_feats,
+                 const rdm_backbone_out& o, cudaStream_t st) {
+  const int S = p.num_stages, top = S - 1;
+  const int nc = p.n[top], c = d.h_transformer1->c_out;
+  RDM_CHECK_ARG(nc_ref >= 1 && nc_ref < nc, "rdm_backbone_forward: both clouds need at least one coarse node");
+  float* enc_out[8] = {nullptr};
+  int last_c[8] = {0};
+  for (int i = 0; i < d.num_blocks; i++) last_c[d.h_blocks[i].stage] = d.h_blocks[i].c_out;
+  for (int s = 0; s < S; s++) enc_out[s] = a.f((size_t)p.n[s] * last_c[s]);
+  RDM_TRY(encoder_run(a, d.h_blocks, d.num_blocks, p, d.groups, in_feats, enc_out, st));
+  // first ThDRoFormer on the coarsest stage (model.py:154-159), n2p score head (:160-167)
+  const float* pc = p.points[top];
+  RDM_TRY(thdroformer_run(a, *d.h_transformer1, pc, nc_ref, pc + 3 * (size_t)nc_ref, nc - nc_ref, enc_out[top], last_c[top],
+                          enc_out[top] + (size_t)nc_ref * last_c[top], last_c[top], o.feats_c, o.feats_c + (size_t)nc_ref * c, st));
+  float* logit = a.f((size_t)nc);
+  float* cat = a.f((size_t)nc * (c + 1));
+  RDM_TRY(linear(a, o.feats_c, c, d.n2p_w, c, 1, d.n2p_b, logit, nc, 1, c, st));
+  if (!a.dry) {
+    RDM_TRY(rdm_activation(logit, o.n2p_scores, nc, 3, 0.f, st));
+    RDM_TRY(rdm_append_column(o.feats_c, logit, nc, c, cat, st));
+  }
+  // decoder (backbone.py:118-151) on [tf | n2p logit] and the encoder skips; last column = p2p logit (model.py:168-174)
+  const float* skips[8] = {nullptr};
+  for (int i = 0; i < d.num_dec; i++) skips[i] = enc_out[top - 1 - i];
+  RDM_TRY(decoder_run(a, d.h_dec, d.num_dec, p, top, d.groups, cat, c + 1, skips, o.feats_f, o.ld_feats_f, st));
+  if (!a.dry) {
+    const int s_out = top - d.num_dec, c_out = d.h_dec[d.num_dec - 1].c_out;
+    RDM_TRY(rdm_sigmoid_column(o.feats_f + (c_out - 1), o.ld_feats_f, p.n[s_out], o.p2p_scores, st));
+  }
+  return RDM_OK;
+}
+}  // namespace
+
+extern "C" size_t rdm_backbone_workspace(const rdm_backbone_desc* h_desc, const rdm_pyramid_desc* h_pyr, int nc_ref) {
+  Arena a(nullptr, 0, true);
+  rdm_backbone_out o = {};
+  if (backbone_run(a, *h_desc, *h_pyr, nc_ref, nullptr, o, 0) != RDM_OK) return 0;
+  return a.peak + 4096;
+}
+
+extern "C" int rdm_backbone_forward(const rdm_backbone_desc* h_desc, const rdm_pyramid_desc* h_pyr, int nc_ref,
+                                    const float* in_feats, const rdm_backbone_out* h_out, void* workspace, size_t workspace_bytes,
+                                    cudaStream_t stream) {
+  RDM_CHECK_ARG(h_desc && h_pyr && h_out && h_desc->h_blocks && h_desc->h_transformer1 && h_desc->h_dec && h_desc->num_dec >= 1,
+                "rdm_backbone_forward: null argument");
+  const size_t need = rdm_backbone_workspace(h_desc, h_pyr, nc_ref);
+  if (need == 0 || workspace_bytes < need) {
+    rdm_set_error("rdm_backbone_forward: workspace too small (%zu needed)", need);
+    return RDM_ERR_WORKSPACE;
+  }
+  Arena a(workspace, workspace_bytes, false);
+  return backbone_run(a, *h_desc, *h_pyr, nc_ref, in_feats, *h_out, stream);
+}
+
 // ------------------------------------------------------------------------------------------------ matching tail
 namespace {
 struct MatchPinned {

@@ -411,14 +411,19 @@ class Decoder(_Module):
         self.decoder3 = UnaryBlock(init_dim * 24, init_dim * 8, group_norm)
         self.decoder2 = LastUnaryBlock(init_dim * 12, output_dim + 1)
 
-    def forward(self, feats, data_dict, pyr=None):
-        """rdm_decoder_forward: three (nearest upsample || skip -> unary) levels in one host call. Returns [l2]."""
+    def unary_descs(self):
+        """rdm_unary_desc[3] = decoder4, decoder3, decoder2 (cached; see _Module)."""
         key = _state_key(self)
         if getattr(self, "_desc_key", None) != key:
             keep = []
             arr = (L.UnaryDesc * 3)(_unary_desc(self.decoder4, keep), _unary_desc(self.decoder3, keep),
                                     _unary_desc(self.decoder2, keep))
             self._descs, self._desc_keep, self._desc_key = arr, keep, key
+        return self._descs
+
+    def forward(self, feats, data_dict, pyr=None):
+        """rdm_decoder_forward: three (nearest upsample || skip -> unary) levels in one host call. Returns [l2]."""
+        self.unary_descs()
         if pyr is None:
             lh = data_dict.get("lengths_host") or [l.tolist() for l in data_dict["lengths"]]
             pyr = pyramid_desc(data_dict, lh)
@@ -489,6 +494,39 @@ class RDMNet(_Module):
         b = self.cfg.backbone
         return precompute_data_stack_mode(points.contiguous(), lengths, b.num_stages, b.init_voxel_size, b.init_radius,
                                           self.cfg.neighbor_limits, index_dtype=torch.int32, skip_unused=True)
+
+    def _backbone(self, desc, nc_ref, feats):
+        """rdm_backbone_forward: encoder + transformer 1 + n2p head + decoder + p2p head, one asynchronous host call.
+        Returns (tf (nc, 256), n2p (nc,), dec (nf, 257) view with row stride 260, p2p (nf,))."""
+        key = cache_key(self)
+        if getattr(self, "_bdesc_key", None) != key:
+            blocks, dec, t1 = self.encoder._block_descs(), self.decoder.unary_descs(), self.transformer.runner_desc()
+            d = L.BackboneDesc()
+            d.h_blocks, d.num_blocks, d.groups = ctypes.addressof(blocks), len(blocks), self.encoder.encoder1_1.norm.num_groups
+            d.h_transformer1 = ctypes.addressof(t1)
+            d.n2p_w, d.n2p_b = _p(self.proj_n2p_score.weight), _p(self.proj_n2p_score.bias)
+            d.h_dec, d.num_dec = ctypes.addressof(dec), 3
+            self._bdesc, self._bdesc_keep, self._bdesc_key = d, (blocks, dec, t1), key
+        d = self._bdesc
+        dev = feats.device
+        S = desc.num_stages
+        nc, nf = desc.n[S - 1], desc.n[S - 1 - d.num_dec]
+        c, c_out = self.transformer.out_proj.out_features, self.decoder.decoder2.out_channels
+        ld = (c_out + 3) // 4 * 4
+        tf = torch.empty((nc, c), dtype=torch.float32, device=dev)
+        n2p = torch.empty(nc, dtype=torch.float32, device=dev)
+        dec_full = torch.empty((nf, ld), dtype=torch.float32, device=dev)
+        p2p = torch.empty(nf, dtype=torch.float32, device=dev)
+        o = L.BackboneOut(tf.data_ptr(), n2p.data_ptr(), dec_full.data_ptr(), ld, p2p.data_ptr())
+        lib = L.lib()
+        wsb = int(lib.rdm_backbone_workspace(ctypes.byref(d), ctypes.byref(desc), nc_ref))
+        if wsb == 0:
+            raise RuntimeError("rdm_backbone_workspace failed: " + lib.rdm_last_error().decode())
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            L.call("rdm_backbone_forward", ctypes.byref(d), ctypes.byref(desc), nc_ref, L.ptr(feats.contiguous()), ctypes.byref(o),
+                   L.ptr(ws), wsb, L.stream())
+        return tf, n2p, dec_full[:, :c_out], p2p
 
     def _match_desc(self):
         """rdm_match_desc over this model's vote / score / transformer2 / matching parameters (cached; see _Module)."""
@@ -603,17 +641,20 @@ class RDMNet(_Module):
         out["ref_points_f"], out["src_points_f"] = ref_points_f, src_points_f
         out["ref_points"], out["src_points"] = points[:n0], points[n0:]
 
-        feats_list = self.encoder(feats, data_dict, pyr)
-        feats_c = feats_list[-1]
-        ref_feats_c, src_feats_c = self.transformer(points_c[:nc].contiguous(), points_c[nc:].contiguous(),
-                                                    feats_c[:nc], feats_c[nc:])
-        tf = torch.cat([ref_feats_c, src_feats_c], 0)
-        n2p_logit = ops.linear(tf, self.proj_n2p_score.weight, self.proj_n2p_score.bias)  # (Nc,1)
-        n2p = ops.activation(n2p_logit.view(-1), 3)
-        feats_list[-1] = torch.cat([tf, n2p_logit], 1)
-        dec = self.decoder(feats_list, data_dict, pyr)[0]
+        if data_dict.get("stepwise", False):  # per-module host calls (kept for the module-level parity tests)
+            feats_list = self.encoder(feats, data_dict, pyr)
+            feats_c = feats_list[-1]
+            ref_feats_c, src_feats_c = self.transformer(points_c[:nc].contiguous(), points_c[nc:].contiguous(),
+                                                        feats_c[:nc], feats_c[nc:])
+            tf = torch.cat([ref_feats_c, src_feats_c], 0)
+            n2p_logit = ops.linear(tf, self.proj_n2p_score.weight, self.proj_n2p_score.bias)  # (Nc,1)
+            n2p = ops.activation(n2p_logit.view(-1), 3)
+            feats_list[-1] = torch.cat([tf, n2p_logit], 1)
+            dec = self.decoder(feats_list, data_dict, pyr)[0]
+            p2p = ops.activation(dec[:, -1].contiguous(), 3)
+        else:
+            tf, n2p, dec, p2p = self._backbone(pyr[0], nc, feats)
         feats_f = dec[:, :-1]  # strided view (row stride 260): no copy of the 16 MB feature table
-        p2p = ops.activation(dec[:, -1].contiguous(), 3)
         out["ref_p2p_scores_c"], out["src_p2p_scores_c"] = p2p[:nf], p2p[nf:]
         ref_n2p, src_n2p = n2p[:nc], n2p[nc:]
         out["ref_feats_f"], out["src_feats_f"] = feats_f[:nf], feats_f[nf:]
