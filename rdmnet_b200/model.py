@@ -592,7 +592,7 @@ class RDMNet(_Module):
             L.call("rdm_match_forward", ctypes.byref(d), ctypes.byref(io), ctypes.byref(res), L.ptr(ws), wsb, L.stream())
         n0, n1, k, ncorr = res.n_ref_sel, res.n_src_sel, res.num_patches, res.num_corr
         out["shifted_ref_points_c"], out["shifted_src_points_c"] = B["shifted"][:nc_ref], B["shifted"][nc_ref:]
-        out["mask"] = B["mask"].bool()
+        out["mask"] = B["mask"].view(torch.bool)  # 0/1 bytes reinterpreted: no conversion kernel
         out["ref_points_c"], out["src_points_c"] = B["sel_points"][:n0], B["sel_points"][n0:n0 + n1]
         out["ref_feats_c"], out["src_feats_c"] = B["sel_feats"][:n0], B["sel_feats"][n0:n0 + n1]
         out["ref_n2p_scores_c"], out["src_n2p_scores_c"] = B["sel_n2p"][:n0], B["sel_n2p"][n0:n0 + n1]
@@ -600,7 +600,8 @@ class RDMNet(_Module):
         out["ref_node_corr_indices"], out["src_node_corr_indices"] = B["corr_ref"][:k], B["corr_src"][:k]
         out["node_corr_scores"] = B["corr_sc"][:k]
         out["ref_node_knn_indices"], out["src_node_knn_indices"] = B["knn"][:n0], B["knn"][n0:n0 + n1]
-        out["ref_node_knn_masks"], out["src_node_knn_masks"] = B["knn_masks"][:n0].bool(), B["knn_masks"][n0:n0 + n1].bool()
+        km = B["knn_masks"].view(torch.bool)
+        out["ref_node_knn_masks"], out["src_node_knn_masks"] = km[:n0], km[n0:n0 + n1]
         out["matching_scores"] = B["ms"][:k]
         out["ref_corr_points"], out["src_corr_points"], out["corr_scores"] = B["rcp"][:ncorr], B["scp"][:ncorr], B["cs"][:ncorr]
         out["corr_patch_ij"] = B["bij"][:ncorr]
