@@ -1,5 +1,6 @@
 // Error reporting + version for librdm_sm100.so.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <vector>
 #include "common.cuh"
 #include "../../include/rdm_sm100.h"
@@ -15,6 +16,15 @@ void rdm_set_error(const char* fmt, ...) {
 
 extern "C" const char* rdm_last_error(void) { return g_err; }
 extern "C" int rdm_version(void) { return 101; }
+
+bool rdm_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("RDM_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
 
 unsigned long long g_rdm_launches = 0;
 extern "C" unsigned long long rdm_launch_count(void) { return __atomic_load_n(&g_rdm_launches, __ATOMIC_RELAXED); }

@@ -36,6 +36,32 @@ extern unsigned long long g_rdm_launches;
     RDM_CUDA(cudaGetLastError());                               \
   } while (0)
 
+// ---- programmatic dependent launch (PDL). Kernels of the long launch chains (encoder / decoder / transformer) start
+// with pdl_trigger() - "my dependents may be scheduled as soon as every CTA of mine has started" - and call pdl_wait()
+// before their first access to memory a predecessor may still be using; constant data (weights) may be touched before
+// it. Launched through rdm_launch_pdl (programmatic stream serialization), the next kernel's CTAs are resident and past
+// their prologue when the current grid drains, which hides the ~2 us launch gap per kernel boundary. Kernels launched
+// the ordinary way are unaffected (the two instructions are no-ops there). RDM_PDL=0 disables the attribute.
+bool rdm_pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t rdm_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = rdm_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // optional kernel timing (api.cu); id < 0 = profiling off
 int rdm_prof_begin(int tag, int m, int n, int h, int c, cudaStream_t stream);
 void rdm_prof_end(int id, cudaStream_t stream);

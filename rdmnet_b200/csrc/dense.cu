@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
                                                     int ldb, const float* __restrict__ bias, float* __restrict__ C,
                                                     int ldc, int M, int N, int K, int k_per_split, int vecA, int vecB,
                                                     int vecC, int act) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int TM = BM / 16, TN = BN / 16;  // 8x8 (128 tile) or 4x4 (64 tile)
   constexpr int PAD = 4;
   __shared__ __align__(16) float As[2][GEMM_BK][BM + PAD];
@@ -182,6 +184,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, const float* __restrict__ bias,
                                      float* __restrict__ C, int ldc, int M, int N, int act) {
+  pdl_trigger();
+  pdl_wait();
   long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (e >= (long long)M * N) return;
   int m = (int)(e / N), n = (int)(e - (long long)m * N);
@@ -201,6 +205,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_stats_kernel(const float* _
                                                                   const float* __restrict__ bias, float* __restrict__ C,
                                                                   int ldc, int M, int N, double* __restrict__ stats,
                                                                   int cpg, int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_s[8][32], s_q[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + lane, r0 = blockIdx.y * rows_per_block;
@@ -279,11 +285,12 @@ int rdm_linear_gn(const float* A, int lda, const float* B, int ldb, int b_is_nk,
       if (gn_stats != nullptr && act == 0 && N % 32 == 0 && pow2) {
         int rpb = 64;  // rows per block: small problems get more, shorter blocks (the pass is latency-bound)
         while (rpb > 8 && (long long)(N / 32) * cdiv(M, rpb) < 296) rpb >>= 1;
-        splitk_reduce_stats_kernel<<<dim3(N / 32, cdiv(M, rpb)), 256, 0, stream>>>((const float*)workspace, tc_splits, bias, C,
-                                                                                    ldc, M, N, gn_stats, gn_cpg, rpb);
+        RDM_CUDA(rdm_launch_pdl(splitk_reduce_stats_kernel, dim3(N / 32, cdiv(M, rpb)), dim3(256), 0, stream, (const float*)workspace,
+                                tc_splits, bias, C, ldc, M, N, gn_stats, gn_cpg, rpb));
         if (stats_fused) *stats_fused = 1;
       } else {
-        splitk_reduce_kernel<<<cdiv((long long)M * N, 256), 256, 0, stream>>>((const float*)workspace, tc_splits, bias, C, ldc, M, N, act);
+        RDM_CUDA(rdm_launch_pdl(splitk_reduce_kernel, dim3(cdiv((long long)M * N, 256)), dim3(256), 0, stream, (const float*)workspace,
+                                tc_splits, bias, C, ldc, M, N, act));
       }
       RDM_LAUNCH_CHECK();
     }
@@ -328,6 +335,8 @@ int rdm_linear_gn(const float* A, int lda, const float* B, int ldb, int b_is_nk,
 // stats[g] = {sum, sumsq} (double) over rows x (C/G) channels of group g.
 __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const float* __restrict__ x, int N, int C, int G,
                                                               int rows_per_cta, double* __restrict__ stats) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_part[];  // [2*C]
   const int tid = threadIdx.x;
   const int r0 = blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
@@ -361,6 +370,8 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float* __res
                                                               const float* __restrict__ beta,
                                                               const float* __restrict__ res, float* __restrict__ y, int N,
                                                               int C, int G, float eps, int act, float slope) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_ms[];  // mean[G], rstd[G]
   const int tid = threadIdx.x;
   const int cpg = C / G;
@@ -393,6 +404,8 @@ __global__ void __launch_bounds__(256) groupnorm_apply_vec_kernel(const float* _
                                                                   const float* __restrict__ res, float* __restrict__ y, int N, int C,
                                                                   int G, float eps, int act, float slope,
                                                                   unsigned char* __restrict__ rowpos) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_par[];  // mean[C], scale[C], beta[C]
   float *s_mean = s_par, *s_scale = s_par + C, *s_beta = s_par + 2 * C;
   const int tid = threadIdx.x, cpg = C / G;
@@ -460,9 +473,9 @@ int rdm_groupnorm_apply(const float* x, const double* stats, const float* gamma,
     const long long warps_needed = cdiv(N, rpw);
     const int grid = (int)min((long long)148 * 4, (warps_needed + 7) / 8);
     const size_t smem = 3 * (size_t)C * sizeof(float);
-#define GN_APPLY(LPRv)                                                                                               \
-  groupnorm_apply_vec_kernel<LPRv><<<grid, 256, smem, stream>>>(x, stats, gamma, beta, residual, y, N, C, groups, eps, act, \
-                                                                slope, rowpos_out)
+#define GN_APPLY(LPRv)                                                                                                     \
+  RDM_CUDA(rdm_launch_pdl(groupnorm_apply_vec_kernel<LPRv>, dim3(grid), dim3(256), smem, stream, x, stats, gamma, beta, residual, y, N, \
+                          C, groups, eps, act, slope, rowpos_out))
     if (lpr == 8) GN_APPLY(8);
     else if (lpr == 16) GN_APPLY(16);
     else GN_APPLY(32);
@@ -495,6 +508,8 @@ extern "C" int rdm_groupnorm(const float* x, const float* gamma, const float* be
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float* __restrict__ y, int N, int C, float eps, int act) {
+  pdl_trigger();
+  pdl_wait();
   int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= N) return;
   const float* xr = x + (size_t)row * C;

@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const __grid
   const int nk = min(kb_per_split, nk_total - kb0);
   if (gridDim.z > 1) C += (size_t)blockIdx.z * M * N;
 
+  pdl_trigger();
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");  // hide the descriptor fetch behind the set-up
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const __grid
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = sm.tmem_base;
   if (threadIdx.x == 0) TC_STAMP(1);
+  pdl_wait();  // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -353,7 +355,8 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, f
     attr = true;
   }
   dim3 grid(cdiv(N, BN), cdiv(M, TC_BM), splits);
-  gemm_tf32x3_kernel<BN, STAGES><<<grid, TC_THREADS, smem, stream>>>(ma, mb, bias, C, ldc, M, N, K, act, kb_per_split, gn_stats, gn_cpg, dbg);
+  RDM_CUDA(rdm_launch_pdl(gemm_tf32x3_kernel<BN, STAGES>, grid, dim3(TC_THREADS), smem, stream, ma, mb, bias, C, ldc, M, N, K, act,
+                          kb_per_split, gn_stats, gn_cpg, dbg));
   RDM_LAUNCH_CHECK();
   __atomic_fetch_add(&g_tc_launches, 1ull, __ATOMIC_RELAXED);
   return RDM_OK;

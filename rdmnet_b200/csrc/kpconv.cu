@@ -16,6 +16,8 @@
 
 // flag[n] = (sum_c F[n,c] > 0)   (kpconv.py:113-114)
 __global__ void row_positive_kernel(const float* __restrict__ f, int n, int c, unsigned char* __restrict__ flag) {
+  pdl_trigger();
+  pdl_wait();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= n) return;
   float s = 0.f;
@@ -78,6 +80,8 @@ __global__ void __launch_bounds__(256) kpconv_gather_c1_kernel(const float* __re
                                                                const IdxT* __restrict__ idx, const KPts kp,
                                                                float inv_sigma, int M, int N, int H,
                                                                const int* __restrict__ order, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, t = lane & 7;
   const int mi = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4 + (lane >> 3);
   const bool qvalid = mi < M;
@@ -445,6 +449,8 @@ __global__ void __launch_bounds__(128, 4) kpconv_gather_v4_kernel(const float* _
                                                                   float inv_sigma, int M, int N, int H, int C, int NS,
                                                                   const int* __restrict__ order,
                                                                   float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int G = 32 / L;
   constexpr int STEP = SPLIT ? 32 : L;  // neighbour slots per chunk (per query)
   constexpr int HALF = L / 2;
@@ -581,8 +587,8 @@ static int launch_v4(long long warps, const float* feats, const unsigned char* r
     RDM_CUDA(cudaFuncSetAttribute(kpconv_gather_v4_kernel<L, SPLIT, IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  kpconv_gather_v4_kernel<L, SPLIT, IdxT><<<cdiv(warps, 4), 128, smem, stream>>>(feats, rowpos, q, s, idx, kp, inv_sigma, M, N, H,
-                                                                                 C, NS, order, out);
+  RDM_CUDA(rdm_launch_pdl(kpconv_gather_v4_kernel<L, SPLIT, IdxT>, dim3(cdiv(warps, 4)), dim3(128), smem, stream, feats, rowpos, q, s,
+                          idx, kp, inv_sigma, M, N, H, C, NS, order, out));
   RDM_LAUNCH_CHECK();
   return RDM_OK;
 }
@@ -601,7 +607,8 @@ static int launch_gather(const float* feats, const unsigned char* rowpos, const 
   kp.x[15] = kp.y[15] = kp.z[15] = 1.0e6f;  // dummy 16th point: |d - kp| / sigma >> 1 -> influence exactly 0
   const float inv_sigma = 1.f / sigma;
   if (C == 1) {
-    kpconv_gather_c1_kernel<IdxT><<<cdiv(M, 32), 256, 0, stream>>>(feats, q, s, idx, kp, inv_sigma, M, N, H, order, out);
+    RDM_CUDA(rdm_launch_pdl(kpconv_gather_c1_kernel<IdxT>, dim3(cdiv(M, 32)), dim3(256), 0, stream, feats, q, s, idx, kp, inv_sigma, M,
+                            N, H, order, out));
     RDM_LAUNCH_CHECK();
     return RDM_OK;
   }
@@ -741,6 +748,8 @@ int rdm_kpconv_gather_impl(const float* s_feats, const float* q_points, const fl
 template <typename IdxT>
 __global__ void maxpool_kernel(const float* __restrict__ f, const IdxT* __restrict__ idx, int M, int N, int H, int C,
                                float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   int cv = C >> 2;
   if (e >= (long long)M * cv) return;
@@ -766,9 +775,11 @@ extern "C" int rdm_maxpool(const float* feats, const void* neighbor_indices, int
   if (M == 0) return RDM_OK;
   long long total = (long long)M * (C / 4);
   if (index_bytes == 8)
-    maxpool_kernel<int64_t><<<cdiv(total, 256), 256, 0, stream>>>(feats, (const int64_t*)neighbor_indices, M, N, H, C, out);
+    RDM_CUDA(rdm_launch_pdl(maxpool_kernel<int64_t>, dim3(cdiv(total, 256)), dim3(256), 0, stream, feats,
+                            (const int64_t*)neighbor_indices, M, N, H, C, out));
   else
-    maxpool_kernel<int><<<cdiv(total, 256), 256, 0, stream>>>(feats, (const int*)neighbor_indices, M, N, H, C, out);
+    RDM_CUDA(rdm_launch_pdl(maxpool_kernel<int>, dim3(cdiv(total, 256)), dim3(256), 0, stream, feats, (const int*)neighbor_indices, M, N,
+                            H, C, out));
   RDM_LAUNCH_CHECK();
   return RDM_OK;
 }
@@ -778,6 +789,8 @@ template <typename IdxT>
 __global__ void upsample_concat_kernel(const float* __restrict__ f, const IdxT* __restrict__ idx, int idx_stride,
                                        const float* __restrict__ skip, int M, int N, int C1, int C2,
                                        float* __restrict__ out, int ld_out) {
+  pdl_trigger();
+  pdl_wait();
   long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   int C = C1 + C2;
   if (e >= (long long)M * ld_out) return;
@@ -808,11 +821,11 @@ int rdm_upsample_concat_ld(const float* feats, const void* upsample_indices, int
   if (M == 0) return RDM_OK;
   long long total = (long long)M * ld_out;
   if (index_bytes == 8)
-    upsample_concat_kernel<int64_t><<<cdiv(total, 256), 256, 0, stream>>>(feats, (const int64_t*)upsample_indices,
-                                                                         index_stride, skip, M, N, C1, C2, out, ld_out);
+    RDM_CUDA(rdm_launch_pdl(upsample_concat_kernel<int64_t>, dim3(cdiv(total, 256)), dim3(256), 0, stream, feats,
+                            (const int64_t*)upsample_indices, index_stride, skip, M, N, C1, C2, out, ld_out));
   else
-    upsample_concat_kernel<int><<<cdiv(total, 256), 256, 0, stream>>>(feats, (const int*)upsample_indices,
-                                                                     index_stride, skip, M, N, C1, C2, out, ld_out);
+    RDM_CUDA(rdm_launch_pdl(upsample_concat_kernel<int>, dim3(cdiv(total, 256)), dim3(256), 0, stream, feats,
+                            (const int*)upsample_indices, index_stride, skip, M, N, C1, C2, out, ld_out));
   RDM_LAUNCH_CHECK();
   return RDM_OK;
 }

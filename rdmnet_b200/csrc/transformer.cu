@@ -69,6 +69,8 @@ __device__ __forceinline__ void rowblock_gemv4(const float* __restrict__ WT, int
 // ------------------------------------------------------------------------------------------------ projection
 // grid (ceil(maxN/8), num_jobs), 256 threads: thread (o = tid & 127, rh = tid >> 7) -> output o of rows rh*4..rh*4+3.
 __global__ void __launch_bounds__(256) tf_project_kernel(const ProjJobs jobs) {
+  pdl_trigger();
+  pdl_wait();
   const rdm_tf_proj_job jb = jobs.j[blockIdx.y];
   const int n0 = blockIdx.x * TF_R;
   if (n0 >= jb.n) return;
@@ -114,7 +116,7 @@ extern "C" int rdm_tf_project(const rdm_tf_proj_job* h_jobs, int num_jobs, cudaS
     maxn = max(maxn, h_jobs[i].n);
   }
   if (maxn == 0) return RDM_OK;
-  tf_project_kernel<<<dim3(cdiv(maxn, TF_R), num_jobs), 256, 0, stream>>>(pj);
+  RDM_CUDA(rdm_launch_pdl(tf_project_kernel, dim3(cdiv(maxn, TF_R), num_jobs), dim3(256), 0, stream, pj));
   RDM_LAUNCH_CHECK();
   return RDM_OK;
 }
@@ -197,8 +199,10 @@ __global__ void __launch_bounds__(256) tf_attend_kernel(const AttnJobs jobs) {
   const int nvalid = min(TF_R, jb.nq - n0);
   const float scale = 0.17677669529663687f;  // 1/sqrt(32)
   const float* B = jb.blob;
+  pdl_trigger();
   stage_chunk(sm.W0, B + TFB_WO, tid);  // group 0: out-projection [128][128]
   stage_chunk(sm.W1, B + TFB_W1, tid);  // group 1: FFN expand, k = 0..63 of [128][256]
+  pdl_wait();  // the weight copies above touch constants only: they overlap the projection kernel still running
   for (int e = tid; e < TF_R * TF_D; e += 256) {
     int r = e >> 7, c = e & 127;
     sm.Qt[c * TF_R + r] = (r < nvalid) ? jb.q[(size_t)(n0 + r) * TF_D + c] * scale : 0.f;
@@ -351,7 +355,7 @@ extern "C" int rdm_tf_attend(const rdm_tf_attn_job* h_jobs, int num_jobs, cudaSt
     RDM_CUDA(cudaFuncSetAttribute(tf_attend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmem)));
     attr_set = true;
   }
-  tf_attend_kernel<<<dim3(cdiv(maxn, TF_R), num_jobs), 256, sizeof(AttnSmem), stream>>>(aj);
+  RDM_CUDA(rdm_launch_pdl(tf_attend_kernel, dim3(cdiv(maxn, TF_R), num_jobs), dim3(256), sizeof(AttnSmem), stream, aj));
   RDM_LAUNCH_CHECK();
   return RDM_OK;
 }
