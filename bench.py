@@ -68,38 +68,54 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe). The sampler
+    process is started BEFORE the warm-up (NVML start-up stalls the driver for tens of milliseconds - inside a ~150 ms
+    timed region that showed up as 2x outliers) and keeps polling; mark_begin()/stop() select the samples whose
+    timestamps fall inside the timed region."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.t0 = index, None, [], None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t1 = time.time()
+        time.sleep(0.12)  # let the sample that was being taken at t1 arrive
         self.proc.terminate()
         self.t.join(timeout=2)
+        t0 = self.t0 if self.t0 is not None else 0.0
+        inside = [ln for (t, ln) in self.lines if t0 <= t <= t1 + 0.12]
+        if not inside:  # region shorter than one polling period: take the sample nearest to it
+            inside = [min(self.lines, key=lambda x: abs(x[0] - t1))[1]] if self.lines else []
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
@@ -218,6 +234,8 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)
+    clocks.start()  # before the warm-up: see ClockSampler
     if pipelined:
         for _ in pipe.run(d_pairs[i % len(d_pairs)] for i in range(args.warmup)):
             pass
@@ -230,17 +248,18 @@ def run_ours(args, rank, world, local_rank):
     # Pipelined: while step i is in the network the pyramid of step i+1 is built on a side stream, so every timed step
     # contains exactly one pyramid build and one network pass; the events live on the main stream, which also waits
     # (inside the bracket) for the pyramid it consumes.
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    L.prof_enable(True)
+    L.prof_enable(os.environ.get("BENCH_NO_PROF", "0") != "1")  # debug knob: kernel-level event brackets off
+    no_flush = os.environ.get("BENCH_NO_FLUSH", "0") == "1"    # debug knob (the reported configuration always flushes)
     launches0 = L.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    clocks.mark_begin()
     t_wall0 = time.perf_counter()
     if pipelined:
         def before(i):
             if i < args.steps:
-                flush.fill_(i & 0xFF)
+                if not no_flush:
+                    flush.fill_(i & 0xFF)
                 ev[i][0].record()
         gen = pipe.run((d_pairs[i % len(d_pairs)] for i in range(args.steps + 1)), before_step=before)
         for i in range(args.steps):
@@ -338,6 +357,7 @@ def run_ours(args, rank, world, local_rank):
                        "pipeline": ("pair pipeline: pyramid of pair i+1 on a side stream during the network pass of pair i"
                                     if pipelined else "off: one pair at a time")},
             "wall_ms_per_step_incl_flush": wall_ms / args.steps,
+            "step_ms_stats": {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)), "max": float(np.max(step_ms))},
             "e2e": {"value": world * args.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": reg.h2d_bytes,
                     "d2h_bytes_per_step": reg.d2h_bytes, "ms_per_step": e2e_ms / args.steps,
                     "api": api_name},

@@ -215,7 +215,10 @@ class PairPipeline:
     def __init__(self, model, device=None):
         self.model = model
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.side = torch.cuda.Stream(self.device)
+        # high priority: the side stream's kernels are few and small, and the host waits on the first of them (the
+        # subsampling chain) before it can queue the rest of the pair in flight - they must not starve behind the
+        # network's large grids
+        self.side = torch.cuda.Stream(self.device, priority=-1)
         self.jobs = [PyramidJob(), PyramidJob()]
 
     def _begin(self, item, slot):
