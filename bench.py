@@ -81,7 +81,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -99,11 +99,11 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         t1 = time.time()
-        time.sleep(0.12)  # let the sample that was being taken at t1 arrive
+        time.sleep(0.22)  # let the sample that was being taken at t1 arrive
         self.proc.terminate()
         self.t.join(timeout=2)
         t0 = self.t0 if self.t0 is not None else 0.0
-        inside = [ln for (t, ln) in self.lines if t0 <= t <= t1 + 0.12]
+        inside = [ln for (t, ln) in self.lines if t0 <= t <= t1 + 0.22]
         if not inside:  # region shorter than one polling period: take the sample nearest to it
             inside = [min(self.lines, key=lambda x: abs(x[0] - t1))[1]] if self.lines else []
         sm, mx, reasons = [], [], set()

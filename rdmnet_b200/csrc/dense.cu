@@ -313,15 +313,19 @@ int rdm_linear_gn(const float* A, int lda, const float* B, int ldb, int b_is_nk,
   if (big) {
     dim3 grid(cdiv(N, 128), cdiv(M, 128), 1);
     if (b_is_nk)
-      sgemm_kernel<128, 128, true><<<grid, 256, 0, stream>>>(A, lda, B, ldb, bias, out, ldo, M, N, K, kps, vecA, vecB, vecO, act);
+      RDM_CUDA(rdm_launch_pdl(sgemm_kernel<128, 128, true>, grid, dim3(256), 0, stream, A, lda, B, ldb, bias, out, ldo, M, N, K, kps, vecA, vecB,
+                              vecO, act));
     else
-      sgemm_kernel<128, 128, false><<<grid, 256, 0, stream>>>(A, lda, B, ldb, bias, out, ldo, M, N, K, kps, vecA, vecB, vecO, act);
+      RDM_CUDA(rdm_launch_pdl(sgemm_kernel<128, 128, false>, grid, dim3(256), 0, stream, A, lda, B, ldb, bias, out, ldo, M, N, K, kps, vecA, vecB,
+                              vecO, act));
   } else {
     dim3 grid(cdiv(N, 64), cdiv(M, 64), splits);
     if (b_is_nk)
-      sgemm_kernel<64, 64, true><<<grid, 256, 0, stream>>>(A, lda, B, ldb, bias, out, ldo, M, N, K, kps, vecA, vecB, vecO, act);
+      RDM_CUDA(rdm_launch_pdl(sgemm_kernel<64, 64, true>, grid, dim3(256), 0, stream, A, lda, B, ldb, bias, out, ldo, M, N, K, kps, vecA, vecB,
+                              vecO, act));
     else
-      sgemm_kernel<64, 64, false><<<grid, 256, 0, stream>>>(A, lda, B, ldb, bias, out, ldo, M, N, K, kps, vecA, vecB, vecO, act);
+      RDM_CUDA(rdm_launch_pdl(sgemm_kernel<64, 64, false>, grid, dim3(256), 0, stream, A, lda, B, ldb, bias, out, ldo, M, N, K, kps, vecA, vecB,
+                              vecO, act));
   }
   RDM_LAUNCH_CHECK();
   if (splits > 1) {
@@ -457,7 +461,8 @@ int rdm_groupnorm_stats(const float* x, int N, int C, int groups, double* stats_
   if (N == 0) return RDM_OK;
   int rows = 64;
   while (rows > 4 && cdiv(N, rows) < 296) rows >>= 1;
-  groupnorm_stats_kernel<<<cdiv(N, rows), 256, 2 * C * sizeof(float), stream>>>(x, N, C, groups, rows, stats_zeroed);
+  RDM_CUDA(rdm_launch_pdl(groupnorm_stats_kernel, dim3(cdiv(N, rows)), dim3(256), 2 * C * sizeof(float), stream, x, N, C, groups, rows,
+                          stats_zeroed));
   RDM_LAUNCH_CHECK();
   return RDM_OK;
 }
@@ -534,7 +539,7 @@ extern "C" int rdm_layernorm(const float* x, const float* residual, const float*
                              int N, int C, float eps, int act, cudaStream_t stream) {
   RDM_CHECK_ARG(N >= 0 && C >= 1, "rdm_layernorm: bad shape");
   if (N == 0) return RDM_OK;
-  layernorm_kernel<<<cdiv(N, 8), 256, 0, stream>>>(x, residual, gamma, beta, y, N, C, eps, act);
+  RDM_CUDA(rdm_launch_pdl(layernorm_kernel, dim3(cdiv(N, 8)), dim3(256), 0, stream, x, residual, gamma, beta, y, N, C, eps, act));
   RDM_LAUNCH_CHECK();
   return RDM_OK;
 }
@@ -542,6 +547,8 @@ extern "C" int rdm_layernorm(const float* x, const float* residual, const float*
 // ------------------------------------------------------------------------------------------------- small elementwise
 // y = act(x): 1 LeakyReLU(slope), 2 ReLU, 3 sigmoid clamped to [0,1]
 __global__ void activation_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, int act, float slope) {
+  pdl_trigger();
+  pdl_wait();
   long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (e >= n) return;
   float v = x[e];

@@ -459,6 +459,8 @@ __global__ void __launch_bounds__(256) patch_scores_kernel(const float* __restri
                                                            const int64_t* __restrict__ ridx,
                                                            const int64_t* __restrict__ sidx, float scale,
                                                            float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) float As[2][16][PS_K + 4];
   __shared__ __align__(16) float Bs[2][16][PS_K + 4];
   __shared__ int s_ra[PS_K], s_rb[PS_K];
@@ -535,8 +537,8 @@ extern "C" int rdm_patch_scores(const float* ref_feats, int Nr, const float* src
   RDM_CHECK_ARG(ld_feats >= C && ld_feats % 4 == 0, "rdm_patch_scores: feature row stride must be a multiple of 4 floats");
   RDM_CHECK_ARG(((uintptr_t)ref_feats & 15) == 0 && ((uintptr_t)src_feats & 15) == 0, "rdm_patch_scores: unaligned features");
   if (num_patches == 0) return RDM_OK;
-  patch_scores_kernel<<<num_patches, 256, 0, stream>>>(ref_feats, Nr, src_feats, Ns, C, ld_feats, ref_knn_indices, src_knn_indices,
-                                                      ref_corr_indices, src_corr_indices, scale, out_scores);
+  RDM_CUDA(rdm_launch_pdl(patch_scores_kernel, dim3(num_patches), dim3(256), 0, stream, ref_feats, Nr, src_feats, Ns, C, ld_feats,
+                          ref_knn_indices, src_knn_indices, ref_corr_indices, src_corr_indices, scale, out_scores));
   RDM_LAUNCH_CHECK();
   return RDM_OK;
 }
@@ -686,6 +688,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sinkhorn128_kernel(const float*
                                                                    const int64_t* __restrict__ sidx,
                                                                    const float* __restrict__ alpha_ptr, int iters, float inf,
                                                                    float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) float us[4 * SK_LD], vs[4 * SK_LD];
   __shared__ float lmu[SK_N + 4], lnu[SK_N + 4];
   __shared__ short liveR[SK_N + 1], liveC[SK_N + 1], posR[SK_N + 1], posC[SK_N + 1];
@@ -770,8 +774,8 @@ extern "C" int rdm_sinkhorn(const float* scores, int num_patches, int R, int C, 
   RDM_CHECK_ARG(R >= 1 && C >= 1 && R <= 159 && C <= 159, "rdm_sinkhorn: patch size must be <= 159");
   if (num_patches == 0) return RDM_OK;
   if (R == SK_N && C == SK_N) {
-    sinkhorn128_kernel<<<num_patches, SK_THREADS, 0, stream>>>(scores, row_masks, col_masks, row_mask_gather, col_mask_gather,
-                                                               alpha, num_iterations, inf, out);
+    RDM_CUDA(rdm_launch_pdl(sinkhorn128_kernel, dim3(num_patches), dim3(SK_THREADS), 0, stream, scores, row_masks, col_masks,
+                            row_mask_gather, col_mask_gather, alpha, num_iterations, inf, out));
     RDM_LAUNCH_CHECK();
     return RDM_OK;
   }
@@ -793,6 +797,8 @@ __global__ void __launch_bounds__(256) vote_finish_kernel(const float* __restric
                                                           const float* __restrict__ feats, int ld_f, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float lx, float ly, float lz, float eps,
                                                           int N, int C, float* __restrict__ xyz_out, float* __restrict__ feat_out) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= N) return;
   const float* o = off + (size_t)r * ld_off;
@@ -827,8 +833,8 @@ int rdm_vote_finish(const float* off, int ld_off, const float* xyz, const float*
                     cudaStream_t stream) {
   RDM_CHECK_ARG(C >= 1 && C <= 1024, "rdm_vote_finish: C must be <= 1024");
   if (N == 0) return RDM_OK;
-  vote_finish_kernel<<<cdiv(N, 8), 256, 0, stream>>>(off, ld_off, xyz, feats, ld_f, gamma, beta, h_limit3[0], h_limit3[1],
-                                                     h_limit3[2], eps, N, C, xyz_out, feat_out);
+  RDM_CUDA(rdm_launch_pdl(vote_finish_kernel, dim3(cdiv(N, 8)), dim3(256), 0, stream, off, ld_off, xyz, feats, ld_f, gamma, beta,
+                          h_limit3[0], h_limit3[1], h_limit3[2], eps, N, C, xyz_out, feat_out));
   RDM_LAUNCH_CHECK();
   return RDM_OK;
 }
@@ -842,6 +848,8 @@ struct GatherJobs {
   int c[4], ld[4], n;
 };
 __global__ void __launch_bounds__(256) gather_rows_kernel(const GatherJobs jobs, const int64_t* __restrict__ sel, int count) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= count) return;
   const long long s = sel[r];
@@ -860,12 +868,14 @@ int rdm_gather_rows(const float* const* h_src, float* const* h_dst, const int* h
     g.c[i] = h_c[i];
     g.ld[i] = h_ld[i];
   }
-  gather_rows_kernel<<<cdiv(count, 8), 256, 0, stream>>>(g, sel, count);
+  RDM_CUDA(rdm_launch_pdl(gather_rows_kernel, dim3(cdiv(count, 8)), dim3(256), 0, stream, g, sel, count));
   RDM_LAUNCH_CHECK();
   return RDM_OK;
 }
 
 __global__ void __launch_bounds__(256) l2_normalize_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= N) return;
   float q = 0.f;
@@ -878,7 +888,7 @@ __global__ void __launch_bounds__(256) l2_normalize_kernel(const float* __restri
 }
 int rdm_l2_normalize(const float* x, float* y, int N, int C, cudaStream_t stream) {
   if (N == 0) return RDM_OK;
-  l2_normalize_kernel<<<cdiv(N, 8), 256, 0, stream>>>(x, y, N, C);
+  RDM_CUDA(rdm_launch_pdl(l2_normalize_kernel, dim3(cdiv(N, 8)), dim3(256), 0, stream, x, y, N, C));
   RDM_LAUNCH_CHECK();
   return RDM_OK;
 }
@@ -886,6 +896,8 @@ int rdm_l2_normalize(const float* x, float* y, int N, int C, cudaStream_t stream
 // out[r, :C] = x[r, :C]; out[r, C] = col[r]   (torch.cat([feats_c, n2p_logit], 1), experiments/model.py:166-167)
 __global__ void append_column_kernel(const float* __restrict__ x, const float* __restrict__ col, int N, int C,
                                      float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (e >= (long long)N * (C + 1)) return;
   const int r = (int)(e / (C + 1)), c = (int)(e - (long long)r * (C + 1));
@@ -893,12 +905,14 @@ __global__ void append_column_kernel(const float* __restrict__ x, const float* _
 }
 int rdm_append_column(const float* x, const float* col, int N, int C, float* out, cudaStream_t stream) {
   if (N == 0) return RDM_OK;
-  append_column_kernel<<<cdiv((long long)N * (C + 1), 256), 256, 0, stream>>>(x, col, N, C, out);
+  RDM_CUDA(rdm_launch_pdl(append_column_kernel, dim3(cdiv((long long)N * (C + 1), 256)), dim3(256), 0, stream, x, col, N, C, out));
   RDM_LAUNCH_CHECK();
   return RDM_OK;
 }
 // y[r] = clamp(sigmoid(x[r * ld]), 0, 1): score head on a strided column (the p2p logit = last decoder column)
 __global__ void sigmoid_column_kernel(const float* __restrict__ x, int ld, int N, float* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= N) return;
   const float v = 1.f / (1.f + expf(-x[(size_t)r * ld]));
@@ -906,7 +920,7 @@ __global__ void sigmoid_column_kernel(const float* __restrict__ x, int ld, int N
 }
 int rdm_sigmoid_column(const float* x, int ld, int N, float* y, cudaStream_t stream) {
   if (N == 0) return RDM_OK;
-  sigmoid_column_kernel<<<cdiv(N, 256), 256, 0, stream>>>(x, ld, N, y);
+  RDM_CUDA(rdm_launch_pdl(sigmoid_column_kernel, dim3(cdiv(N, 256)), dim3(256), 0, stream, x, ld, N, y));
   RDM_LAUNCH_CHECK();
   return RDM_OK;
 }

@@ -183,3 +183,26 @@ def test_pair_pipeline_equals_sequential(model, scans):
     for g, w in zip(got, want):
         for k in w:
             assert np.array_equal(g[k], w[k]), k
+
+
+@pytest.mark.parametrize("size_class", ["4k", "8k", "32k"])
+def test_forward_size_sweep_runners_equal_stepwise(model, size_class):
+    """Config-5 size classes (4k-32k points/scan): the runner path (pyramid + backbone + match runners) and the per-operator
+    path agree, and the pose is a rigid transform. Guards shape-dependent kernel choices (split/non-split gather, split-K
+    GEMMs, tile tails) away from the KITTI-sized pairs the other tests use."""
+    from rdmnet_b200 import synthetic
+    n_elev, n_azim = synthetic.SIZE_CLASSES[size_class]
+    p = synthetic.make_pair(pair_id=11, n_elev=n_elev, n_azim=n_azim)
+    pts = torch.from_numpy(np.concatenate([p["ref_points"], p["src_points"]])).cuda()
+    lens = torch.tensor([len(p["ref_points"]), len(p["src_points"])], dtype=torch.int64).cuda()
+    fast = model({"points": pts, "lengths": lens})
+    slow = model({"points": pts, "lengths": lens, "stepwise": True})
+    assert torch.equal(fast["mask"], slow["mask"])
+    assert torch.equal(fast["ref_node_corr_indices"], slow["ref_node_corr_indices"])
+    assert torch.equal(fast["ref_corr_points"], slow["ref_corr_points"])
+    close(fast["ref_feats_c"], slow["ref_feats_c"], 1e-5, "ref_feats_c")
+    close(fast["estimated_transform"], slow["estimated_transform"], 1e-5, "estimated_transform")
+    T = fast["estimated_transform"].cpu().double()
+    R = T[:3, :3]
+    assert torch.allclose(R @ R.T, torch.eye(3, dtype=torch.float64), atol=1e-4) and abs(torch.det(R).item() - 1) < 1e-4
+    assert torch.equal(T[3], torch.tensor([0, 0, 0, 1], dtype=torch.float64))
