@@ -68,58 +68,91 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe). The sampler
-    process is started BEFORE the warm-up (NVML start-up stalls the driver for tens of milliseconds - inside a ~150 ms
-    timed region that showed up as 2x outliers) and keeps polling; mark_begin()/stop() select the samples whose
-    timestamps fall inside the timed region."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe). Default source: NVML
+    in-process (the counters behind `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*`), polled
+    every 50 ms from a thread; BENCH_CLOCKS=smi runs the recipe's nvidia-smi -lms 200 process instead. The external
+    process was measured to stall the GPU work of this bench for 50-190 ms per poll often enough to turn one step in
+    ~100 into a 10-40x outlier (profiles/README.md), so it is the fallback. Started before the warm-up; mark_begin() /
+    stop() select the samples inside the timed region."""
     Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines, self.t0 = index, None, [], None
+        self.index, self.proc, self.samples, self.t0, self.mode, self._stop = index, None, [], None, None, False
 
     def start(self):
+        if os.environ.get("BENCH_CLOCKS", "nvml") != "smi":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                phys = int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[self.index]) if os.environ.get(
+                    "CUDA_VISIBLE_DEVICES", "").replace(",", "").isdigit() else self.index
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+                self.nv, self.mode = pynvml, "nvml"
+                self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+                self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+                self.t.start()
+                return
+            except Exception:
+                self.mode = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.mode = "smi"
+            self.t = threading.Thread(target=self._pump_smi, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.proc, self.mode = None, None
 
-    def _pump(self):
+    def _poll_nvml(self):
+        nv = self.nv
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        while not self._stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                self.samples.append((time.time(), sm, self.max_sm, [n for n, bit in names if mask & bit]))
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def _pump_smi(self):
         for ln in self.proc.stdout:
-            self.lines.append((time.time(), ln))
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm, mx = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            rs = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8])
+                  if v.lower().startswith("active")]
+            self.samples.append((time.time(), sm, mx, rs))
 
     def mark_begin(self):
         self.t0 = time.time()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampler unavailable"]}
         t1 = time.time()
-        time.sleep(0.22)  # let the sample that was being taken at t1 arrive
-        self.proc.terminate()
+        if self.mode == "smi":
+            time.sleep(0.22)  # let the sample that was being taken at t1 arrive
+            self.proc.terminate()
+        else:
+            self._stop = True
         self.t.join(timeout=2)
         t0 = self.t0 if self.t0 is not None else 0.0
-        inside = [ln for (t, ln) in self.lines if t0 <= t <= t1 + 0.22]
-        if not inside:  # region shorter than one polling period: take the sample nearest to it
-            inside = [min(self.lines, key=lambda x: abs(x[0] - t1))[1]] if self.lines else []
-        sm, mx, reasons = [], [], set()
-        for ln in inside:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        slack = 0.22 if self.mode == "smi" else 0.0
+        inside = [x for x in self.samples if t0 <= x[0] <= t1 + slack]
+        if not inside and self.samples:  # region shorter than one polling period: the sample nearest to it
+            inside = [min(self.samples, key=lambda x: abs(x[0] - t1))]
+        sm = [x[1] for x in inside]
+        reasons = sorted({r for x in inside for r in x[3]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(x[2] for x in inside) if inside else None,
+                "reasons": reasons, "samples": len(sm), "source": "nvml" if self.mode == "nvml" else "nvidia-smi -lms 200"}
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm

@@ -37,14 +37,26 @@ struct ProfRec {
   int tag, m, n, h, c;
 };
 std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_prof_pool;  // events are created when profiling is switched on, never inside a timed region
 bool g_prof_on = false;
+cudaEvent_t prof_take() {
+  if (g_prof_pool.empty()) {
+    cudaEvent_t e = nullptr;
+    return cudaEventCreate(&e) == cudaSuccess ? e : nullptr;
+  }
+  cudaEvent_t e = g_prof_pool.back();
+  g_prof_pool.pop_back();
+  return e;
+}
 }  // namespace
 
 int rdm_prof_begin(int tag, int m, int n, int h, int c, cudaStream_t stream) {
   if (!g_prof_on) return -1;
   ProfRec r;
   r.tag = tag; r.m = m; r.n = n; r.h = h; r.c = c;
-  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return -1;
+  r.e0 = prof_take();
+  r.e1 = prof_take();
+  if (r.e0 == nullptr || r.e1 == nullptr) return -1;
   cudaEventRecord(r.e0, stream);
   g_prof.push_back(r);
   return (int)g_prof.size() - 1;
@@ -55,11 +67,19 @@ void rdm_prof_end(int id, cudaStream_t stream) {
 }
 
 extern "C" void rdm_prof_enable(int on) {
-  for (auto& r : g_prof) {
-    cudaEventDestroy(r.e0);
-    cudaEventDestroy(r.e1);
+  for (auto& r : g_prof) {  // recycle
+    g_prof_pool.push_back(r.e0);
+    g_prof_pool.push_back(r.e1);
   }
   g_prof.clear();
+  g_prof.reserve(1 << 14);
+  if (on) {
+    while (g_prof_pool.size() < 8192) {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreate(&e) != cudaSuccess) break;
+      g_prof_pool.push_back(e);
+    }
+  }
   g_prof_on = on != 0;
 }
 
