@@ -217,7 +217,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------------- GPU arm
@@ -410,13 +410,28 @@ def run_ours(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu_baseline:
             cb, _, _ = cpu_arm(pairs, args.cpu_pairs, 1, budget_s=60.0)
             line["cpu_baseline"] = cb
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process' original stdout; everything else that libraries print to fd 1 (NCCL's
+    version banner under NCCL_DEBUG=VERSION, for instance) was redirected to stderr in main()."""
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
