@@ -45,7 +45,7 @@ typedef struct {
   float ms;
   int m, n, h, c;
 } rdm_prof_record;
-void rdm_prof_enable(int on);
+void rdm_prof_enable(int on); /* bit mask of the tags to bracket: 1 = gather, 2 = weight GEMM, 3 = both, 0 = off */
 int rdm_prof_read(rdm_prof_record* h_out, int max_records);
 
 /* ---- rdmnet.ext.grid_subsampling (geotransformer/extensions/cpu/grid_subsampling/grid_subsampling.cpp:5-62,

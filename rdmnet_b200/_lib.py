@@ -203,7 +203,7 @@ class ProfRecord(ctypes.Structure):
 
 def prof_enable(on):
     """In-library CUDA-event timing of the KPConv gather / weight-GEMM launches (rdm_prof_enable)."""
-    lib().rdm_prof_enable(1 if on else 0)
+    lib().rdm_prof_enable(int(on))  # bit mask: 1 = gather brackets, 2 = weight-GEMM brackets
 
 
 def prof_read(max_records=1 << 16):

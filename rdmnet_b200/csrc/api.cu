@@ -38,6 +38,7 @@ struct ProfRec {
 };
 std::vector<ProfRec> g_prof;
 std::vector<cudaEvent_t> g_prof_pool;  // events are created when profiling is switched on, never inside a timed region
+int g_prof_mask = 0;  // bit 0: KPConv gather brackets, bit 1: KPConv weight-GEMM brackets
 bool g_prof_on = false;
 cudaEvent_t prof_take() {
   if (g_prof_pool.empty()) {
@@ -51,7 +52,7 @@ cudaEvent_t prof_take() {
 }  // namespace
 
 int rdm_prof_begin(int tag, int m, int n, int h, int c, cudaStream_t stream) {
-  if (!g_prof_on) return -1;
+  if (!g_prof_on || !(g_prof_mask & (1 << (tag - 1)))) return -1;
   ProfRec r;
   r.tag = tag; r.m = m; r.n = n; r.h = h; r.c = c;
   r.e0 = prof_take();
@@ -81,6 +82,7 @@ extern "C" void rdm_prof_enable(int on) {
     }
   }
   g_prof_on = on != 0;
+  g_prof_mask = on;  // rdm_prof_enable(1): gather only; (3): gather + weight GEMM
 }
 
 extern "C" int rdm_prof_read(rdm_prof_record* out, int max_records) {

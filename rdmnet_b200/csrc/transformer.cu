@@ -67,22 +67,38 @@ __device__ __forceinline__ void rowblock_gemv4(const float* __restrict__ WT, int
 }
 
 // ------------------------------------------------------------------------------------------------ projection
+__device__ __forceinline__ void tfp_cp16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
 // grid (ceil(maxN/8), num_jobs), 256 threads: thread (o = tid & 127, rh = tid >> 7) -> output o of rows rh*4..rh*4+3.
+// The job's 64 KB weight matrix is copied to shared memory with cp.async BEFORE the programmatic-dependency wait (it is
+// constant data), i.e. while the previous kernel is still running; the multiply then reads it conflict-free.
 __global__ void __launch_bounds__(256) tf_project_kernel(const ProjJobs jobs) {
-  pdl_trigger();
-  pdl_wait();
+  extern __shared__ __align__(16) float tfp_smem[];  // W [128][128] k-major, then xt [128][8]
+  float* Ws = tfp_smem;
+  float* xt = tfp_smem + TF_D * TF_D;
   const rdm_tf_proj_job jb = jobs.j[blockIdx.y];
   const int n0 = blockIdx.x * TF_R;
+  pdl_trigger();
   if (n0 >= jb.n) return;
-  __shared__ __align__(16) float xt[TF_D * TF_R];
   const int tid = threadIdx.x, o = tid & 127, rh = tid >> 7;
+#pragma unroll
+  for (int i = 0; i < TF_D * TF_D / 4 / 256; i++) tfp_cp16(Ws + 4 * (tid + i * 256), jb.wt + 4 * (tid + i * 256));
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  pdl_wait();
   for (int e = tid; e < TF_R * TF_D; e += 256) {
     int r = e >> 7, c = e & 127;
     xt[c * TF_R + r] = (n0 + r < jb.n) ? jb.x[(size_t)(n0 + r) * jb.ldx + c] : 0.f;
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  rowblock_gemv4<TF_D>(jb.wt, TF_D, o, xt, rh * 4, acc);
+#pragma unroll 8
+  for (int k = 0; k < TF_D; k++) {
+    const float w = Ws[k * TF_D + o];
+    const float4 x = *(const float4*)(xt + k * TF_R + rh * 4);
+    acc[0] = fmaf(w, x.x, acc[0]); acc[1] = fmaf(w, x.y, acc[1]); acc[2] = fmaf(w, x.z, acc[2]); acc[3] = fmaf(w, x.w, acc[3]);
+  }
   const float b = jb.bias[o];
 #pragma unroll
   for (int i = 0; i < 4; i++) {
@@ -116,7 +132,13 @@ extern "C" int rdm_tf_project(const rdm_tf_proj_job* h_jobs, int num_jobs, cudaS
     maxn = max(maxn, h_jobs[i].n);
   }
   if (maxn == 0) return RDM_OK;
-  RDM_CUDA(rdm_launch_pdl(tf_project_kernel, dim3(cdiv(maxn, TF_R), num_jobs), dim3(256), 0, stream, pj));
+  const size_t smem = (size_t)(TF_D * TF_D + TF_D * TF_R) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RDM_CUDA(cudaFuncSetAttribute(tf_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  RDM_CUDA(rdm_launch_pdl(tf_project_kernel, dim3(cdiv(maxn, TF_R), num_jobs), dim3(256), smem, stream, pj));
   RDM_LAUNCH_CHECK();
   return RDM_OK;
 }
