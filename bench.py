@@ -69,8 +69,8 @@ def peaks():
 
 class ClockSampler:
     """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe). Default source: NVML
-    in-process (the counters behind `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*`), polled
-    every 50 ms from a thread; BENCH_CLOCKS=smi runs the recipe's nvidia-smi -lms 200 process instead. The external
+    in-process (the counters behind `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*`), sampled
+    synchronously between timed steps (sample_now); BENCH_CLOCKS=smi runs the recipe's nvidia-smi -lms 200 process instead. The external
     process was measured to stall the GPU work of this bench for 50-190 ms per poll often enough to turn one step in
     ~100 into a 10-40x outlier (profiles/README.md), so it is the fallback. Started before the warm-up; mark_begin() /
     stop() select the samples inside the timed region."""
@@ -90,8 +90,7 @@ class ClockSampler:
                 self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
                 self.nv, self.mode = pynvml, "nvml"
                 self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-                self.t = threading.Thread(target=self._poll_nvml, daemon=True)
-                self.t.start()
+                self.sample_now()
                 return
             except Exception:
                 self.mode = None
@@ -105,18 +104,21 @@ class ClockSampler:
         except Exception:
             self.proc, self.mode = None, None
 
-    def _poll_nvml(self):
+    def sample_now(self):
+        """NVML mode: one synchronous sample. bench.py calls it BETWEEN timed steps (every few steps, next to the L2 flush
+        and outside the per-step event brackets): a query perturbs the GPU work in flight for milliseconds, and between
+        steps the main stream is idle, so the observer effect stays out of the step times."""
+        if self.mode != "nvml":
+            return
         nv = self.nv
         names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
                  ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
-        while not self._stop:
-            try:
-                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                self.samples.append((time.time(), sm, self.max_sm, [n for n, bit in names if mask & bit]))
-            except Exception:
-                pass
-            time.sleep(0.05)
+        try:
+            sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            self.samples.append((time.time(), sm, self.max_sm, [n for n, bit in names if mask & bit]))
+        except Exception:
+            pass
 
     def _pump_smi(self):
         for ln in self.proc.stdout:
@@ -141,9 +143,7 @@ class ClockSampler:
         if self.mode == "smi":
             time.sleep(0.22)  # let the sample that was being taken at t1 arrive
             self.proc.terminate()
-        else:
-            self._stop = True
-        self.t.join(timeout=2)
+            self.t.join(timeout=2)
         t0 = self.t0 if self.t0 is not None else 0.0
         slack = 0.22 if self.mode == "smi" else 0.0
         inside = [x for x in self.samples if t0 <= x[0] <= t1 + slack]
@@ -293,6 +293,8 @@ def run_ours(args, rank, world, local_rank):
     if pipelined:
         def before(i):
             if i < args.steps:
+                if i % 6 == 3:
+                    clocks.sample_now()  # under load (the side stream is building the next pyramid), outside the brackets
                 if not no_flush:
                     flush.fill_(i & 0xFF)
                 ev[i][0].record()
@@ -307,6 +309,8 @@ def run_ours(args, rank, world, local_rank):
             pass
     else:
         for i in range(args.steps):
+            if i % 6 == 3:
+                clocks.sample_now()
             flush.fill_(i & 0xFF)
             ev[i][0].record()
             out = step(i)

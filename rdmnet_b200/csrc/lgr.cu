@@ -12,40 +12,43 @@
 
 // ------------------------------------------------------------------------------------------- 3x3 SVD -> rotation
 // R = V diag(1,1,sign det(V U^T)) U^T for H = U S V^T (procrustes.py:53-57). One-sided Jacobi in double.
-__device__ void rotation_from_H(const double Hin[9], float R[9]) {
+template <typename F>
+__device__ void rotation_from_H_t(const F Hin[9], float R[9]) {
+  const F tiny = sizeof(F) == 8 ? (F)1e-300 : (F)1e-30, conv = sizeof(F) == 8 ? (F)1e-15 : (F)2e-7,
+          rtol = sizeof(F) == 8 ? (F)1e-12 : (F)1e-6;
   // A = H (columns rotated until orthogonal): A = U S, accumulated right rotations = V
-  double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  F A[9], V[9] = {(F)1, (F)0, (F)0, (F)0, (F)1, (F)0, (F)0, (F)0, (F)1};
   for (int i = 0; i < 9; i++) A[i] = Hin[i];
   for (int sweep = 0; sweep < 30; sweep++) {
-    double off = 0.0;
+    F off = (F)0;
     for (int p = 0; p < 2; p++)
       for (int q = p + 1; q < 3; q++) {
-        double alpha = 0, beta = 0, gamma = 0;
+        F alpha = (F)0, beta = (F)0, gamma = (F)0;
         for (int r = 0; r < 3; r++) {
           alpha += A[3 * r + p] * A[3 * r + p];
           beta += A[3 * r + q] * A[3 * r + q];
           gamma += A[3 * r + p] * A[3 * r + q];
         }
-        off = fmax(off, fabs(gamma) / (sqrt(alpha * beta) + 1e-300));
-        if (fabs(gamma) < 1e-300) continue;
-        double zeta = (beta - alpha) / (2.0 * gamma);
-        double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        off = fmax((F)off, fabs((F)gamma) / (sqrt((F)alpha * beta) + tiny));
+        if (fabs((F)gamma) < tiny) continue;
+        F zeta = (beta - alpha) / ((F)2 * gamma);
+        F t = (zeta >= 0 ? (F)1 : (F)-1) / (fabs((F)zeta) + sqrt((F)(F)1 + zeta * zeta));
+        F c = (F)1 / sqrt((F)1 + t * t), s = c * t;
         for (int r = 0; r < 3; r++) {
-          double ap = A[3 * r + p], aq = A[3 * r + q];
+          F ap = A[3 * r + p], aq = A[3 * r + q];
           A[3 * r + p] = c * ap - s * aq;
           A[3 * r + q] = s * ap + c * aq;
-          double vp = V[3 * r + p], vq = V[3 * r + q];
+          F vp = V[3 * r + p], vq = V[3 * r + q];
           V[3 * r + p] = c * vp - s * vq;
           V[3 * r + q] = s * vp + c * vq;
         }
       }
-    if (off < 1e-15) break;
+    if (off < conv) break;
   }
   // singular values = column norms; sort descending (LAPACK order) so that the reflection fix hits the smallest
-  double sv[3];
+  F sv[3];
   int ord[3] = {0, 1, 2};
-  for (int j = 0; j < 3; j++) sv[j] = sqrt(A[j] * A[j] + A[3 + j] * A[3 + j] + A[6 + j] * A[6 + j]);
+  for (int j = 0; j < 3; j++) sv[j] = sqrt((F)A[j] * A[j] + A[3 + j] * A[3 + j] + A[6 + j] * A[6 + j]);
   for (int a = 0; a < 2; a++)
     for (int b = a + 1; b < 3; b++)
       if (sv[ord[b]] > sv[ord[a]]) {
@@ -53,13 +56,13 @@ __device__ void rotation_from_H(const double Hin[9], float R[9]) {
         ord[a] = ord[b];
         ord[b] = t;
       }
-  double U[9], Vs[9];
+  F U[9], Vs[9];
   for (int j = 0; j < 3; j++) {
     int c = ord[j];
     for (int r = 0; r < 3; r++) Vs[3 * r + j] = V[3 * r + c];
   }
   // U columns: normalised A columns; complete degenerate ones by cross products
-  double tol = 1e-12 * fmax(sv[ord[0]], 1e-300);
+  F tol = rtol * fmax((F)sv[ord[0]], tiny);
   int rank = 0;
   for (int j = 0; j < 3; j++) {
     int c = ord[j];
@@ -69,12 +72,12 @@ __device__ void rotation_from_H(const double Hin[9], float R[9]) {
     }
   }
   if (rank == 0) {
-    for (int i = 0; i < 9; i++) U[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    for (int i = 0; i < 9; i++) U[i] = (i % 4 == 0) ? (F)1 : (F)0;
   } else if (rank == 1) {
-    double x = U[0], y = U[3], z = U[6];
-    double ax = fabs(x) < 0.9 ? 1.0 : 0.0, ay = fabs(x) < 0.9 ? 0.0 : 1.0, az = 0.0;
-    double bx = y * az - z * ay, by = z * ax - x * az, bz = x * ay - y * ax;
-    double nb = sqrt(bx * bx + by * by + bz * bz);
+    F x = U[0], y = U[3], z = U[6];
+    F ax = fabs((F)x) < (F)0.9 ? (F)1 : (F)0, ay = fabs((F)x) < (F)0.9 ? (F)0 : (F)1, az = (F)0;
+    F bx = y * az - z * ay, by = z * ax - x * az, bz = x * ay - y * ax;
+    F nb = sqrt((F)bx * bx + by * by + bz * bz);
     U[1] = bx / nb; U[4] = by / nb; U[7] = bz / nb;
     rank = 2;
   }
@@ -84,15 +87,17 @@ __device__ void rotation_from_H(const double Hin[9], float R[9]) {
     U[8] = U[0] * U[4] - U[3] * U[1];
   }
   // d = sign(det(V U^T)) = sign(det V * det U)
-  auto det3 = [](const double* M) {
+  auto det3 = [](const F* M) -> F {
     return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
   };
-  double dd = det3(Vs) * det3(U);
-  double d = dd > 0 ? 1.0 : (dd < 0 ? -1.0 : 0.0);
+  F dd = det3(Vs) * det3(U);
+  F d = dd > (F)0 ? (F)1 : (dd < (F)0 ? (F)-1 : (F)0);
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++)
       R[3 * i + j] = (float)(Vs[3 * i + 0] * U[3 * j + 0] + Vs[3 * i + 1] * U[3 * j + 1] + d * Vs[3 * i + 2] * U[3 * j + 2]);
 }
+
+__device__ void rotation_from_H(const double Hin[9], float R[9]) { rotation_from_H_t<double>(Hin, R); }
 
 // Weighted Procrustes over n correspondences by one warp. T (row-major 4x4) written by lane 0.
 __device__ void warp_procrustes(const float* __restrict__ src, const float* __restrict__ ref,
@@ -394,10 +399,12 @@ __global__ void __launch_bounds__(1024) lgr_refine_kernel(const int* __restrict_
     }
     block_sum(v, 9);
     if (tid == 0) {
-      double Hd[9];
-      for (int k = 0; k < 9; k++) Hd[k] = (double)s_red[0][k];
+      // single-precision Jacobi here (the reference's SVD is LAPACK sgesdd, procrustes.py:53): this thread is the serial
+      // section of the refinement loop, and B200's FP64 sqrt / divide made the double version 84 us for the 6 solves
+      float Hf[9];
+      for (int k = 0; k < 9; k++) Hf[k] = s_red[0][k];
       float R[9];
-      rotation_from_H(Hd, R);
+      rotation_from_H_t<float>(Hf, R);
       for (int a = 0; a < 3; a++) {
         s_T[4 * a] = R[3 * a];
         s_T[4 * a + 1] = R[3 * a + 1];
