@@ -396,7 +396,8 @@ def run_ours(args, rank, world, local_rank):
                        "pipeline": ("pair pipeline: pyramid of pair i+1 on a side stream during the network pass of pair i"
                                     if pipelined else "off: one pair at a time")},
             "wall_ms_per_step_incl_flush": wall_ms / args.steps,
-            "step_ms_stats": {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)), "max": float(np.max(step_ms))},
+            "step_ms_stats": {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)), "max": float(np.max(step_ms)),
+                              "outlier_steps": [int(i) for i, t in enumerate(step_ms) if t > 1.5 * float(np.median(step_ms))]},
             "e2e": {"value": world * args.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": reg.h2d_bytes,
                     "d2h_bytes_per_step": reg.d2h_bytes, "ms_per_step": e2e_ms / args.steps,
                     "api": api_name},

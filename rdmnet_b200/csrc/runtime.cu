@@ -4,6 +4,7 @@
 // rdmnet/thdroformer/thdroformer.py:229-251, 304-347 (RPEConditionalTransformer / ThDRoFormer forward).
 // No kernel lives here: the functions below only sequence the launch functions of the other translation units and
 // carve temporaries out of the caller's workspace (the same code runs "dry" to size that workspace).
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "../../include/rdm_sm100.h"
@@ -93,13 +94,14 @@ int unary(Arena& a, StatSlots& ss, const rdm_unary_desc& u, const float* x, int 
 // KPConv.forward (kpconv.py:79-122) + norm_conv + LeakyReLU: out [M, c_mid_out]
 int kpconv_norm(Arena& a, StatSlots& ss, const rdm_block_desc& b, const float* feats, const unsigned char* rowpos_ready,
                 const float* q_pts, const float* s_pts, const void* idx, int index_bytes, int M, int N, int H, const int* order,
-                float* out, int groups, cudaStream_t st) {
+                float* out, int groups, cudaStream_t st, cudaEvent_t after_gather = nullptr) {
   size_t mark = a.off;
   float* gathered = a.f((size_t)M * 15 * b.c_mid_in);
   unsigned char* rowpos = rowpos_ready ? const_cast<unsigned char*>(rowpos_ready) : (unsigned char*)a.raw((size_t)(N > 0 ? N : 1));
   if (!a.dry)
     RDM_TRY(rdm_kpconv_gather_impl(feats, q_pts, s_pts, idx, index_bytes, b.kernel_points, b.h_kernel_points, b.sigma, M, N, H,
                                    b.c_mid_in, order, gathered, rowpos, rowpos_ready != nullptr, st));
+  if (!a.dry && after_gather != nullptr) RDM_CUDA(cudaEventRecord(after_gather, st));
   const int prof = a.dry ? -1 : rdm_prof_begin(RDM_PROF_KPCONV_GEMM, M, 15 * b.c_mid_in, 0, b.c_mid_out, st);
   const int K = 15 * b.c_mid_in;
   double* stats = ss.take(groups);
@@ -119,6 +121,31 @@ int kpconv_norm(Arena& a, StatSlots& ss, const rdm_block_desc& b, const float* f
   a.off = mark;
   return RDM_OK;
 }
+
+// The shortcut branch of a ResidualBlock (max-pool over the neighbours for strided blocks, Linear + GroupNorm when the
+// width changes; modules.py:213-220) depends only on the block input. It runs on a second stream, forked right AFTER the
+// block's neighbour gather (so the gather is timed alone) and joined before unary2 adds it: ~40 us of small-grid kernels
+// per block that overlap the KPConv weight GEMM and its norm instead of extending the chain. RDM_DUAL_STREAM=0 disables.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork[32], join[32];
+  int state = 0;  // 0 unknown, 1 ready, -1 off
+  bool ready() {
+    if (state == 0) {
+      const char* e = getenv("RDM_DUAL_STREAM");
+      state = (e && e[0] == '0') ? -1 : 1;
+      if (state == 1) {
+        if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) state = -1;
+        for (int i = 0; i < 32 && state == 1; i++)
+          if (cudaEventCreateWithFlags(&fork[i], cudaEventDisableTiming) != cudaSuccess ||
+              cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming) != cudaSuccess)
+            state = -1;
+      }
+    }
+    return state == 1;
+  }
+};
+SideStream g_side;
 
 int encoder_run(Arena& a, const rdm_block_desc* blocks, int nb, const rdm_pyramid_desc& p, int groups, const float* in_feats,
                 float* const* out_feats, cudaStream_t st) {
@@ -153,17 +180,36 @@ int encoder_run(Arena& a, const rdm_block_desc* blocks, int nb, const rdm_pyrami
         x = t;
       }
       float* c = a.f((size_t)M * b.c_mid_out);
-      RDM_TRY(kpconv_norm(a, ss, b, x, rowpos, q_pts, s_pts, idx, p.index_bytes, M, N, H, p.order[s], c, groups, st));
+      // shortcut buffers are carved BEFORE kpconv_norm so that they never alias its (released) gather buffer
+      float* mp = b.strided ? a.f((size_t)M * b.c_in) : nullptr;
+      float* sct = b.shortcut.w != nullptr ? a.f((size_t)M * b.c_out) : nullptr;
+      // ... and so is the split-K scratch of the shortcut GEMM: linear() carves it at the current arena offset, which after
+      // kpconv_norm would be the gather buffer the main stream's weight GEMM is still reading
+      size_t branch_ws = 0;
+      if (sct != nullptr && (long long)M * b.c_out <= (1 << 20)) branch_ws = rdm_linear_workspace(M, b.c_out, b.c_in) + 512;
+      const size_t branch_off = a.off;
+      if (branch_ws) a.raw(branch_ws);
+      const bool has_branch = mp != nullptr || sct != nullptr;
+      const bool dual = has_branch && !a.dry && i < 32 && g_side.ready();
+      RDM_TRY(kpconv_norm(a, ss, b, x, rowpos, q_pts, s_pts, idx, p.index_bytes, M, N, H, p.order[s], c, groups, st,
+                          dual ? g_side.fork[i] : nullptr));
+      const cudaStream_t bs = dual ? g_side.stream : st;
+      if (dual) RDM_CUDA(cudaStreamWaitEvent(bs, g_side.fork[i], 0));
       const float* sc = cur;
       if (b.strided) {
-        float* mp = a.f((size_t)M * b.c_in);
-        if (!a.dry) RDM_TRY(rdm_maxpool(cur, idx, p.index_bytes, M, N, H, b.c_in, mp, st));
+        if (!a.dry) RDM_TRY(rdm_maxpool(cur, idx, p.index_bytes, M, N, H, b.c_in, mp, bs));
         sc = mp;
       }
       if (b.shortcut.w != nullptr) {
-        float* t = a.f((size_t)M * b.c_out);
-        RDM_TRY(unary(a, ss, b.shortcut, sc, b.c_in, t, M, groups, nullptr, 0, nullptr, st));
-        sc = t;
+        const size_t keep = a.off;
+        a.off = branch_off;  // scratch inside the reserved region
+        RDM_TRY(unary(a, ss, b.shortcut, sc, b.c_in, sct, M, groups, nullptr, 0, nullptr, bs));
+        a.off = keep;
+        sc = sct;
+      }
+      if (dual) {
+        RDM_CUDA(cudaEventRecord(g_side.join[i], bs));
+        RDM_CUDA(cudaStreamWaitEvent(st, g_side.join[i], 0));
       }
       RDM_TRY(unary(a, ss, b.unary2, c, b.c_mid_out, out, M, groups, sc, 1, nullptr, st));
     }
