@@ -181,15 +181,16 @@ int encoder_run(Arena& a, const rdm_block_desc* blocks, int nb, const rdm_pyrami
       }
       float* c = a.f((size_t)M * b.c_mid_out);
       // shortcut buffers are carved BEFORE kpconv_norm so that they never alias its (released) gather buffer
-      float* mp = b.strided ? a.f((size_t)M * b.c_in) : nullptr;
-      float* sct = b.shortcut.w != nullptr ? a.f((size_t)M * b.c_out) : nullptr;
+      const bool need_mp = b.strided != 0, need_sct = b.shortcut.w != nullptr;  // (pointers are NULL in the sizing dry run)
+      float* mp = need_mp ? a.f((size_t)M * b.c_in) : nullptr;
+      float* sct = need_sct ? a.f((size_t)M * b.c_out) : nullptr;
       // ... and so is the split-K scratch of the shortcut GEMM: linear() carves it at the current arena offset, which after
       // kpconv_norm would be the gather buffer the main stream's weight GEMM is still reading
       size_t branch_ws = 0;
-      if (sct != nullptr && (long long)M * b.c_out <= (1 << 20)) branch_ws = rdm_linear_workspace(M, b.c_out, b.c_in) + 512;
+      if (need_sct && (long long)M * b.c_out <= (1 << 20)) branch_ws = rdm_linear_workspace(M, b.c_out, b.c_in) + 512;
       const size_t branch_off = a.off;
       if (branch_ws) a.raw(branch_ws);
-      const bool has_branch = mp != nullptr || sct != nullptr;
+      const bool has_branch = need_mp || need_sct;
       const bool dual = has_branch && !a.dry && i < 32 && g_side.ready();
       RDM_TRY(kpconv_norm(a, ss, b, x, rowpos, q_pts, s_pts, idx, p.index_bytes, M, N, H, p.order[s], c, groups, st,
                           dual ? g_side.fork[i] : nullptr));
