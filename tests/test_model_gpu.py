@@ -185,7 +185,7 @@ def test_pair_pipeline_equals_sequential(model, scans):
             assert np.array_equal(g[k], w[k]), k
 
 
-@pytest.mark.parametrize("size_class", ["4k", "8k", "32k"])
+@pytest.mark.parametrize("size_class", ["4k", "8k", "16k", "32k"])
 def test_forward_size_sweep_runners_equal_stepwise(model, size_class):
     """Config-5 size classes (4k-32k points/scan): the runner path (pyramid + backbone + match runners) and the per-operator
     path agree, and the pose is a rigid transform. Guards shape-dependent kernel choices (split/non-split gather, split-K
