@@ -297,6 +297,9 @@ def run_ours(args, rank, world, local_rank):
     no_flush = os.environ.get("BENCH_NO_FLUSH", "0") == "1"    # debug knob (the reported configuration always flushes)
     launches0 = L.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev:  # torch creates the CUDA event at its first record(): do that here, not inside the timed loop
+        a.record()
+        b.record()
     barrier()
     clocks.mark_begin()
     t_wall0 = time.perf_counter()

@@ -218,7 +218,8 @@ class PairPipeline:
         # high priority: the side stream's kernels are few and small, and the host waits on the first of them (the
         # subsampling chain) before it can queue the rest of the pair in flight - they must not starve behind the
         # network's large grids
-        self.side = torch.cuda.Stream(self.device, priority=-1)
+        import os
+        self.side = torch.cuda.Stream(self.device, priority=int(os.environ.get("RDM_PIPE_PRIORITY", "-1")))
         self.jobs = [PyramidJob(), PyramidJob()]
 
     def _begin(self, item, slot):
