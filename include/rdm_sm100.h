@@ -37,6 +37,13 @@ unsigned long long rdm_launch_count(void);
 /* how many of those were tensor-core GEMMs (tcgen05 kind::tf32, 3-term split): lets tests assert the path taken */
 unsigned long long rdm_tc_gemm_count(void);
 
+/* ABI self-description (host only, no GPU): sizeof of every struct below in declaration order (rdm_prof_record,
+ * rdm_tf_proj_job, rdm_tf_attn_job, rdm_unary_desc, rdm_block_desc, rdm_pyramid_desc, rdm_pyramid_cfg,
+ * rdm_thdroformer_desc, rdm_backbone_desc, rdm_backbone_out, rdm_match_desc, rdm_match_io, rdm_match_result), then
+ * offsetof(rdm_block_desc, sigma), (rdm_pyramid_desc, order), (rdm_match_desc, nms_limit), (rdm_match_io, transform),
+ * (rdm_match_result, transform). Returns the number of entries. A binding checks its struct mirrors against it. */
+int rdm_abi_layout(int64_t* h_out, int max_entries);
+
 /* optional kernel timing: after rdm_prof_enable(1) the library brackets selected launches with CUDA events on the launch
  * stream; rdm_prof_read synchronises those events and returns the records. tag 1 = KPConv gather (row_positive prepass +
  * gather kernel, m/n/h/c = M, N, H, C_in), tag 2 = KPConv weight GEMM (m, n, -, c = M, K, 0, N). */

@@ -16,6 +16,7 @@ SIGNATURES = {
     "rdm_version": (c_int, []),
     "rdm_launch_count": (ctypes.c_ulonglong, []),
     "rdm_tc_gemm_count": (ctypes.c_ulonglong, []),
+    "rdm_abi_layout": (c_int, [c_void_p, c_int]),
     "rdm_prof_enable": (None, [c_int]),
     "rdm_prof_read": (c_int, [c_void_p, c_int]),
     "rdm_grid_subsample_workspace": (c_size_t, [c_i64, c_int]),

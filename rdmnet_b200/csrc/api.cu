@@ -96,3 +96,20 @@ extern "C" int rdm_prof_read(rdm_prof_record* out, int max_records) {
   }
   return n;
 }
+
+// ---- ABI self-description: sizeof / selected offsetof of every struct of include/rdm_sm100.h, so that a host binding
+// (rdmnet_b200/_lib.py's ctypes mirrors) can be checked against the compiled layout without a GPU (tests/test_abi_cpu.py).
+#include <stddef.h>
+extern "C" int rdm_abi_layout(int64_t* out, int max_entries) {
+  const int64_t v[] = {
+      (int64_t)sizeof(rdm_prof_record),      (int64_t)sizeof(rdm_tf_proj_job),     (int64_t)sizeof(rdm_tf_attn_job),
+      (int64_t)sizeof(rdm_unary_desc),       (int64_t)sizeof(rdm_block_desc),      (int64_t)sizeof(rdm_pyramid_desc),
+      (int64_t)sizeof(rdm_pyramid_cfg),      (int64_t)sizeof(rdm_thdroformer_desc), (int64_t)sizeof(rdm_backbone_desc),
+      (int64_t)sizeof(rdm_backbone_out),     (int64_t)sizeof(rdm_match_desc),      (int64_t)sizeof(rdm_match_io),
+      (int64_t)sizeof(rdm_match_result),
+      (int64_t)offsetof(rdm_block_desc, sigma), (int64_t)offsetof(rdm_pyramid_desc, order), (int64_t)offsetof(rdm_match_desc, nms_limit),
+      (int64_t)offsetof(rdm_match_io, transform), (int64_t)offsetof(rdm_match_result, transform)};
+  const int n = (int)(sizeof(v) / sizeof(v[0]));
+  for (int i = 0; i < n && i < max_entries; i++) out[i] = v[i];
+  return n;
+}

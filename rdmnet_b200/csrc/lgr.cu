@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) lgr_extract_kernel(const float* __restric
                                                           float* __restrict__ st_score) {
   __shared__ int s_rarg[LGR_MAXK + 1], s_carg[LGR_MAXK + 1];
   __shared__ float s_rmax[LGR_MAXK + 1], s_cmax[LGR_MAXK + 1];
-  __shared__ int s_rowcnt[LGR_MAXK], s_scan[33];
+  __shared__ int s_scan[33];
   const int p = blockIdx.x, tid = threadIdx.x, K1 = K + 1;
   const float* sp = scores + (size_t)p * K1 * K1;
   const unsigned char* rm = rmask_nodes + (size_t)ridx[p] * K;
@@ -222,7 +222,6 @@ __global__ void __launch_bounds__(256) lgr_extract_kernel(const float* __restric
   int myc = 0;
   if (tid < K) {
     for (int j = 0; j < K; j++) myc += is_corr(tid, j);
-    s_rowcnt[tid] = myc;
   }
   int total;
   int pre = block_exclusive_scan(tid < K ? myc : 0, s_scan, &total);

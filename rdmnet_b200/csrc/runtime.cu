@@ -23,7 +23,6 @@ struct Arena {
     if (off > peak) peak = off;
     return r;
   }
-  bool ok() const { return dry || peak <= cap; }
 };
 
 #define RDM_TRY(call)          \

@@ -49,23 +49,6 @@ struct AttnJobs {
   rdm_tf_attn_job j[2];
 };
 
-// acc[i] += sum_k WT[k][o] * xt[k][r0 + i], i < 4.   xt is a [K][8] shared tile (rows of the CTA, transposed).
-template <int K>
-__device__ __forceinline__ void rowblock_gemv4(const float* __restrict__ WT, int ldw, int o, const float* xt, int r0,
-                                               float acc[4]) {
-#pragma unroll 4
-  for (int k = 0; k < K; k += 4) {
-    const float w0 = __ldg(WT + (size_t)(k + 0) * ldw + o), w1 = __ldg(WT + (size_t)(k + 1) * ldw + o),
-                w2 = __ldg(WT + (size_t)(k + 2) * ldw + o), w3 = __ldg(WT + (size_t)(k + 3) * ldw + o);
-    const float4 x0 = *(const float4*)(xt + (k + 0) * TF_R + r0), x1 = *(const float4*)(xt + (k + 1) * TF_R + r0),
-                 x2 = *(const float4*)(xt + (k + 2) * TF_R + r0), x3 = *(const float4*)(xt + (k + 3) * TF_R + r0);
-    acc[0] = fmaf(w0, x0.x, acc[0]); acc[1] = fmaf(w0, x0.y, acc[1]); acc[2] = fmaf(w0, x0.z, acc[2]); acc[3] = fmaf(w0, x0.w, acc[3]);
-    acc[0] = fmaf(w1, x1.x, acc[0]); acc[1] = fmaf(w1, x1.y, acc[1]); acc[2] = fmaf(w1, x1.z, acc[2]); acc[3] = fmaf(w1, x1.w, acc[3]);
-    acc[0] = fmaf(w2, x2.x, acc[0]); acc[1] = fmaf(w2, x2.y, acc[1]); acc[2] = fmaf(w2, x2.z, acc[2]); acc[3] = fmaf(w2, x2.w, acc[3]);
-    acc[0] = fmaf(w3, x3.x, acc[0]); acc[1] = fmaf(w3, x3.y, acc[1]); acc[2] = fmaf(w3, x3.z, acc[2]); acc[3] = fmaf(w3, x3.w, acc[3]);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ projection
 __device__ __forceinline__ void tfp_cp16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");

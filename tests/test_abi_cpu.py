@@ -68,3 +68,17 @@ def test_no_cpu_fallback():
         ops.radius_search(pts, pts, lens, lens, 0.2, 8)
     with pytest.raises(RuntimeError, match="float32"):  # dtype preconditions of torch_helper.h:6-35
         ops.grid_subsample(pts.double(), lens, 0.1)
+
+
+def test_ctypes_struct_mirrors_match_compiled_layout():
+    """sizeof / offsetof of every C struct of the header == the ctypes.Structure mirrors of rdmnet_b200/_lib.py."""
+    from rdmnet_b200 import _lib as L
+    buf = (ctypes.c_int64 * 64)()
+    n = L.lib().rdm_abi_layout(ctypes.cast(buf, ctypes.c_void_p), 64)
+    got = [int(buf[i]) for i in range(n)]
+    mirrors = [L.ProfRecord, L.TfProjJob, L.TfAttnJob, L.UnaryDesc, L.BlockDesc, L.PyramidDesc, L.PyramidCfg,
+               L.ThdroformerDesc, L.BackboneDesc, L.BackboneOut, L.MatchDesc, L.MatchIO, L.MatchResult]
+    want = [ctypes.sizeof(m) for m in mirrors] + [L.BlockDesc.sigma.offset, L.PyramidDesc.order.offset,
+                                                  L.MatchDesc.nms_limit.offset, L.MatchIO.transform.offset,
+                                                  L.MatchResult.transform.offset]
+    assert got == want, list(zip(got, want))
