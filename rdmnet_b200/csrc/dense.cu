@@ -255,6 +255,11 @@ int rdm_linear_tc(const float* A, int lda, const float* B, int ldb, const float*
                   int act, void* workspace, size_t workspace_bytes, int* out_splits, double* gn_stats, int gn_cpg,
                   int* out_stats_fused, cudaStream_t stream);  // gemm_tc.cu
 
+// experimental A-in-TMEM variant of the same kernel (gemm_tc_atmem.cu): -1 unless RDM_GEMM_ATMEM=1
+int rdm_linear_tc_atmem(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N, int K,
+                        int act, void* workspace, size_t workspace_bytes, int* out_splits, double* gn_stats, int gn_cpg,
+                        int* out_stats_fused, cudaStream_t stream);
+
 extern "C" int rdm_linear(const float* A, int lda, const float* B, int ldb, int b_is_nk, const float* bias, float* C,
                           int ldc, int M, int N, int K, int act, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   return rdm_linear_gn(A, lda, B, ldb, b_is_nk, bias, C, ldc, M, N, K, act, workspace, workspace_bytes, nullptr, 0, nullptr,
@@ -278,8 +283,11 @@ int rdm_linear_gn(const float* A, int lda, const float* B, int ldb, int b_is_nk,
   }
   if (use_tc && b_is_nk && M >= 64) {
     int tc_splits = 1;
-    int rc = rdm_linear_tc(A, lda, B, ldb, bias, C, ldc, M, N, K, act, workspace, workspace_bytes, &tc_splits, gn_stats, gn_cpg,
-                           stats_fused, stream);
+    int rc = rdm_linear_tc_atmem(A, lda, B, ldb, bias, C, ldc, M, N, K, act, workspace, workspace_bytes, &tc_splits, gn_stats,
+                                 gn_cpg, stats_fused, stream);
+    if (rc == -1)
+      rc = rdm_linear_tc(A, lda, B, ldb, bias, C, ldc, M, N, K, act, workspace, workspace_bytes, &tc_splits, gn_stats, gn_cpg,
+                         stats_fused, stream);
     if (rc == RDM_OK && tc_splits > 1) {
       const bool pow2 = gn_cpg >= 1 && (gn_cpg & (gn_cpg - 1)) == 0 && (gn_cpg <= 32 || gn_cpg % 32 == 0);
       if (gn_stats != nullptr && act == 0 && N % 32 == 0 && pow2) {

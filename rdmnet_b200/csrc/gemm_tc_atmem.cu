@@ -1,31 +1,49 @@
-// fp32-accurate tensor-core GEMM for sm_100a: C[M,N] = act(A[M,K] * B[N,K]^T + bias), A and B fp32 row-major.
+// EXPERIMENTAL (off by default, RDM_GEMM_ATMEM=1 / rdm_debug_gemm_variant(1) to enable; not yet validated on hardware):
+// the tcgen05 3-term-split GEMM of gemm_tc.cu with the A operand in TENSOR MEMORY.
 //
-// The dense contractions of the backbone (UnaryBlock / decoder Linear layers, the KPConv weight contraction
-// (M x 15C) * (15C x C'), in_proj of the transformers) are ~100 GFLOP per pair; on the SIMT fp32 path they were ~30 % of
-// the GPU time. This kernel runs them on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in
-// TMEM) while keeping fp32-level accuracy with the 3-term split  a*b ~= ah*bh + ah*bl + al*bh  (ah = tf32(a),
-// al = tf32(a - ah)): the north-star tolerance is 1e-4 on features, which a single TF32 pass (2^-11) does not meet.
-//
-// CTA = 192 threads, one 128 x BN output tile, K blocks of 32 floats (one 128-byte swizzle atom):
-//   warp 0     TMA producer: cp.async.bulk.tensor loads of the raw fp32 A / B tiles (SWIZZLE_128B), mbarrier tx-count
-//   warps 2-5  split the landed tile in place into hi (same buffer) and lo (second buffer) - an element-wise pass
-//              at identical offsets, so the swizzle is preserved - then fence.proxy.async and arrive
-//   warp 1     one elected lane issues 3 x 4 tcgen05.mma (M128 x N x K8) per K block and tcgen05.commit's the
-//              stage back to the producer; the last commit signals the epilogue
-//   warps 2-5  epilogue: tcgen05.ld 32x32b (each warp its 32 TMEM lanes), + bias, activation, 128-bit stores
-// All waits are bounded spins that trap, so a protocol bug aborts the kernel instead of hanging the GPU.
+// Why: gemm_tc.cu is shared-memory-bandwidth bound (scripts/gemm_timeline.py: ~1100 cycles per 128 x 64 x 32 k-block for
+// ~100 cycles of MMA). Per k-block it moves 24 KB (TMA) + 24 KB (converter reads) + 48 KB (converter writes of hi / lo)
+// + 72 KB (operand reads of the three products) through a 128 B/clk shared memory. Here the converter threads write
+// A_hi / A_lo straight into TMEM with tcgen05.st (thread = tile row = TMEM lane) and the MMAs take A from TMEM
+// ("ts" form: tcgen05.mma [d], [a_tmem], b_desc), so A costs 16 KB of shared-memory reads per k-block instead of 112 KB:
+// 88 KB per k-block in total. Everything else (TMA pipeline, B split in place, epilogue with bias / activation /
+// GroupNorm statistics, split-K) is the gemm_tc.cu design.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/rdm_sm100.h"
 #include "tc_common.cuh"
 
+extern unsigned long long g_tc_launches_ext;
+
 namespace {
 
+// D[tmem] (+)= A[tmem] * B[smem desc]: A rows = TMEM lanes, K along columns
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 consecutive columns of this thread's TMEM lane <- r[0..31]
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+
 template <int BN, int STAGES>
-struct TcSmem {
+struct TcaSmem {
   // every buffer is a multiple of 1024 B: the 128-byte swizzle pattern repeats every 8 rows
-  float a_hi[STAGES][TC_BM * TC_BK];
-  float a_lo[STAGES][TC_BM * TC_BK];
+  float a_raw[STAGES][TC_BM * TC_BK];  // raw fp32 A tile (TMA, SWIZZLE_128B); its hi / lo split lives in TMEM
   float b_hi[STAGES][BN * TC_BK];
   float b_lo[STAGES][BN * TC_BK];
   uint64_t raw_full[STAGES], conv_full[STAGES], empty[STAGES], accum_full;
@@ -33,14 +51,14 @@ struct TcSmem {
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_atmem_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                    const __grid_constant__ CUtensorMap map_b,
                                                                    const float* __restrict__ bias, float* __restrict__ C,
                                                                    int ldc, int M, int N, int K, int act, int kb_per_split,
                                                                    double* __restrict__ gn_stats, int gn_cpg,
                                                                    long long* __restrict__ dbg) {
   extern __shared__ unsigned char smem_raw[];
-  using Smem = TcSmem<BN, STAGES>;
+  using Smem = TcaSmem<BN, STAGES>;
   Smem& sm = *reinterpret_cast<Smem*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
@@ -67,8 +85,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const __grid
     mbar_init(&sm.accum_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM: BN fp32 accumulator columns (power of two >= 32)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(BN));
+  // TMEM columns: [0, BN) accumulators, then per stage 32 columns of A_hi and 32 of A_lo (row m of the tile = lane m)
+  constexpr int A_COL0 = BN;
+  static_assert(BN + 64 * STAGES <= 512, "TMEM budget");
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -86,7 +107,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const __grid
         const int s = kb % STAGES;
         mbar_wait(&sm.empty[s], ((kb / STAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(&sm.raw_full[s], bytes);
-        tma_load_2d(sm.a_hi[s], &map_a, &sm.raw_full[s], (kb0 + kb) * TC_BK, m0);
+        tma_load_2d(sm.a_raw[s], &map_a, &sm.raw_full[s], (kb0 + kb) * TC_BK, m0);
         tma_load_2d(sm.b_hi[s], &map_b, &sm.raw_full[s], (kb0 + kb) * TC_BK, n0);
         if (kb == 0) TC_STAMP(2);
       }
@@ -101,14 +122,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const __grid
         mbar_wait(&sm.conv_full[s], (kb / STAGES) & 1);
         if (kb == 0) TC_STAMP(4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t dah = umma_desc_sw128(smem_u32(sm.a_hi[s])), dal = umma_desc_sw128(smem_u32(sm.a_lo[s]));
         const uint64_t dbh = umma_desc_sw128(smem_u32(sm.b_hi[s])), dbl = umma_desc_sw128(smem_u32(sm.b_lo[s]));
+        const uint32_t ta_hi = tmem + (uint32_t)(A_COL0 + 64 * s), ta_lo = ta_hi + 32;
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; k++) {
-          const uint64_t adv = (uint64_t)(k * 32 / 16);  // 8 tf32 = 32 bytes along K inside the swizzle atom
-          umma_tf32(tmem, dal + adv, dbh + adv, idesc, (kb | k) != 0);
-          umma_tf32(tmem, dah + adv, dbl + adv, idesc, 1);
-          umma_tf32(tmem, dah + adv, dbh + adv, idesc, 1);
+          const uint64_t adv = (uint64_t)(k * 32 / 16);  // 8 tf32 = 32 bytes along K inside the swizzle atom (B operand)
+          umma_tf32_ts(tmem, ta_lo + 8 * k, dbh + adv, idesc, (kb | k) != 0);
+          umma_tf32_ts(tmem, ta_hi + 8 * k, dbl + adv, idesc, 1);
+          umma_tf32_ts(tmem, ta_hi + 8 * k, dbh + adv, idesc, 1);
         }
         umma_commit(&sm.empty[s]);  // frees the stage when these MMAs have read it
       }
@@ -121,14 +142,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const __grid
       const int s = kb % STAGES;
       mbar_wait(&sm.raw_full[s], (kb / STAGES) & 1);
       if (kb == 0 && t == 0) TC_STAMP(3);
-      float4* ah = reinterpret_cast<float4*>(sm.a_hi[s]);
-      float4* al = reinterpret_cast<float4*>(sm.a_lo[s]);
+      {
+        // A: this thread owns row (q*32 + lane) of the tile = TMEM lane of the same number (a warp may only touch its
+        // own lane quarter q = warp & 3). Read the row's 32 floats from the swizzled raw tile (16-byte chunk c of row r
+        // sits at chunk c ^ (r & 7)), split, and store hi / lo as 32 columns each with tcgen05.st.
+        const int q = warp & 3, r = q * 32 + lane;
+        const float4* arow = reinterpret_cast<const float4*>(sm.a_raw[s]) + r * 8;
+        uint32_t hi[32], lo[32];
 #pragma unroll
-      for (int i = 0; i < TC_BM * TC_BK / 4 / 128; i++) {
-        const float4 v = ah[t + i * 128];
-        const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-        ah[t + i * 128] = h;
-        al[t + i * 128] = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+        for (int c = 0; c < 8; c++) {
+          const float4 v = arow[c ^ (r & 7)];
+          const float h0 = to_tf32(v.x), h1 = to_tf32(v.y), h2 = to_tf32(v.z), h3 = to_tf32(v.w);
+          hi[4 * c] = __float_as_uint(h0); hi[4 * c + 1] = __float_as_uint(h1);
+          hi[4 * c + 2] = __float_as_uint(h2); hi[4 * c + 3] = __float_as_uint(h3);
+          lo[4 * c] = __float_as_uint(to_tf32(v.x - h0)); lo[4 * c + 1] = __float_as_uint(to_tf32(v.y - h1));
+          lo[4 * c + 2] = __float_as_uint(to_tf32(v.z - h2)); lo[4 * c + 3] = __float_as_uint(to_tf32(v.w - h3));
+        }
+        const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(A_COL0 + 64 * s);
+        tmem_st32(ta, hi);
+        tmem_st32(ta + 32, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
       float4* bh = reinterpret_cast<float4*>(sm.b_hi[s]);
       float4* bl = reinterpret_cast<float4*>(sm.b_lo[s]);
@@ -139,7 +172,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const __grid
         bh[t + i * 128] = h;
         bl[t + i * 128] = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the UMMA reads
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes (B) -> visible to the UMMA reads
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // TMEM stores (A) ordered before the arrive
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.conv_full[s]);
     }
@@ -207,48 +241,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const __grid
   if (threadIdx.x == 0) TC_STAMP(8);
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
   }
 }
 
-unsigned long long g_tc_launches = 0;
-}  // namespace
-unsigned long long g_tc_launches_ext = 0;  // launches of the experimental A-in-TMEM variant (gemm_tc_atmem.cu)
-namespace {
-
 template <int BN, int STAGES>
-int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, float* C, int ldc, int M, int N, int K, int act,
+int launch_tca(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, float* C, int ldc, int M, int N, int K, int act,
               int splits, int kb_per_split, double* gn_stats, int gn_cpg, cudaStream_t stream, long long* dbg = nullptr) {
-  const size_t smem = sizeof(TcSmem<BN, STAGES>) + 1024;
+  const size_t smem = sizeof(TcaSmem<BN, STAGES>) + 1024;
   static bool attr = false;
   if (!attr) {
-    RDM_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RDM_CUDA(cudaFuncSetAttribute(gemm_tf32x3_atmem_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   dim3 grid(cdiv(N, BN), cdiv(M, TC_BM), splits);
-  RDM_CUDA(rdm_launch_pdl(gemm_tf32x3_kernel<BN, STAGES>, grid, dim3(TC_THREADS), smem, stream, ma, mb, bias, C, ldc, M, N, K, act,
+  RDM_CUDA(rdm_launch_pdl(gemm_tf32x3_atmem_kernel<BN, STAGES>, grid, dim3(TC_THREADS), smem, stream, ma, mb, bias, C, ldc, M, N, K, act,
                           kb_per_split, gn_stats, gn_cpg, dbg));
   RDM_LAUNCH_CHECK();
-  __atomic_fetch_add(&g_tc_launches, 1ull, __ATOMIC_RELAXED);
+  __atomic_fetch_add(&g_tc_launches_ext, 1ull, __ATOMIC_RELAXED);
   return RDM_OK;
 }
 }  // namespace
 
-// Returns RDM_OK if the GEMM was launched on the tensor-core path, -1 if the shape / alignment does not qualify (the
-// caller then uses the SIMT kernel), or an error code. With a workspace, small-tile-count problems are split along K into
-// partial tiles (deterministic: `*out_splits` partials that the caller reduces with bias / activation).
-// gn_stats / gn_cpg (optional): GroupNorm {sum, sumsq} accumulation of the OUTPUT in the epilogue (N % 32 == 0, cpg a power
-// of two, aligned rows, no split-K); *out_stats_fused says whether it happened.
-int rdm_linear_tc(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N, int K,
-                  int act, void* workspace, size_t workspace_bytes, int* out_splits, double* gn_stats, int gn_cpg,
-                  int* out_stats_fused, cudaStream_t stream) {
+// Same contract as rdm_linear_tc (gemm_tc.cu). Returns -1 when the variant is off or the shape does not qualify.
+int g_gemm_variant = -1;  // -1 unknown (read RDM_GEMM_ATMEM), 0 off, 1 on
+extern "C" void rdm_debug_gemm_variant(int v) { g_gemm_variant = v ? 1 : 0; }
+
+int rdm_linear_tc_atmem(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N, int K,
+                        int act, void* workspace, size_t workspace_bytes, int* out_splits, double* gn_stats, int gn_cpg,
+                        int* out_stats_fused, cudaStream_t stream) {
+  if (g_gemm_variant < 0) {
+    const char* e = getenv("RDM_GEMM_ATMEM");
+    g_gemm_variant = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (g_gemm_variant != 1) return -1;
   *out_splits = 1;
   if (out_stats_fused) *out_stats_fused = 0;
   if (M < 1 || N < 8 || K < 8) return -1;
-  if ((lda % 4) || (ldb % 4) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) return -1;  // TMA: 16-byte strides / base
+  if ((lda % 4) || (ldb % 4) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) return -1;
   if (!load_encoder()) return -1;
-  // 128-wide tiles move 1.5x fewer shared-memory bytes per flop (the limiter of the 3-term split); use them when they
-  // still fill the machine, possibly with the help of split-K
   const int nk_all = cdiv(K, TC_BK);
   const long long t128 = (long long)cdiv(M, TC_BM) * cdiv(N, 128);
   const bool can_split = workspace != nullptr && nk_all >= 16;
@@ -278,40 +309,6 @@ int rdm_linear_tc(const float* A, int lda, const float* B, int ldb, const float*
     st = gn_stats;
     if (out_stats_fused) *out_stats_fused = 1;
   }
-  if (narrow) return launch_tc<64, 4>(ma, mb, b, out, ldo, M, N, K, a, splits, kps, st, gn_cpg, stream);
-  return launch_tc<128, 3>(ma, mb, b, out, ldo, M, N, K, a, splits, kps, st, gn_cpg, stream);
-}
-
-extern "C" unsigned long long rdm_tc_gemm_count(void) {
-  return __atomic_load_n(&g_tc_launches, __ATOMIC_RELAXED) + __atomic_load_n(&g_tc_launches_ext, __ATOMIC_RELAXED);
-}
-
-// debug: clock64 timeline of CTA (0,0,0) of one narrow-tile GEMM on scratch buffers (prints cycles since CTA start)
-extern "C" int rdm_debug_gemm_timeline(int M, int N, int K) {
-  if (!load_encoder()) return -1;
-  float *A, *B, *C;
-  long long* dbg;
-  RDM_CUDA(cudaMalloc(&A, (size_t)M * K * 4));
-  RDM_CUDA(cudaMalloc(&B, (size_t)N * K * 4));
-  RDM_CUDA(cudaMalloc(&C, (size_t)M * N * 4));
-  RDM_CUDA(cudaMalloc(&dbg, 16 * 8));
-  RDM_CUDA(cudaMemset(A, 0, (size_t)M * K * 4));
-  RDM_CUDA(cudaMemset(B, 0, (size_t)N * K * 4));
-  CUtensorMap ma, mb;
-  if (!make_map(&ma, A, M, K, K, TC_BM) || !make_map(&mb, B, N, K, K, 64)) return -1;
-  for (int rep = 0; rep < 3; rep++) {
-    RDM_CUDA(cudaMemset(dbg, 0, 16 * 8));
-    int rc = launch_tc<64, 4>(ma, mb, nullptr, C, N, M, N, K, 0, 1, cdiv(K, TC_BK), nullptr, 0, 0, dbg);
-    if (rc != RDM_OK) return rc;
-    RDM_CUDA(cudaDeviceSynchronize());
-    long long h[16];
-    RDM_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
-    printf("gemm timeline M%d N%d K%d rep%d:", M, N, K, rep);
-    const char* names[9] = {"start", "init+alloc", "tma0 issued", "raw0 landed", "conv0 done(mma)", "conv all done", "accum ready",
-                            "stores done", "final sync"};
-    for (int i = 1; i < 9; i++) printf("  %s=%lld", names[i], h[i] - h[0]);
-    printf("\n");
-  }
-  cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(dbg);
-  return RDM_OK;
+  if (narrow) return launch_tca<64, 4>(ma, mb, b, out, ldo, M, N, K, a, splits, kps, st, gn_cpg, stream);
+  return launch_tca<128, 3>(ma, mb, b, out, ldo, M, N, K, a, splits, kps, st, gn_cpg, stream);
 }
