@@ -441,7 +441,11 @@ def run_ours(args, rank, world, local_rank):
                          "kpconv_gather_ms_per_step": g["ms"] / args.steps,
                          "per_layer_GBps": {k: (v[1] / 1e9) / (v[0] / 1e3) for k, v in per_layer.items() if v[0] > 0}},
             "clocks": clk,
-            "pose_check": {"rre_deg": rre, "rte_m": rte, "n_corr": int(res["corr_scores"].shape[0])},
+            # context only, not a quality metric: the pretrained KITTI weights do not register the self-similar procedural
+            # corridor - the reference's own CPU path returns poses 9-14 m off on the same pairs. Pose PARITY with
+            # the reference is what tests/test_model_gpu.py pins, on the bundled KITTI scans.
+            "pose_vs_synthetic_gt": {"rre_deg": rre, "rte_m": rte, "n_corr": int(res["corr_scores"].shape[0]),
+                                     "note": "the reference path itself fails on this synthetic scene; see DESIGN.md"},
         }
         if world == 1 and not args.no_cpu_baseline:
             cb, _, _ = cpu_arm(pairs, args.cpu_pairs, 1, budget_s=60.0)

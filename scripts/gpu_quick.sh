@@ -12,6 +12,6 @@ r=l["roofline"]
 print("value",round(l["value"],2),"e2e",round(l["e2e"]["value"],2),"ms/step",round(l["ms_per_step"],3),"launches/step",l["gpu_launches"]/l["steps"])
 print("gather GB/s",round(r["achieved"],1),"frac",round(r["frac"],3),"gather ms/step",round(r["kpconv_gather_ms_per_step"],3),"step stats",l.get("step_ms_stats"))
 print({k:round(v) for k,v in r["per_layer_GBps"].items()})
-print(l["pose_check"], l["clocks"])
+print(l["pose_vs_synthetic_gt"], l["clocks"])
 PY
 tail -3 gpurun_out/${TAG}_bench.err
