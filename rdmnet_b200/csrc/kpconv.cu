@@ -577,6 +577,173 @@ __global__ void __launch_bounds__(128, 4) kpconv_gather_v4_kernel(const float* _
     *(float4*)(op + (size_t)k * C) = make_float4(acc[k][0].x * inv, acc[k][0].y * inv, acc[k][1].x * inv, acc[k][1].y * inv);
 }
 
+// EXPERIMENTAL (RDM_GATHER_PERSIST=1, off by default, not yet measured): persistent form of the v4 gather. 148 x 4 CTAs stay
+// resident and every warp pulls batches of 4 consecutive work items (= neighbouring queries in the cell-sorted walk order:
+// the L1 reuse of the CTA-per-4-items form is kept in time instead of in space) from a global counter - no ragged last wave,
+// no CTA relaunch cost, and the warps that drew dense neighbourhoods no longer decide the kernel time alone. The item body
+// is a verbatim copy of kpconv_gather_v4_kernel's (kept separate so that the default kernel's code generation is untouched).
+// cnt[0] = next item, cnt[1] = warps finished; the last warp out re-arms both for the next launch.
+template <int L, bool SPLIT, typename IdxT>
+__global__ void __launch_bounds__(128, 4) kpconv_gather_v4p_kernel(const float* __restrict__ feats,
+                                                                   const unsigned char* __restrict__ rowpos,
+                                                                   const float* __restrict__ q_pts,
+                                                                   const float* __restrict__ s_pts,
+                                                                   const IdxT* __restrict__ idx, const KPts kp,
+                                                                   float inv_sigma, int M, int N, int H, int C, int NS,
+                                                                   const int* __restrict__ order, float* __restrict__ out,
+                                                                   int total_items, int* __restrict__ cnt) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float4 s_dyn[];
+  auto item = [&](const int gw) {
+    constexpr int G = 32 / L;
+    constexpr int STEP = SPLIT ? 32 : L;  // neighbour slots per chunk (per query)
+    constexpr int HALF = L / 2;
+    constexpr int WARP_F4 = 32 * L + 32 * KP_WS / 4;  // float4 per warp: row buffer + influence tile
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / L, t = lane % L;
+    int m, slice;
+    if (SPLIT || L == 32) {
+      m = gw / NS;
+      slice = gw - m * NS;
+    } else {
+      m = gw * G + g;
+      slice = 0;
+    }
+    const bool qvalid = m < M;
+    if (__all_sync(FULL_MASK, !qvalid)) return;
+    if (qvalid && order != nullptr) m = order[m];
+    const int mm = qvalid ? m : M - 1;
+    const float qx = q_pts[3 * (size_t)mm], qy = q_pts[3 * (size_t)mm + 1], qz = q_pts[3 * (size_t)mm + 2];
+    const IdxT* row = idx + (size_t)mm * H;
+    const float* fbase = feats + slice * (4 * L) + 4 * t;
+    float4* rowbuf = s_dyn + (size_t)warp * WARP_F4;           // [32 rows][L] float4; row (g, u) at (g * L + u) * L
+    float* wtile = reinterpret_cast<float*>(rowbuf + 32 * L);  // [32][KP_WS]
+    float2 acc[KP_K][2];
+  #pragma unroll
+    for (int k = 0; k < KP_K; k++) acc[k][0] = acc[k][1] = make_float2(0.f, 0.f);
+    int npos = 0;
+    float4* wrow = (float4*)(wtile + (t * G + g) * KP_WS);  // rows interleaved over groups: (u, g) -> u*G + g
+    const int myslot = SPLIT ? lane : t;
+    auto load_j = [&](int h) -> int {
+      if (qvalid && h < H) {
+        long long jj = (long long)row[h];
+        if (jj < N) return (int)jj;
+      }
+      return -1;
+    };
+    // asynchronous copy of rows [u0, u0 + HALF) of every group for the chunk whose slot indices are `jc`; one commit group
+    auto issue_half = [&](int jc, int u0) {
+  #pragma unroll
+      for (int u = u0; u < u0 + HALF; u++) {
+        const int ju = __shfl_sync(FULL_MASK, jc, g * L + u);
+        if (ju >= 0) gather_cp16(rowbuf + (g * L + u) * L + t, fbase + (size_t)ju * C);
+      }
+      gather_commit();
+    };
+    int j = load_j(myslot);
+    int jn = load_j(STEP + myslot);
+    issue_half(j, 0);
+    issue_half(j, HALF);
+    for (int h0 = 0; h0 < H; h0 += STEP) {
+      if (!__any_sync(FULL_MASK, j >= 0)) break;  // rows are valid-first: nothing but padding from here on
+      const int jn2 = load_j(h0 + 2 * STEP + myslot);
+      // ---- (A) influences of this lane's slot
+      float w[16];
+      if (j >= 0) {
+        influences16(s_pts[3 * (size_t)j] - qx, s_pts[3 * (size_t)j + 1] - qy, s_pts[3 * (size_t)j + 2] - qz, kp, inv_sigma, w);
+        npos += rowpos[j];
+      } else {
+  #pragma unroll
+        for (int k = 0; k < 16; k++) w[k] = 0.f;
+      }
+      wrow[0] = make_float4(w[0], w[1], w[2], w[3]);
+      wrow[1] = make_float4(w[4], w[5], w[6], w[7]);
+      wrow[2] = make_float4(w[8], w[9], w[10], w[11]);
+      wrow[3] = make_float4(w[12], w[13], w[14], w[15]);
+      const unsigned vb = __ballot_sync(FULL_MASK, j >= 0);
+      int nu = 0;
+  #pragma unroll
+      for (int gg = 0; gg < G; gg++) {
+        const unsigned mg = (L == 32) ? vb : ((vb >> (gg * L)) & ((1u << (L & 31)) - 1u));
+        nu = max(nu, 32 - __clz(mg));
+      }
+      // ---- (B) two halves: multiply the landed rows, then refill their slots with the next chunk's rows
+  #pragma unroll
+      for (int half = 0; half < 2; half++) {
+        gather_wait<1>();  // this half's rows (the older of the two pending groups) have landed for this lane ...
+        __syncwarp();      // ... and for the whole warp; also orders the influence tile stores above
+        const int ue = min(nu, (half + 1) * HALF);
+  #pragma unroll 4
+        for (int u = half * HALF; u < ue; u++) {
+          const int ju = __shfl_sync(FULL_MASK, j, g * L + u);
+          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ju >= 0) f = rowbuf[(g * L + u) * L + t];
+          const float4* wp = (const float4*)(wtile + (u * G + g) * KP_WS);
+          const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+          const float ww[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+          const float2 fa = make_float2(f.x, f.y), fb = make_float2(f.z, f.w);
+  #pragma unroll
+          for (int k = 0; k < KP_K; k++) {
+            acc[k][0] = ffma2(ww[k], fa, acc[k][0]);
+            acc[k][1] = ffma2(ww[k], fb, acc[k][1]);
+          }
+        }
+        __syncwarp();  // every lane is done with this half's rows (and, after the second half, with the influence tile)
+        issue_half(jn, half * HALF);
+      }
+      j = jn;
+      jn = jn2;
+    }
+    gather_wait<0>();
+    if (SPLIT) {
+      npos = warp_sum_i(npos);
+  #pragma unroll
+      for (int o = L; o < 32; o <<= 1)
+  #pragma unroll
+        for (int k = 0; k < KP_K; k++) {
+          acc[k][0].x += __shfl_xor_sync(FULL_MASK, acc[k][0].x, o);
+          acc[k][0].y += __shfl_xor_sync(FULL_MASK, acc[k][0].y, o);
+          acc[k][1].x += __shfl_xor_sync(FULL_MASK, acc[k][1].x, o);
+          acc[k][1].y += __shfl_xor_sync(FULL_MASK, acc[k][1].y, o);
+        }
+      if (g != 0) return;
+    } else {
+  #pragma unroll
+      for (int o = L >> 1; o > 0; o >>= 1) npos += __shfl_xor_sync(FULL_MASK, npos, o);
+    }
+    if (!qvalid) return;
+    const float inv = 1.f / (float)max(npos, 1);
+    float* op = out + (size_t)m * KP_K * C + slice * (4 * L) + 4 * t;
+  #pragma unroll
+    for (int k = 0; k < KP_K; k++)
+      *(float4*)(op + (size_t)k * C) = make_float4(acc[k][0].x * inv, acc[k][0].y * inv, acc[k][1].x * inv, acc[k][1].y * inv);
+
+  };
+  constexpr int BATCH = 4;
+  for (;;) {
+    int w0 = 0;
+    if ((threadIdx.x & 31) == 0) w0 = atomicAdd(&cnt[0], BATCH);
+    w0 = __shfl_sync(FULL_MASK, w0, 0);
+    if (w0 >= total_items) break;
+    for (int b = 0; b < BATCH && w0 + b < total_items; b++) {
+      item(w0 + b);
+      __syncwarp();
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    if (atomicAdd(&cnt[1], 1) == nwarps - 1) {  // last warp of the grid: re-arm the counters
+      cnt[0] = 0;
+      cnt[1] = 0;
+      __threadfence();
+    }
+  }
+}
+
+int g_gather_persist = -1;  // -1: read RDM_GATHER_PERSIST; 0 off; 1 on (experimental persistent gather)
+extern "C" void rdm_debug_gather_persist(int v) { g_gather_persist = v ? 1 : 0; }
+
 template <int L, bool SPLIT, typename IdxT>
 static int launch_v4(long long warps, const float* feats, const unsigned char* rowpos, const float* q, const float* s,
                      const IdxT* idx, const KPts& kp, float inv_sigma, int M, int N, int H, int C, int NS, const int* order,
@@ -586,6 +753,26 @@ static int launch_v4(long long warps, const float* feats, const unsigned char* r
   if (!attr && smem > 48 * 1024) {
     RDM_CUDA(cudaFuncSetAttribute(kpconv_gather_v4_kernel<L, SPLIT, IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
+  }
+  static int* counters = nullptr;
+  if (g_gather_persist < 0) {
+    const char* e = getenv("RDM_GATHER_PERSIST");
+    g_gather_persist = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (g_gather_persist == 1 && warps > 148 * 16) {
+    if (counters == nullptr) {
+      RDM_CUDA(cudaMalloc(&counters, 2 * sizeof(int)));
+      RDM_CUDA(cudaMemset(counters, 0, 2 * sizeof(int)));
+    }
+    static bool attr_p = false;
+    if (!attr_p && smem > 48 * 1024) {
+      RDM_CUDA(cudaFuncSetAttribute(kpconv_gather_v4p_kernel<L, SPLIT, IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_p = true;
+    }
+    RDM_CUDA(rdm_launch_pdl(kpconv_gather_v4p_kernel<L, SPLIT, IdxT>, dim3(148 * 4), dim3(128), smem, stream, feats, rowpos, q, s, idx, kp,
+                            inv_sigma, M, N, H, C, NS, order, out, (int)warps, counters));
+    RDM_LAUNCH_CHECK();
+    return RDM_OK;
   }
   RDM_CUDA(rdm_launch_pdl(kpconv_gather_v4_kernel<L, SPLIT, IdxT>, dim3(cdiv(warps, 4)), dim3(128), smem, stream, feats, rowpos, q, s,
                           idx, kp, inv_sigma, M, N, H, C, NS, order, out));
