@@ -11,6 +11,7 @@ Differences from the reference that are part of the design (none changes results
     data-dependent output shapes (pyramid lengths, NMS survivors, number of correspondences).
 """
 import ctypes
+import os
 import types
 
 import torch
@@ -218,9 +219,12 @@ class PairPipeline:
         # high priority: the side stream's kernels are few and small, and the host waits on the first of them (the
         # subsampling chain) before it can queue the rest of the pair in flight - they must not starve behind the
         # network's large grids
-        import os
         self.side = torch.cuda.Stream(self.device, priority=int(os.environ.get("RDM_PIPE_PRIORITY", "-1")))
         self.jobs = [PyramidJob(), PyramidJob()]
+        # experimental knob (off by default, not yet measured): hold the next pair's radius searches back until the
+        # current pair's backbone has drained, so that they share the SMs with the matching tail instead of with the
+        # KPConv gathers (the gathers lose ~8 % to that contention inside the pipelined bench region)
+        self.defer_searches = os.environ.get("RDM_PIPE_DEFER_SEARCH", "0") == "1"
 
     def _begin(self, item, slot):
         points, lengths = item() if callable(item) else item  # a callable may stage host data (runs on the side stream)
@@ -256,8 +260,14 @@ class PairPipeline:
             state = self.model.forward_head(None, gp=gp)  # asynchronous launches on the main stream
             cur = None
             if nxt_item is not None:
+                backbone_done = None
+                if self.defer_searches:
+                    backbone_done = torch.cuda.Event()
+                    backbone_done.record(main)
                 with torch.cuda.stream(self.side):
                     self._begin(nxt_item, (i + 1) & 1)
+                    if backbone_done is not None:
+                        self.side.wait_event(backbone_done)  # ordered before the searches that _finish queues
                     cur = self._finish((i + 1) & 1)  # host waits for the (short) subsampling chain only
             yield self.model.forward_tail(state)
             i += 1

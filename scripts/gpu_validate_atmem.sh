@@ -13,3 +13,5 @@ bash scripts/gpu_repeat.sh ${TAG}_on 2 RDM_GEMM_ATMEM=1
 timeout 200 python scripts/bench_gather.py 2>&1 | tail -16
 RDM_GATHER_PERSIST=1 timeout 200 python scripts/bench_gather.py 2>&1 | tail -16
 bash scripts/gpu_repeat.sh ${TAG}_persist 2 RDM_GATHER_PERSIST=1
+# side-stream searches deferred behind the backbone (gather roofline inside the pipelined region)
+bash scripts/gpu_repeat.sh ${TAG}_defer 2 RDM_PIPE_DEFER_SEARCH=1
