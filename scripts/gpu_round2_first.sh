@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 first step: validate the A-in-TMEM GEMM variant (gemm_tc_atmem.cu) end to end before making it the default.
 #   1. the gated parity test of the variant           2. the WHOLE GPU suite with the variant forced on
-#   3. bench A/B (default kernel vs variant), 2 runs each.        Usage: gpurun -- 'bash scripts/gpu_validate_atmem.sh <tag>'
+#   3. bench A/B (default kernel vs variant), 2 runs each.        Usage: gpurun -- 'bash scripts/gpu_round2_first.sh <tag>'
 TAG=${1:-atmem}
 mkdir -p gpurun_out
 RDM_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_experimental_gpu.py -m gpu -q --timeout 60 -p no:cacheprovider 2>&1 | tail -3
