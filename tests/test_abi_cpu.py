@@ -102,3 +102,16 @@ def test_bench_reference_arm_emits_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_bench_gpu_arm_fails_loudly_without_gpu():
+    """The product arm of bench.py has no CPU path: without a CUDA device it must exit non-zero with a clear message and
+    print no JSON line (a silent fallback would void the measurement)."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode != 0
+    assert "CUDA device" in out.stderr and "no CPU path" in out.stderr
+    assert out.stdout.strip() == ""
