@@ -392,6 +392,53 @@ size_t rdm_match_workspace(const rdm_match_desc* h_desc, int nc, int nc_ref, int
 int rdm_match_forward(const rdm_match_desc* h_desc, const rdm_match_io* h_io, rdm_match_result* h_result, void* workspace,
                       size_t workspace_bytes, rdm_stream_t stream);
 
+/* ---- index_select(data, index, dim=0) (geotransformer/modules/ops/index_select.py:4-30) on rows of `row_words` 4-byte
+ * words: out[i, :] = data[index[i], :], i < count. *err_flag (device int, zeroed by the caller, may be NULL) is set when
+ * an index falls outside [0, rows): the host shim raises, as torch.index_select does. */
+int rdm_index_select(const void* data, int64_t rows, int row_words, const void* index, int index_bytes, int64_t count,
+                     void* out, int* err_flag, rdm_stream_t stream);
+
+/* ---- apply_transform (geotransformer/modules/ops/transformation.py:7-60): out = points @ R^T + t for [batch, n, 3]
+ * points and [batch, 4, 4] transforms (or one [4,4] for all batches: shared_transform = 1); normals rotate only. */
+int rdm_apply_transform(const float* points, const float* transforms, int batch, int64_t n_per_batch, int shared_transform,
+                        float* out, const float* normals, float* normals_out, rdm_stream_t stream);
+
+/* ---- neighbour-count histogram of calibrate_neighbors_stack_mode (geotransformer/utils/data.py:207-211):
+ * hist_accum[c] += #{q : counts[q] == c} for c < hist_n (counts = rdm_radius_search's out_counts). */
+int rdm_neighbor_histogram(const int* counts, int n, int hist_n, int* hist_accum, rdm_stream_t stream);
+
+/* ---- ground-truth superpoint correspondences, train / val path (geotransformer/modules/registration/matching.py).
+ * rdm_node_correspondences = get_node_correspondences (:252-366, sphere_filter = 1) and get_node_overlap (:368-436,
+ * sphere_filter = 0): src nodes / patch points are transformed by `transform` [4,4] (may be NULL) on the fly; masks are 0/1
+ * bytes or NULL (= all valid). out_overlaps [M,N] (0 where the pair is filtered out); out_intersect [M,N] (may be NULL) is
+ * the sphere-test matrix (return_mask = True); out_corr_indices [M*N,2] / out_corr_overlaps [M*N] / out_count receive
+ * the row-major compaction of the pairs with overlap > 0 (all three may be NULL). K <= 256. */
+size_t rdm_node_correspondences_workspace(int M, int N);
+int rdm_node_correspondences(const float* ref_nodes, const float* src_nodes, const float* ref_knn_points,
+                             const float* src_knn_points, const float* transform, float pos_radius, int M, int N, int K,
+                             const unsigned char* ref_masks, const unsigned char* src_masks,
+                             const unsigned char* ref_knn_masks, const unsigned char* src_knn_masks, int sphere_filter,
+                             float* out_overlaps, unsigned char* out_intersect, int64_t* out_corr_indices,
+                             float* out_corr_overlaps, int* out_count, void* workspace, size_t workspace_bytes,
+                             rdm_stream_t stream);
+/* torch.nonzero of a [rows, cols] matrix in row-major order: entries > 0 of `mat` (float) or != 0 of `bmat` (bytes),
+ * exactly one of the two given; out_indices [rows*cols, 2], out_values (may be NULL), *out_count. */
+int rdm_compact_nonzero(const float* mat, const unsigned char* bmat, int rows, int cols, int64_t* out_indices,
+                        float* out_values, int* out_count, rdm_stream_t stream);
+/* get_node_correspondences_disance (matching.py:441-503): mutual-nearest-node mask [M,N] under `transform`. */
+int rdm_node_distance_mask(const float* ref_nodes, const float* src_nodes, const float* transform, float pos_radius, int M,
+                           int N, const unsigned char* ref_masks, const unsigned char* src_masks, unsigned char* out_mask,
+                           rdm_stream_t stream);
+
+/* ---- registration_with_ransac_from_correspondences (geotransformer/utils/open3d.py:173-203; open3d's CPU RANSAC, called
+ * per pair by experiments/infer.py:76-82 with 50 000 iterations) on the GPU: src/ref [C,3] are matched row by row.
+ * Deterministic for a given seed. out_transform [4,4]; out_meta[0] = inliers of the winner, [1] = its iteration. */
+size_t rdm_ransac_workspace(int num_correspondences);
+int rdm_ransac_correspondences(const float* src_points, const float* ref_points, int num_correspondences,
+                               float distance_threshold, int ransac_n, int num_iterations, unsigned long long seed,
+                               float* out_transform, int* out_meta, void* workspace, size_t workspace_bytes,
+                               rdm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

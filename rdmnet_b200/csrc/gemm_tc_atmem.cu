@@ -1,5 +1,5 @@
-// EXPERIMENTAL (off by default, RDM_GEMM_ATMEM=1 / rdm_debug_gemm_variant(1) to enable; not yet validated on hardware):
-// the tcgen05 3-term-split GEMM of gemm_tc.cu with the A operand in TENSOR MEMORY.
+// DEFAULT tcgen05 GEMM (RDM_GEMM_ATMEM=0 / rdm_debug_gemm_variant(0) select the all-shared-memory kernel of gemm_tc.cu):
+// the 3-term-split tf32 GEMM with the A operand in TENSOR MEMORY. Validated in round 2 on the whole GPU suite and the bench.
 //
 // Why: gemm_tc.cu is shared-memory-bandwidth bound (scripts/gemm_timeline.py: ~1100 cycles per 128 x 64 x 32 k-block for
 // ~100 cycles of MMA). Per k-block it moves 24 KB (TMA) + 24 KB (converter reads) + 48 KB (converter writes of hi / lo)
@@ -264,7 +264,7 @@ int launch_tca(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, 
 }  // namespace
 
 // Same contract as rdm_linear_tc (gemm_tc.cu). Returns -1 when the variant is off or the shape does not qualify.
-int g_gemm_variant = -1;  // -1 unknown (read RDM_GEMM_ATMEM), 0 off, 1 on
+int g_gemm_variant = -1;  // -1 unknown (read RDM_GEMM_ATMEM, default on), 0 off, 1 on
 extern "C" void rdm_debug_gemm_variant(int v) { g_gemm_variant = v ? 1 : 0; }
 
 int rdm_linear_tc_atmem(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N, int K,
@@ -272,7 +272,7 @@ int rdm_linear_tc_atmem(const float* A, int lda, const float* B, int ldb, const 
                         int* out_stats_fused, cudaStream_t stream) {
   if (g_gemm_variant < 0) {
     const char* e = getenv("RDM_GEMM_ATMEM");
-    g_gemm_variant = (e && e[0] == '1') ? 1 : 0;
+    g_gemm_variant = (e && e[0] == '0') ? 0 : 1;
   }
   if (g_gemm_variant != 1) return -1;
   *out_splits = 1;

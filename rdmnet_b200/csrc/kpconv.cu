@@ -269,156 +269,12 @@ __global__ void __launch_bounds__(256) kpconv_gather_kernel(const float* __restr
 // at the first slot that is padding for every group. No block barrier, 2.5 KB of shared memory per warp.
 #define KP_WS 20  // influence row stride (floats): 80 B keeps STS.128 / LDS.128 of interleaved rows conflict free
 
-template <int VEC>
-struct FVec;
-template <>
-struct FVec<4> {
-  typedef float4 T;
-};
-template <>
-struct FVec<2> {
-  typedef float2 T;
-};
-
-template <int L, bool SPLIT, int VEC, typename IdxT>
-__global__ void __launch_bounds__(128, VEC == 4 ? 4 : 7) kpconv_gather_v3_kernel(const float* __restrict__ feats,
-                                                                  const unsigned char* __restrict__ rowpos,
-                                                                  const float* __restrict__ q_pts,
-                                                                  const float* __restrict__ s_pts,
-                                                                  const IdxT* __restrict__ idx, const KPts kp,
-                                                                  float inv_sigma, int M, int N, int H, int C, int NS,
-                                                                  const int* __restrict__ order,
-                                                                  float* __restrict__ out) {
-  constexpr int G = 32 / L;
-  constexpr int STEP = SPLIT ? 32 : L;  // neighbour slots per chunk (per query)
-  __shared__ __align__(16) float s_w[4][32 * KP_WS];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane / L, t = lane % L;
-  const int gw = blockIdx.x * 4 + warp;
-  int m, slice;
-  if (SPLIT || L == 32) {
-    m = gw / NS;
-    slice = gw - m * NS;
-  } else {
-    m = gw * G + g;
-    slice = 0;
-  }
-  const bool qvalid = m < M;
-  if (__all_sync(FULL_MASK, !qvalid)) return;
-  if (qvalid && order != nullptr) m = order[m];  // spatially coherent walk: co-resident warps share neighbour rows
-  const int mm = qvalid ? m : M - 1;
-  const float qx = q_pts[3 * (size_t)mm], qy = q_pts[3 * (size_t)mm + 1], qz = q_pts[3 * (size_t)mm + 2];
-  const IdxT* row = idx + (size_t)mm * H;
-  const float* fbase = feats + slice * (VEC * L) + VEC * t;
-  float acc[KP_K][VEC];
-#pragma unroll
-  for (int k = 0; k < KP_K; k++)
-#pragma unroll
-    for (int v = 0; v < VEC; v++) acc[k][v] = 0.f;
-  int npos = 0;
-  float* wtile = s_w[warp];
-  float4* wrow = (float4*)(wtile + (t * G + g) * KP_WS);  // rows interleaved over groups: (u, g) -> u*G + g
-  const int myslot = SPLIT ? lane : t;
-  // slot -> neighbour index of this lane (or -1); prefetched one chunk ahead
-  auto load_j = [&](int h) -> int {
-    if (qvalid && h < H) {
-      long long jj = (long long)row[h];
-      if (jj < N) return (int)jj;
-    }
-    return -1;
-  };
-  int j = load_j(myslot);
-  for (int h0 = 0; h0 < H; h0 += STEP) {
-    if (!__any_sync(FULL_MASK, j >= 0)) break;  // rows are valid-first: nothing but padding from here on
-    const int jn = load_j(h0 + STEP + myslot);  // next chunk's index: in flight during the influence math
-    // ---- (A) influences of this lane's slot
-    float w[16];
-    if (j >= 0) {
-      const float dx = s_pts[3 * (size_t)j] - qx, dy = s_pts[3 * (size_t)j + 1] - qy, dz = s_pts[3 * (size_t)j + 2] - qz;
-#pragma unroll
-      for (int k = 0; k < KP_K; k++) {
-        const float ex = dx - kp.x[k], ey = dy - kp.y[k], ez = dz - kp.z[k];
-        const float d = sqrt_approx(fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
-        w[k] = fmaxf(0.f, fmaf(-d, inv_sigma, 1.f));  // kpconv.py:98-99
-      }
-      npos += rowpos[j];
-    } else {
-#pragma unroll
-      for (int k = 0; k < KP_K; k++) w[k] = 0.f;
-    }
-    w[15] = 0.f;
-    __syncwarp();  // previous chunk's readers are done
-    wrow[0] = make_float4(w[0], w[1], w[2], w[3]);
-    wrow[1] = make_float4(w[4], w[5], w[6], w[7]);
-    wrow[2] = make_float4(w[8], w[9], w[10], w[11]);
-    wrow[3] = make_float4(w[12], w[13], w[14], w[15]);
-    __syncwarp();
-    // ---- (B) each group streams its L rows of the chunk
-    // trip count = last valid slot of any group (+1), known before the loop so that it unrolls and the loads batch
-    const unsigned vb = __ballot_sync(FULL_MASK, j >= 0);
-    int nu = 0;
-#pragma unroll
-    for (int gg = 0; gg < G; gg++) {
-      const unsigned mg = (L == 32) ? vb : ((vb >> (gg * L)) & ((1u << (L & 31)) - 1u));
-      nu = max(nu, 32 - __clz(mg));
-    }
-#pragma unroll 4
-    for (int u = 0; u < nu; u++) {
-      const int ju = __shfl_sync(FULL_MASK, j, g * L + u);
-      float f[VEC];
-#pragma unroll
-      for (int v = 0; v < VEC; v++) f[v] = 0.f;
-      if (ju >= 0) {
-        const typename FVec<VEC>::T fv = __ldg((const typename FVec<VEC>::T*)(fbase + (size_t)ju * C));
-        f[0] = fv.x;
-        f[1] = fv.y;
-        if constexpr (VEC == 4) {
-          f[2] = fv.z;
-          f[3] = fv.w;
-        }
-      }
-      const float4* wp = (const float4*)(wtile + (u * G + g) * KP_WS);
-      const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
-      const float ww[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
-#pragma unroll
-      for (int k = 0; k < KP_K; k++)
-#pragma unroll
-        for (int v = 0; v < VEC; v++) acc[k][v] = fmaf(ww[k], f[v], acc[k][v]);
-    }
-    j = jn;
-  }
-  // neighbour count of the query (kpconv.py:113-116) and, in SPLIT mode, the sum of the groups' partial results
-  if (SPLIT) {
-    npos = warp_sum_i(npos);
-#pragma unroll
-    for (int o = L; o < 32; o <<= 1)
-#pragma unroll
-      for (int k = 0; k < KP_K; k++)
-#pragma unroll
-        for (int v = 0; v < VEC; v++) acc[k][v] += __shfl_xor_sync(FULL_MASK, acc[k][v], o);
-    if (g != 0) return;
-  } else {
-#pragma unroll
-    for (int o = L >> 1; o > 0; o >>= 1) npos += __shfl_xor_sync(FULL_MASK, npos, o);
-  }
-  if (!qvalid) return;
-  const float inv = 1.f / (float)max(npos, 1);
-  float* op = out + (size_t)m * KP_K * C + slice * (VEC * L) + VEC * t;
-#pragma unroll
-  for (int k = 0; k < KP_K; k++) {
-    if constexpr (VEC == 4)
-      *(float4*)(op + (size_t)k * C) = make_float4(acc[k][0] * inv, acc[k][1] * inv, acc[k][2] * inv, acc[k][3] * inv);
-    else
-      *(float2*)(op + (size_t)k * C) = make_float2(acc[k][0] * inv, acc[k][1] * inv);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------- gather, v4
-// Same warp-autonomous mapping as v3, with the two Blackwell-specific changes that the ncu captures of v3 asked for
+// Two Blackwell-specific choices, both answers to ncu captures of the register-staged predecessor
 // (long-scoreboard stalls at 25 % occupancy, FMA pipe the next limiter):
 //   * neighbour rows are STAGED IN SHARED MEMORY with cp.async (LDGSTS): the 32 rows of a chunk land in a per-warp
 //     buffer while the previous half-chunk is being multiplied, so 16 rows per warp are in flight without holding a
-//     single register (v3: 4 per lane group, each pinning a float4);
+//     single register (the predecessor held 4 per lane group, each pinning a float4);
 //   * the 15 x 4 accumulators of a lane are 30 packed pairs updated with FFMA2 (fma.rn.f32x2, scalar-broadcast
 //     influence operand): half the issue slots and register-operand traffic per row.
 // Shared memory per warp: 32 rows x L x 16 B + the 32 x 20 influence tile (L = 8: 6.5 KB, 16: 10.5 KB, 32: 18.5 KB).
@@ -577,203 +433,162 @@ __global__ void __launch_bounds__(128, 4) kpconv_gather_v4_kernel(const float* _
     *(float4*)(op + (size_t)k * C) = make_float4(acc[k][0].x * inv, acc[k][0].y * inv, acc[k][1].x * inv, acc[k][1].y * inv);
 }
 
-// EXPERIMENTAL (RDM_GATHER_PERSIST=1, off by default, not yet measured): persistent form of the v4 gather. 148 x 4 CTAs stay
-// resident and every warp pulls batches of 4 consecutive work items (= neighbouring queries in the cell-sorted walk order:
-// the L1 reuse of the CTA-per-4-items form is kept in time instead of in space) from a global counter - no ragged last wave,
-// no CTA relaunch cost, and the warps that drew dense neighbourhoods no longer decide the kernel time alone. The item body
-// is a verbatim copy of kpconv_gather_v4_kernel's (kept separate so that the default kernel's code generation is untouched).
-// cnt[0] = next item, cnt[1] = warps finished; the last warp out re-arms both for the next launch.
-template <int L, bool SPLIT, typename IdxT>
-__global__ void __launch_bounds__(128, 4) kpconv_gather_v4p_kernel(const float* __restrict__ feats,
+// ---------------------------------------------------------------------------------------------- gather, sparse (default)
+// The influence w[m,h,k] = max(0, 1 - |s_h - q_m - kp_k| / sigma) is SPARSE: sigma is 0.47 of the search radius, so a
+// neighbour lies inside the support of only ~1.7 of the 15 kernel points (measured on the bundled KITTI pair at every
+// stage: 11 % non-zero). The dense kernels above spend 89 % of their FMAs on zeros. Here a warp owns one (query, channel
+// slice) and works in two phases:
+//   (A) lane = neighbour slot: the 15 influences of the slot; for every kernel point a ballot compacts the non-zero
+//       (row, w) pairs into that kernel point's entry list in shared memory (ascending slot order, so the summation order
+//       is the dense kernels');
+//   (B) kernel point by kernel point the warp walks the entry list: one broadcast LDS.64 per entry, one coalesced row
+//       load per lane (LDG.32 / .64 / .128 x NV straight from L1 / L2 - a row is touched ~1.7 times), CPL*NV FMAs, and a
+//       single accumulator set that is scaled and stored when the list ends. ~8 instructions per entry instead of ~50
+//       per neighbour row, no 15-fold accumulator file (60 -> 4..16 registers): 2 - 5 x fewer issued instructions on the
+//       C_in >= 128 layers and twice the resident warps.
+// Lists are padded with (row 0, w 0) entries to a multiple of 4 so that the walk is unrolled by 4 without predicates.
+template <int CPL>
+struct GVec;
+template <>
+struct GVec<1> {
+  typedef float T;
+};
+template <>
+struct GVec<2> {
+  typedef float2 T;
+};
+template <>
+struct GVec<4> {
+  typedef float4 T;
+};
+__device__ __forceinline__ void gv_fma(float w, const float f, float* a) { a[0] = fmaf(w, f, a[0]); }
+__device__ __forceinline__ void gv_fma(float w, const float2 f, float* a) {
+  a[0] = fmaf(w, f.x, a[0]);
+  a[1] = fmaf(w, f.y, a[1]);
+}
+__device__ __forceinline__ void gv_fma(float w, const float4 f, float* a) {
+  a[0] = fmaf(w, f.x, a[0]);
+  a[1] = fmaf(w, f.y, a[1]);
+  a[2] = fmaf(w, f.z, a[2]);
+  a[3] = fmaf(w, f.w, a[3]);
+}
+__device__ __forceinline__ void gv_store(float* p, const float* a, float s, float) { p[0] = a[0] * s; }
+__device__ __forceinline__ void gv_store(float* p, const float* a, float s, float2) { *(float2*)p = make_float2(a[0] * s, a[1] * s); }
+__device__ __forceinline__ void gv_store(float* p, const float* a, float s, float4) {
+  *(float4*)p = make_float4(a[0] * s, a[1] * s, a[2] * s, a[3] * s);
+}
+
+// CPL channels per lane and vector, NV vectors per lane: the warp's slice is 32 * CPL * NV channels, NS slices per row
+template <int CPL, int NV, typename IdxT>
+__global__ void __launch_bounds__(128) kpconv_gather_sparse_kernel(const float* __restrict__ feats,
                                                                    const unsigned char* __restrict__ rowpos,
-                                                                   const float* __restrict__ q_pts,
-                                                                   const float* __restrict__ s_pts,
-                                                                   const IdxT* __restrict__ idx, const KPts kp,
-                                                                   float inv_sigma, int M, int N, int H, int C, int NS,
-                                                                   const int* __restrict__ order, float* __restrict__ out,
-                                                                   int total_items, int* __restrict__ cnt) {
+                                                                   const float* __restrict__ q_pts, const float* __restrict__ s_pts,
+                                                                   const IdxT* __restrict__ idx, const KPts kp, float inv_sigma,
+                                                                   int M, int N, int H, int C, int NS, int HC,
+                                                                   const int* __restrict__ order, float* __restrict__ out) {
   pdl_trigger();
   pdl_wait();
-  extern __shared__ float4 s_dyn[];
-  auto item = [&](const int gw) {
-    constexpr int G = 32 / L;
-    constexpr int STEP = SPLIT ? 32 : L;  // neighbour slots per chunk (per query)
-    constexpr int HALF = L / 2;
-    constexpr int WARP_F4 = 32 * L + 32 * KP_WS / 4;  // float4 per warp: row buffer + influence tile
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane / L, t = lane % L;
-    int m, slice;
-    if (SPLIT || L == 32) {
-      m = gw / NS;
-      slice = gw - m * NS;
+  typedef typename GVec<CPL>::T V;
+  extern __shared__ int2 s_lists[];  // [4 warps][15][HC]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long gw = (long long)blockIdx.x * 4 + warp;
+  const int mi = (int)(gw / NS), slice = (int)(gw - (long long)mi * NS);
+  if (mi >= M) return;
+  const int m = order != nullptr ? order[mi] : mi;
+  const float qx = q_pts[3 * (size_t)m], qy = q_pts[3 * (size_t)m + 1], qz = q_pts[3 * (size_t)m + 2];
+  const IdxT* row = idx + (size_t)m * H;
+  int2* lst = s_lists + (size_t)warp * KP_K * HC;
+  const unsigned lt = (1u << lane) - 1u;
+  int cnt[KP_K];
+#pragma unroll
+  for (int k = 0; k < KP_K; k++) cnt[k] = 0;
+  int npos = 0;
+  // ---- (A) influences -> per-kernel-point entry lists
+  for (int h0 = 0; h0 < H; h0 += 32) {
+    const int h = h0 + lane;
+    int j = -1;
+    if (h < H) {
+      const long long jj = (long long)row[h];
+      if (jj < N) j = (int)jj;
+    }
+    if (!__any_sync(FULL_MASK, j >= 0)) break;  // rows are valid-first: nothing but padding from here on
+    float w[16];
+    if (j >= 0) {
+      influences16(s_pts[3 * (size_t)j] - qx, s_pts[3 * (size_t)j + 1] - qy, s_pts[3 * (size_t)j + 2] - qz, kp, inv_sigma, w);
+      npos += rowpos[j];
     } else {
-      m = gw * G + g;
-      slice = 0;
+#pragma unroll
+      for (int k = 0; k < 16; k++) w[k] = 0.f;
     }
-    const bool qvalid = m < M;
-    if (__all_sync(FULL_MASK, !qvalid)) return;
-    if (qvalid && order != nullptr) m = order[m];
-    const int mm = qvalid ? m : M - 1;
-    const float qx = q_pts[3 * (size_t)mm], qy = q_pts[3 * (size_t)mm + 1], qz = q_pts[3 * (size_t)mm + 2];
-    const IdxT* row = idx + (size_t)mm * H;
-    const float* fbase = feats + slice * (4 * L) + 4 * t;
-    float4* rowbuf = s_dyn + (size_t)warp * WARP_F4;           // [32 rows][L] float4; row (g, u) at (g * L + u) * L
-    float* wtile = reinterpret_cast<float*>(rowbuf + 32 * L);  // [32][KP_WS]
-    float2 acc[KP_K][2];
-  #pragma unroll
-    for (int k = 0; k < KP_K; k++) acc[k][0] = acc[k][1] = make_float2(0.f, 0.f);
-    int npos = 0;
-    float4* wrow = (float4*)(wtile + (t * G + g) * KP_WS);  // rows interleaved over groups: (u, g) -> u*G + g
-    const int myslot = SPLIT ? lane : t;
-    auto load_j = [&](int h) -> int {
-      if (qvalid && h < H) {
-        long long jj = (long long)row[h];
-        if (jj < N) return (int)jj;
-      }
-      return -1;
-    };
-    // asynchronous copy of rows [u0, u0 + HALF) of every group for the chunk whose slot indices are `jc`; one commit group
-    auto issue_half = [&](int jc, int u0) {
-  #pragma unroll
-      for (int u = u0; u < u0 + HALF; u++) {
-        const int ju = __shfl_sync(FULL_MASK, jc, g * L + u);
-        if (ju >= 0) gather_cp16(rowbuf + (g * L + u) * L + t, fbase + (size_t)ju * C);
-      }
-      gather_commit();
-    };
-    int j = load_j(myslot);
-    int jn = load_j(STEP + myslot);
-    issue_half(j, 0);
-    issue_half(j, HALF);
-    for (int h0 = 0; h0 < H; h0 += STEP) {
-      if (!__any_sync(FULL_MASK, j >= 0)) break;  // rows are valid-first: nothing but padding from here on
-      const int jn2 = load_j(h0 + 2 * STEP + myslot);
-      // ---- (A) influences of this lane's slot
-      float w[16];
-      if (j >= 0) {
-        influences16(s_pts[3 * (size_t)j] - qx, s_pts[3 * (size_t)j + 1] - qy, s_pts[3 * (size_t)j + 2] - qz, kp, inv_sigma, w);
-        npos += rowpos[j];
-      } else {
-  #pragma unroll
-        for (int k = 0; k < 16; k++) w[k] = 0.f;
-      }
-      wrow[0] = make_float4(w[0], w[1], w[2], w[3]);
-      wrow[1] = make_float4(w[4], w[5], w[6], w[7]);
-      wrow[2] = make_float4(w[8], w[9], w[10], w[11]);
-      wrow[3] = make_float4(w[12], w[13], w[14], w[15]);
-      const unsigned vb = __ballot_sync(FULL_MASK, j >= 0);
-      int nu = 0;
-  #pragma unroll
-      for (int gg = 0; gg < G; gg++) {
-        const unsigned mg = (L == 32) ? vb : ((vb >> (gg * L)) & ((1u << (L & 31)) - 1u));
-        nu = max(nu, 32 - __clz(mg));
-      }
-      // ---- (B) two halves: multiply the landed rows, then refill their slots with the next chunk's rows
-  #pragma unroll
-      for (int half = 0; half < 2; half++) {
-        gather_wait<1>();  // this half's rows (the older of the two pending groups) have landed for this lane ...
-        __syncwarp();      // ... and for the whole warp; also orders the influence tile stores above
-        const int ue = min(nu, (half + 1) * HALF);
-  #pragma unroll 4
-        for (int u = half * HALF; u < ue; u++) {
-          const int ju = __shfl_sync(FULL_MASK, j, g * L + u);
-          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ju >= 0) f = rowbuf[(g * L + u) * L + t];
-          const float4* wp = (const float4*)(wtile + (u * G + g) * KP_WS);
-          const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
-          const float ww[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
-          const float2 fa = make_float2(f.x, f.y), fb = make_float2(f.z, f.w);
-  #pragma unroll
-          for (int k = 0; k < KP_K; k++) {
-            acc[k][0] = ffma2(ww[k], fa, acc[k][0]);
-            acc[k][1] = ffma2(ww[k], fb, acc[k][1]);
-          }
-        }
-        __syncwarp();  // every lane is done with this half's rows (and, after the second half, with the influence tile)
-        issue_half(jn, half * HALF);
-      }
-      j = jn;
-      jn = jn2;
-    }
-    gather_wait<0>();
-    if (SPLIT) {
-      npos = warp_sum_i(npos);
-  #pragma unroll
-      for (int o = L; o < 32; o <<= 1)
-  #pragma unroll
-        for (int k = 0; k < KP_K; k++) {
-          acc[k][0].x += __shfl_xor_sync(FULL_MASK, acc[k][0].x, o);
-          acc[k][0].y += __shfl_xor_sync(FULL_MASK, acc[k][0].y, o);
-          acc[k][1].x += __shfl_xor_sync(FULL_MASK, acc[k][1].x, o);
-          acc[k][1].y += __shfl_xor_sync(FULL_MASK, acc[k][1].y, o);
-        }
-      if (g != 0) return;
-    } else {
-  #pragma unroll
-      for (int o = L >> 1; o > 0; o >>= 1) npos += __shfl_xor_sync(FULL_MASK, npos, o);
-    }
-    if (!qvalid) return;
-    const float inv = 1.f / (float)max(npos, 1);
-    float* op = out + (size_t)m * KP_K * C + slice * (4 * L) + 4 * t;
-  #pragma unroll
-    for (int k = 0; k < KP_K; k++)
-      *(float4*)(op + (size_t)k * C) = make_float4(acc[k][0].x * inv, acc[k][0].y * inv, acc[k][1].x * inv, acc[k][1].y * inv);
-
-  };
-  constexpr int BATCH = 4;
-  for (;;) {
-    int w0 = 0;
-    if ((threadIdx.x & 31) == 0) w0 = atomicAdd(&cnt[0], BATCH);
-    w0 = __shfl_sync(FULL_MASK, w0, 0);
-    if (w0 >= total_items) break;
-    for (int b = 0; b < BATCH && w0 + b < total_items; b++) {
-      item(w0 + b);
-      __syncwarp();
+#pragma unroll
+    for (int k = 0; k < KP_K; k++) {
+      const bool nz = w[k] > 0.f;
+      const unsigned mk = __ballot_sync(FULL_MASK, nz);
+      if (nz) lst[k * HC + cnt[k] + __popc(mk & lt)] = make_int2(j, __float_as_int(w[k]));
+      cnt[k] += __popc(mk);
     }
   }
-  if ((threadIdx.x & 31) == 0) {
-    const int nwarps = gridDim.x * (blockDim.x >> 5);
-    if (atomicAdd(&cnt[1], 1) == nwarps - 1) {  // last warp of the grid: re-arm the counters
-      cnt[0] = 0;
-      cnt[1] = 0;
-      __threadfence();
+  // pad every list with three no-op entries (row 0 exists: N >= 1; weight 0)
+  if (lane < 3) {
+#pragma unroll
+    for (int k = 0; k < KP_K; k++) lst[k * HC + cnt[k] + lane] = make_int2(0, 0);
+  }
+  npos = warp_sum_i(npos);
+  const float inv = 1.f / (float)max(npos, 1);  // kpconv.py:113-116
+  __syncwarp();
+  // ---- (B) one accumulator set, kernel point by kernel point
+  const float* fbase = feats + (size_t)slice * (32 * CPL * NV) + CPL * lane;
+  float* obase = out + (size_t)m * KP_K * C + (size_t)slice * (32 * CPL * NV) + CPL * lane;
+#pragma unroll
+  for (int k = 0; k < KP_K; k++) {
+    float acc[NV][CPL];
+#pragma unroll
+    for (int v = 0; v < NV; v++)
+#pragma unroll
+      for (int c = 0; c < CPL; c++) acc[v][c] = 0.f;
+    const int2* lk = lst + k * HC;
+    const int n = cnt[k];
+    for (int e = 0; e < n; e += 4) {
+      int2 en[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) en[u] = lk[e + u];
+      V f[4][NV];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int v = 0; v < NV; v++) f[u][v] = __ldg((const V*)(fbase + (size_t)en[u].x * C + v * (32 * CPL)));
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int v = 0; v < NV; v++) gv_fma(__int_as_float(en[u].y), f[u][v], acc[v]);
     }
+#pragma unroll
+    for (int v = 0; v < NV; v++) gv_store(obase + (size_t)k * C + v * (32 * CPL), acc[v], inv, V());
   }
 }
 
-int g_gather_persist = -1;  // -1: read RDM_GATHER_PERSIST; 0 off; 1 on (experimental persistent gather)
-extern "C" void rdm_debug_gather_persist(int v) { g_gather_persist = v ? 1 : 0; }
+template <int CPL, int NV, typename IdxT>
+static int launch_sparse(const float* feats, const unsigned char* rowpos, const float* q, const float* s, const IdxT* idx,
+                         const KPts& kp, float inv_sigma, int M, int N, int H, int C, const int* order, float* out,
+                         cudaStream_t stream) {
+  const int NS = C / (32 * CPL * NV), HC = H + 3;
+  const size_t smem = (size_t)4 * KP_K * HC * sizeof(int2);
+  if (smem > 48 * 1024)
+    RDM_CUDA(cudaFuncSetAttribute(kpconv_gather_sparse_kernel<CPL, NV, IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long warps = (long long)M * NS;
+  RDM_CUDA(rdm_launch_pdl(kpconv_gather_sparse_kernel<CPL, NV, IdxT>, dim3(cdiv(warps, 4)), dim3(128), smem, stream, feats, rowpos, q, s,
+                          idx, kp, inv_sigma, M, N, H, C, NS, HC, order, out));
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
 
 template <int L, bool SPLIT, typename IdxT>
 static int launch_v4(long long warps, const float* feats, const unsigned char* rowpos, const float* q, const float* s,
                      const IdxT* idx, const KPts& kp, float inv_sigma, int M, int N, int H, int C, int NS, const int* order,
                      float* out, cudaStream_t stream) {
   const size_t smem = 4 * (size_t)(32 * L + 32 * KP_WS / 4) * sizeof(float4);
-  static bool attr = false;
-  if (!attr && smem > 48 * 1024) {
+  if (smem > 48 * 1024)  // per-device attribute: set on every call (sub-microsecond) rather than cached per process
     RDM_CUDA(cudaFuncSetAttribute(kpconv_gather_v4_kernel<L, SPLIT, IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
-  static int* counters = nullptr;
-  if (g_gather_persist < 0) {
-    const char* e = getenv("RDM_GATHER_PERSIST");
-    g_gather_persist = (e && e[0] == '1') ? 1 : 0;
-  }
-  if (g_gather_persist == 1 && warps > 148 * 16) {
-    if (counters == nullptr) {
-      RDM_CUDA(cudaMalloc(&counters, 2 * sizeof(int)));
-      RDM_CUDA(cudaMemset(counters, 0, 2 * sizeof(int)));
-    }
-    static bool attr_p = false;
-    if (!attr_p && smem > 48 * 1024) {
-      RDM_CUDA(cudaFuncSetAttribute(kpconv_gather_v4p_kernel<L, SPLIT, IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_p = true;
-    }
-    RDM_CUDA(rdm_launch_pdl(kpconv_gather_v4p_kernel<L, SPLIT, IdxT>, dim3(148 * 4), dim3(128), smem, stream, feats, rowpos, q, s, idx, kp,
-                            inv_sigma, M, N, H, C, NS, order, out, (int)warps, counters));
-    RDM_LAUNCH_CHECK();
-    return RDM_OK;
-  }
   RDM_CUDA(rdm_launch_pdl(kpconv_gather_v4_kernel<L, SPLIT, IdxT>, dim3(cdiv(warps, 4)), dim3(128), smem, stream, feats, rowpos, q, s,
                           idx, kp, inv_sigma, M, N, H, C, NS, order, out));
   RDM_LAUNCH_CHECK();
@@ -801,12 +616,23 @@ static int launch_gather(const float* feats, const unsigned char* rowpos, const 
   }
   if (C == 32 || C == 64 || (C % 128 == 0 && C <= 4096)) {
     // candidates from the cheapest mapping (largest L, groups = different queries) to the most parallel one
-    // (small L, groups split one query's neighbour list); take the first that puts >= 16 warps on each of 148 SMs.
-    // A group of L lanes covers VEC*L channels. RDM_GATHER_VEC (debug knob, read once) selects 2 or 4 channels/lane.
-    static int vec = 0;
-    if (vec == 0) {
-      const char* e = getenv("RDM_GATHER_VEC");
-      vec = (e && e[0] == '2') ? 2 : 4;
+    // (small L, groups split one query's neighbour list); take the first that puts >= `wps` warps on each of 148 SMs.
+    static int dense = -1;
+    if (dense < 0) {
+      const char* e = getenv("RDM_GATHER_DENSE");  // A/B knob: 1 selects the dense cp.async/FFMA2 kernels below
+      dense = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (!dense && H <= 1024) {
+      // widest slice per warp (influences computed once per row) that still puts >= 8 warps on every SM
+      const long long want_w = 148LL * 8;
+#define SPARSE(CPLv, NVv) \
+  return launch_sparse<CPLv, NVv, IdxT>(feats, rowpos, q, s, idx, kp, inv_sigma, M, N, H, C, order, out, stream)
+      if (C == 32) SPARSE(1, 1);
+      if (C == 64) SPARSE(2, 1);
+      if (C % 512 == 0 && (long long)M * (C / 512) >= want_w) SPARSE(4, 4);
+      if (C % 256 == 0 && (long long)M * (C / 256) >= want_w) SPARSE(4, 2);
+      SPARSE(4, 1);
+#undef SPARSE
     }
     static int wps = 0;
     if (wps == 0) {
@@ -814,12 +640,6 @@ static int launch_gather(const float* feats, const unsigned char* rowpos, const 
       wps = (e && atoi(e) > 0) ? atoi(e) : 8;  // measured (profiles/r01e): 8 beats 16 on the strided / deep layers
     }
     const long long want = 148LL * wps;
-    static int ver = 0;
-    if (ver == 0) {
-      const char* e = getenv("RDM_GATHER_V");  // debug knob: RDM_GATHER_V=3 selects the register-staged v3 kernels
-      ver = (e && e[0] == '3') ? 3 : 4;
-    }
-    if (ver == 4 && vec == 4) {
 #define GATHER4(Lv, SPLITv, warps, NSv) \
   return launch_v4<Lv, SPLITv, IdxT>((warps), feats, rowpos, q, s, idx, kp, inv_sigma, M, N, H, C, (NSv), order, out, stream)
       if (C == 32) {
@@ -835,39 +655,8 @@ static int launch_gather(const float* feats, const unsigned char* rowpos, const 
         GATHER4(8, true, (long long)M * (C / 32), C / 32);
       }
 #undef GATHER4
-    }
-#define GATHER(Lv, SPLITv, VECv, warps, NSv)                                                                        \
-  do {                                                                                                              \
-    kpconv_gather_v3_kernel<Lv, SPLITv, VECv, IdxT><<<cdiv((long long)(warps), 4), 128, 0, stream>>>(               \
-        feats, rowpos, q, s, idx, kp, inv_sigma, M, N, H, C, (NSv), order, out);                                           \
-    RDM_LAUNCH_CHECK();                                                                                             \
-    return RDM_OK;                                                                                                  \
-  } while (0)
-    if (vec == 2) {  // slices of 2L channels
-      if (C == 32) {
-        if (cdiv(M, 2) >= want) GATHER(16, false, 2, cdiv(M, 2), 1);
-        if (M >= want) GATHER(16, true, 2, M, 1);
-        GATHER(8, true, 2, 2LL * M, 2);
-      } else {
-        if ((long long)M * (C / 64) >= want) GATHER(32, false, 2, (long long)M * (C / 64), C / 64);
-        if ((long long)M * (C / 32) >= want) GATHER(16, true, 2, (long long)M * (C / 32), C / 32);
-        GATHER(8, true, 2, (long long)M * (C / 16), C / 16);
-      }
-    }
-    if (C == 32) {
-      if (cdiv(M, 4) >= want) GATHER(8, false, 4, cdiv(M, 4), 1);
-      GATHER(8, true, 4, M, 1);
-    } else if (C == 64) {
-      if (cdiv(M, 2) >= want) GATHER(16, false, 4, cdiv(M, 2), 1);
-      if (M >= want) GATHER(16, true, 4, M, 1);
-      GATHER(8, true, 4, 2LL * M, 2);
-    } else {
-      if ((long long)M * (C / 128) >= want) GATHER(32, false, 4, (long long)M * (C / 128), C / 128);
-      if ((long long)M * (C / 64) >= want) GATHER(16, true, 4, (long long)M * (C / 64), C / 64);
-      GATHER(8, true, 4, (long long)M * (C / 32), C / 32);
-    }
-#undef GATHER
   }
+  // other widths (not used by RDMNet): CTA-level kernel, influences staged once per query in shared memory
   int VEC = (C % 128 == 0) ? 4 : (C % 64 == 0 ? 2 : 1);
   int NS = cdiv(C, 32 * VEC);
   RDM_CHECK_ARG(NS <= 8, "rdm_kpconv_gather: C_in=%d too wide for one CTA (max 1024)", C);

@@ -499,3 +499,146 @@ extern "C" int rdm_lgr(const float* matching_scores, int num_patches, int K, con
   RDM_LAUNCH_CHECK();
   return RDM_OK;
 }
+
+// ------------------------------------------------------------------------------------------- RANSAC on correspondences
+// GPU counterpart of registration_with_ransac_from_correspondences (geotransformer/utils/open3d.py:173-203, the open3d
+// call experiments/infer.py:76-82 makes per pair with 50 000 iterations on the CPU). One warp per iteration: lane 0 draws
+// ransac_n distinct correspondences from a counter-based generator (seed, iteration, draw) and solves the unweighted
+// Kabsch problem on them (single-precision Jacobi SVD); the 32 lanes count the correspondences within
+// distance_threshold; the best (inliers, lowest iteration) hypothesis wins through one 64-bit atomicMax. A second
+// launch re-derives the winner from its iteration number and refits on all of its inliers.
+namespace {
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// lane 0 only: hypothesis of iteration `it` -> T[12] (rows of [R|t]); false if the sample is degenerate
+__device__ bool ransac_sample_fit(const float* __restrict__ src, const float* __restrict__ ref, int C, int ransac_n,
+                                  unsigned long long seed, int it, float* T12) {
+  int pick[8];
+  unsigned long long ctr = 0;
+  for (int a = 0; a < ransac_n; a++) {
+    for (;;) {
+      const int c = (int)(mix64(seed ^ (((unsigned long long)it << 20) + ctr++)) % (unsigned long long)C);
+      bool dup = false;
+      for (int b = 0; b < a; b++) dup |= pick[b] == c;
+      if (!dup) {
+        pick[a] = c;
+        break;
+      }
+    }
+  }
+  float sc[3] = {0, 0, 0}, rc[3] = {0, 0, 0};
+  for (int a = 0; a < ransac_n; a++)
+    for (int d = 0; d < 3; d++) {
+      sc[d] += src[3 * pick[a] + d];
+      rc[d] += ref[3 * pick[a] + d];
+    }
+  const float inv = 1.f / (float)ransac_n;
+  for (int d = 0; d < 3; d++) {
+    sc[d] *= inv;
+    rc[d] *= inv;
+  }
+  float H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int a = 0; a < ransac_n; a++) {
+    const float s[3] = {src[3 * pick[a]] - sc[0], src[3 * pick[a] + 1] - sc[1], src[3 * pick[a] + 2] - sc[2]};
+    const float r[3] = {ref[3 * pick[a]] - rc[0], ref[3 * pick[a] + 1] - rc[1], ref[3 * pick[a] + 2] - rc[2]};
+    for (int x = 0; x < 3; x++)
+      for (int y = 0; y < 3; y++) H[3 * x + y] = fmaf(s[x], r[y], H[3 * x + y]);
+  }
+  float R[9];
+  rotation_from_H_t<float>(H, R);
+  for (int a = 0; a < 3; a++) {
+    T12[4 * a] = R[3 * a];
+    T12[4 * a + 1] = R[3 * a + 1];
+    T12[4 * a + 2] = R[3 * a + 2];
+    T12[4 * a + 3] = rc[a] - (R[3 * a] * sc[0] + R[3 * a + 1] * sc[1] + R[3 * a + 2] * sc[2]);
+  }
+  return true;
+}
+__device__ __forceinline__ bool ransac_inlier(const float* T, const float* __restrict__ src, const float* __restrict__ ref, int i,
+                                              float thr2) {
+  const float x = src[3 * i], y = src[3 * i + 1], z = src[3 * i + 2];
+  const float dx = fmaf(T[2], z, fmaf(T[1], y, T[0] * x)) + T[3] - ref[3 * i];
+  const float dy = fmaf(T[6], z, fmaf(T[5], y, T[4] * x)) + T[7] - ref[3 * i + 1];
+  const float dz = fmaf(T[10], z, fmaf(T[9], y, T[8] * x)) + T[11] - ref[3 * i + 2];
+  return fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < thr2;
+}
+
+__global__ void __launch_bounds__(128) ransac_hypothesis_kernel(const float* __restrict__ src, const float* __restrict__ ref, int C,
+                                                                int ransac_n, int num_iterations, unsigned long long seed,
+                                                                float thr2, unsigned long long* __restrict__ best) {
+  const int it = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (it >= num_iterations) return;
+  float T[12];
+  if (lane == 0) ransac_sample_fit(src, ref, C, ransac_n, seed, it, T);
+#pragma unroll
+  for (int k = 0; k < 12; k++) T[k] = __shfl_sync(FULL_MASK, T[k], 0);
+  int inl = 0;
+  for (int i = lane; i < C; i += 32) inl += ransac_inlier(T, src, ref, i, thr2) ? 1 : 0;
+  inl = warp_sum_i(inl);
+  if (lane == 0) atomicMax(best, ((unsigned long long)inl << 32) | (unsigned long long)(0x7fffffff - it));
+}
+
+__global__ void __launch_bounds__(32) ransac_refit_kernel(const float* __restrict__ src, const float* __restrict__ ref, int C,
+                                                          int ransac_n, unsigned long long seed, float thr2,
+                                                          const unsigned long long* __restrict__ best, float* __restrict__ weights,
+                                                          float* __restrict__ out_T, int* __restrict__ out_meta) {
+  const int lane = threadIdx.x;
+  const unsigned long long b = *best;
+  const int it = 0x7fffffff - (int)(b & 0xffffffffull);
+  float T[12];
+  if (lane == 0) ransac_sample_fit(src, ref, C, ransac_n, seed, it, T);
+#pragma unroll
+  for (int k = 0; k < 12; k++) T[k] = __shfl_sync(FULL_MASK, T[k], 0);
+  int inl = 0;
+  for (int i = lane; i < C; i += 32) {
+    const bool in = ransac_inlier(T, src, ref, i, thr2);
+    weights[i] = in ? 1.f : 0.f;
+    inl += in ? 1 : 0;
+  }
+  inl = warp_sum_i(inl);
+  __syncwarp();
+  if (inl >= 3) {
+    warp_procrustes(src, ref, weights, C, 0.f, out_T, lane);
+  } else if (lane == 0) {  // nothing to refit on: the sampled model itself
+    for (int k = 0; k < 12; k++) out_T[k] = T[k];
+    out_T[12] = out_T[13] = out_T[14] = 0.f;
+    out_T[15] = 1.f;
+  }
+  if (lane == 0 && out_meta != nullptr) {
+    out_meta[0] = inl;
+    out_meta[1] = it;
+  }
+}
+}  // namespace
+
+extern "C" size_t rdm_ransac_workspace(int num_correspondences) { return align_up((size_t)num_correspondences * 4, 256) + 512; }
+
+extern "C" int rdm_ransac_correspondences(const float* src_points, const float* ref_points, int num_correspondences,
+                                          float distance_threshold, int ransac_n, int num_iterations, unsigned long long seed,
+                                          float* out_transform, int* out_meta, void* workspace, size_t workspace_bytes,
+                                          cudaStream_t stream) {
+  RDM_CHECK_ARG(ransac_n >= 3 && ransac_n <= 8, "rdm_ransac_correspondences: ransac_n must be in [3, 8]");
+  RDM_CHECK_ARG(num_correspondences >= ransac_n, "rdm_ransac_correspondences: fewer correspondences (%d) than ransac_n (%d)",
+                num_correspondences, ransac_n);
+  RDM_CHECK_ARG(num_iterations >= 1 && distance_threshold > 0.f, "rdm_ransac_correspondences: bad arguments");
+  Workspace ws(workspace, workspace_bytes);
+  unsigned long long* best = ws.get<unsigned long long>(1);
+  float* weights = ws.get<float>(num_correspondences);
+  if (!ws.ok) {
+    rdm_set_error("rdm_ransac_correspondences: workspace too small");
+    return RDM_ERR_WORKSPACE;
+  }
+  RDM_CUDA(cudaMemsetAsync(best, 0, sizeof(unsigned long long), stream));
+  const float thr2 = distance_threshold * distance_threshold;
+  ransac_hypothesis_kernel<<<cdiv(num_iterations, 4), 128, 0, stream>>>(src_points, ref_points, num_correspondences, ransac_n,
+                                                                        num_iterations, seed, thr2, best);
+  RDM_LAUNCH_CHECK();
+  ransac_refit_kernel<<<1, 32, 0, stream>>>(src_points, ref_points, num_correspondences, ransac_n, seed, thr2, best, weights,
+                                            out_transform, out_meta);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}

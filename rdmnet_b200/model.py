@@ -221,10 +221,11 @@ class PairPipeline:
         # network's large grids
         self.side = torch.cuda.Stream(self.device, priority=int(os.environ.get("RDM_PIPE_PRIORITY", "-1")))
         self.jobs = [PyramidJob(), PyramidJob()]
-        # experimental knob (off by default, not yet measured): hold the next pair's radius searches back until the
-        # current pair's backbone has drained, so that they share the SMs with the matching tail instead of with the
-        # KPConv gathers (the gathers lose ~8 % to that contention inside the pipelined bench region)
-        self.defer_searches = os.environ.get("RDM_PIPE_DEFER_SEARCH", "0") == "1"
+        # the next pair's radius searches are held back until the current pair's backbone has drained, so that they share
+        # the SMs with the (latency-bound) matching tail instead of with the KPConv gathers: measured +10 % gather
+        # bandwidth and +2 % pairs/s inside the pipelined bench region (profiles/README.md, r2a). RDM_PIPE_DEFER_SEARCH=0
+        # restores the eager order.
+        self.defer_searches = os.environ.get("RDM_PIPE_DEFER_SEARCH", "1") == "1"
 
     def _begin(self, item, slot):
         points, lengths = item() if callable(item) else item  # a callable may stage host data (runs on the side stream)

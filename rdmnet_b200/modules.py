@@ -523,6 +523,30 @@ class SuperPointMatching(_Module):
                                    self.dual_normalization)
 
 
+class SuperPointTargetGenerator(_Module):
+    """geotransformer/modules/geotransformer/superpoint_target.py:6-41: training-time sampler of ground-truth patch
+    correspondences. The random draw stays numpy's global generator on the host (the reference's, :33: the same seed
+    gives the same selection)."""
+
+    def __init__(self, num_targets, overlap_threshold):
+        super().__init__()
+        self.num_targets = num_targets
+        self.overlap_threshold = overlap_threshold
+
+    @torch.no_grad()
+    def forward(self, gt_corr_indices, gt_corr_overlaps):
+        import numpy as np
+        masks = torch.gt(gt_corr_overlaps, self.overlap_threshold)
+        gt_corr_overlaps = gt_corr_overlaps[masks]
+        gt_corr_indices = gt_corr_indices[masks]
+        if gt_corr_indices.shape[0] > self.num_targets:
+            sel = np.random.choice(np.arange(gt_corr_indices.shape[0]), self.num_targets, replace=False)
+            sel = torch.from_numpy(sel).to(gt_corr_indices.device)
+            gt_corr_indices = gt_corr_indices[sel]
+            gt_corr_overlaps = gt_corr_overlaps[sel]
+        return gt_corr_indices[:, 0], gt_corr_indices[:, 1], gt_corr_overlaps
+
+
 class WeightedProcrustes(_Module):
     """geotransformer/modules/registration/procrustes.py:76-91."""
 

@@ -427,3 +427,107 @@ def local_global_registration(matching_scores, ref_points_f, src_points_f, ref_k
            L.stream())
     c = int(meta[0].item())  # the only host sync of the pose solver: the number of correspondences is the output shape
     return ref_c[:c], src_c[:c], sc[:c], T, bij[:c]
+
+
+# ----------------------------------------------------------------------------------------------- small boundary ops
+def index_select(data, index, dim):
+    """geotransformer/modules/ops/index_select.py:4-30: gather along `dim` with an n-d index; the output has the index's
+    shape spliced in at `dim`. Executed by rdm_index_select on rows of 4-byte words (dim != 0 goes through a transposed
+    view). Raises on an out-of-range index, like torch.index_select."""
+    if not torch.is_tensor(data) or not torch.is_tensor(index):
+        raise RuntimeError("index_select: data and index must be tensors")
+    if index.dtype not in (torch.int64, torch.int32):
+        raise RuntimeError("index_select: index must be an int64 (LongTensor) or int32 tensor")
+    if data.element_size() != 4:
+        raise RuntimeError("index_select: only 4-byte element types (float32 / int32) are supported")
+    dim = dim % data.ndim
+    moved = data.movedim(dim, 0).contiguous() if dim != 0 else data.contiguous()
+    rows = moved.shape[0]
+    words = int(moved.numel() // rows) if rows > 0 else 0
+    flat = index.reshape(-1).contiguous()
+    out = torch.empty((flat.shape[0],) + tuple(moved.shape[1:]), dtype=data.dtype, device=data.device)
+    if flat.shape[0] > 0 and words > 0:
+        err = torch.zeros(1, dtype=torch.int32, device=data.device)
+        L.call("rdm_index_select", L.ptr(moved), rows, words, L.ptr(flat), flat.element_size(), flat.shape[0], L.ptr(out),
+               L.ptr(err), L.stream())
+        index_select.pending_checks.append(err)
+        if len(index_select.pending_checks) >= 64:
+            check_index_errors()
+    out = out.view(tuple(index.shape) + tuple(moved.shape[1:]))
+    if dim != 0:  # (b_0..b_{m-1}, a_0..a_{dim-1}, a_{dim+1}..) -> (a_0..a_{dim-1}, b_0..b_{m-1}, a_{dim+1}..)
+        m = index.ndim
+        perm = list(range(m, m + dim)) + list(range(m)) + list(range(m + dim, out.ndim))
+        out = out.permute(*perm)
+    return out
+
+
+index_select.pending_checks = []
+
+
+def check_index_errors():
+    """Out-of-range flags of earlier index_select calls (checked lazily so that the op itself never synchronises)."""
+    flags, index_select.pending_checks = index_select.pending_checks, []
+    if flags and int(torch.stack(flags).max().item()) != 0:
+        raise IndexError("index_select: index out of range")
+
+
+def apply_transform(points, transform, normals=None):
+    """geotransformer/modules/ops/transformation.py:7-60: (*,3) points with a (4,4) transform, or (B,N,3) with (B,4,4)."""
+    if normals is not None and points.shape != normals.shape:
+        raise AssertionError("points and normals must have the same shape")
+    if transform.ndim == 2:
+        batch, n, shared = 1, points.numel() // 3, 1
+    elif transform.ndim == 3 and points.ndim == 3:
+        if transform.shape[0] != points.shape[0] and 1 not in (transform.shape[0], points.shape[0]):
+            raise ValueError("Incompatible shapes between points {} and transform {}.".format(tuple(points.shape), tuple(transform.shape)))
+        if points.shape[0] == 1 and transform.shape[0] > 1:
+            points = points.expand(transform.shape[0], -1, -1)
+            normals = None if normals is None else normals.expand(transform.shape[0], -1, -1)
+        batch, n, shared = points.shape[0], points.shape[1], 1 if transform.shape[0] == 1 else 0
+    else:
+        raise ValueError("Incompatible shapes between points {} and transform {}.".format(tuple(points.shape), tuple(transform.shape)))
+    if points.dtype != torch.float32 or transform.dtype != torch.float32:
+        raise RuntimeError("apply_transform: float32 tensors expected")
+    p, t = points.contiguous(), transform.contiguous()
+    out = torch.empty_like(p)
+    nrm = normals.contiguous() if normals is not None else None
+    nout = torch.empty_like(nrm) if nrm is not None else None
+    L.call("rdm_apply_transform", L.ptr(p), L.ptr(t), batch, n, shared, L.ptr(out), L.ptr(nrm), L.ptr(nout), L.stream())
+    return (out, nout) if normals is not None else out
+
+
+def apply_rotation(points, rotation, normals=None):
+    """transformation.py:63-106 through apply_transform with a zero translation."""
+    T = torch.zeros(rotation.shape[:-2] + (4, 4), dtype=rotation.dtype, device=rotation.device)
+    T[..., :3, :3] = rotation
+    T[..., 3, 3] = 1.0
+    return apply_transform(points, T, normals)
+
+
+def get_rotation_translation_from_transform(transform):
+    """transformation.py:109-122 (views)."""
+    return transform[..., :3, :3], transform[..., :3, 3]
+
+
+def get_transform_from_rotation_translation(rotation, translation):
+    """transformation.py:125-142."""
+    T = torch.eye(4, dtype=rotation.dtype, device=rotation.device).expand(rotation.shape[:-2] + (4, 4)).clone()
+    T[..., :3, :3] = rotation
+    T[..., :3, 3] = translation
+    return T
+
+
+def inverse_transform(transform):
+    """transformation.py:145-162: [R^T, -R^T t]."""
+    R, t = get_rotation_translation_from_transform(transform)
+    Ri = R.transpose(-1, -2)
+    return get_transform_from_rotation_translation(Ri, -(Ri @ t.unsqueeze(-1)).squeeze(-1))
+
+
+def neighbor_histogram(counts, hist_n, hist=None):
+    """One stage of calibrate_neighbors_stack_mode's histogram (geotransformer/utils/data.py:207-211), accumulated on the
+    device: hist[c] += #{queries with c in-radius neighbours}, c < hist_n."""
+    if hist is None:
+        hist = torch.zeros(hist_n, dtype=torch.int32, device=counts.device)
+    L.call("rdm_neighbor_histogram", L.ptr(counts.contiguous()), counts.shape[0], hist_n, L.ptr(hist), L.stream())
+    return hist

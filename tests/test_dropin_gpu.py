@@ -1,0 +1,139 @@
+"""Drop-in boundary on the GPU: the reference's UNMODIFIED Python (baseline/_ref/RDMNet, staged by build()) running on top
+of rdmnet_b200.dropin, compared with the reference's own outputs (tests/golden/pair_outputs.npz):
+  * experiments/model_infer.RDMNet.forward fed by the aliased geotransformer.utils.data collate -> bit-exact index outputs
+    and correspondence points, features / pose at the north-star tolerance;
+  * calibrate_neighbors_stack_mode (GPU histogram) -> the reference's limits [65 63 69 70 81];
+  * GPU RANSAC on the golden correspondences -> the LGR pose;
+  * experiments/infer.py end to end (BASELINE.json config 1) in a subprocess.
+"""
+import importlib
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref", "RDMNet")
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "experiments")),
+                                                  reason="reference tree not staged (baseline/_ref/RDMNet)")]
+NAMES = ("geotransformer", "rdmnet", "config", "backbone", "model_infer", "model", "loss", "dataset")
+
+
+@pytest.fixture(scope="module")
+def ref_model(pretrained_state):
+    from rdmnet_b200 import dropin as D
+    saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in NAMES}
+    for k in saved:
+        del sys.modules[k]
+    path = list(sys.path)
+    D.install(reference_root=REF)
+    config = importlib.import_module("config")
+    model_infer = importlib.import_module("model_infer")
+    cfg = config.make_cfg()
+    cfg.test.vis = False
+    cfg.neighbor_limits = [65, 63, 69, 70, 81]
+    model = model_infer.create_model(cfg)
+    model.load_state_dict(pretrained_state, strict=True)
+    model = model.cuda().eval()
+    yield model, cfg
+    D.uninstall()
+    for k in [k for k in sys.modules if k.split(".")[0] in NAMES]:
+        del sys.modules[k]
+    sys.modules.update(saved)
+    sys.path[:] = path
+
+
+def relerr(got, ref):
+    got = torch.as_tensor(np.asarray(got.detach().cpu()) if torch.is_tensor(got) else got).double()
+    ref = torch.as_tensor(ref).double()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    return (got - ref).abs().max().item() / max(ref.abs().max().item(), 1e-30)
+
+
+@pytest.mark.parametrize("tag,a,b", [("p04", "s000000", "s000004"), ("p07", "s000000", "s000007")])
+def test_unmodified_model_infer_forward_matches_reference_outputs(ref_model, scans, golden_pairs, tag, a, b):
+    model, cfg = ref_model
+    data = importlib.import_module("geotransformer.utils.data")
+    item = dict(ref_points=scans[a], src_points=scans[b], ref_feats=np.ones((len(scans[a]), 1), np.float32),
+                src_feats=np.ones((len(scans[b]), 1), np.float32))
+    dd = data.registration_collate_fn_stack_mode([item], cfg.backbone.num_stages, cfg.backbone.init_voxel_size,
+                                                 cfg.backbone.init_radius, cfg.neighbor_limits)
+    dd = {k: ([t.cuda() for t in v] if isinstance(v, list) else (v.cuda() if torch.is_tensor(v) else v)) for k, v in dd.items()}
+    dd["testing"] = True
+    with torch.no_grad():
+        out = model(dd)  # experiments/model_infer.py:109-354, unmodified
+    g = golden_pairs
+    assert np.array_equal(np.stack([l.cpu().numpy() for l in dd["lengths"]]), g[f"{tag}_lengths"])
+    assert np.array_equal(out["ref_node_corr_indices"].cpu().numpy(), g[f"{tag}_ref_node_corr_indices"])
+    assert np.array_equal(out["src_node_corr_indices"].cpu().numpy(), g[f"{tag}_src_node_corr_indices"])
+    assert np.array_equal(out["ref_corr_points"].cpu().numpy(), g[f"{tag}_ref_corr_points"]), "correspondences (bit-exact)"
+    assert np.array_equal(out["src_corr_points"].cpu().numpy(), g[f"{tag}_src_corr_points"])
+    errs = {k: relerr(out[k], g[f"{tag}_{k}"]) for k in ("ref_points_c", "src_points_c", "ref_feats_c", "src_feats_c",
+                                                         "corr_scores", "estimated_transform")}
+    print(tag, "achieved max|err|/max|ref|:", {k: f"{v:.2e}" for k, v in errs.items()})
+    for k, v in errs.items():
+        assert v <= 1e-4, (k, v)
+
+
+def test_calibrate_neighbors_gpu_histogram_matches_reference(ref_model, scans):
+    model, cfg = ref_model
+    data = importlib.import_module("geotransformer.utils.data")
+
+    class TwoPairs:  # the 'infer' subset of rdmnet/datasets/registration/kitti/dataset.py:56-64
+        pairs = [("s000000", "s000004"), ("s000000", "s000007")]
+
+        def __len__(self):
+            return 2
+
+        def __getitem__(self, i):
+            a, b = self.pairs[i]
+            return dict(ref_points=scans[a], src_points=scans[b], ref_feats=np.ones((len(scans[a]), 1), np.float32),
+                        src_feats=np.ones((len(scans[b]), 1), np.float32))
+
+    limits = data.calibrate_neighbors_stack_mode(TwoPairs(), data.registration_collate_fn_stack_mode, 5, 0.3, 4.25 * 0.3)
+    assert [int(x) for x in limits] == [65, 63, 69, 70, 81]  # what the reference calibrates on these pairs
+
+
+def test_gpu_ransac_recovers_the_pose(golden_pairs):
+    from rdmnet_b200.registration import registration_with_ransac_from_correspondences as ransac
+    g = golden_pairs
+    T = ransac(g["p04_src_corr_points"], g["p04_ref_corr_points"], distance_threshold=0.3, ransac_n=4, num_iterations=50000)
+    ref = g["p04_estimated_transform"].astype(np.float64)
+    rot = np.degrees(np.arccos(np.clip((np.trace(T[:3, :3].T @ ref[:3, :3]) - 1) / 2, -1, 1)))
+    assert rot < 0.3 and np.linalg.norm(T[:3, 3] - ref[:3, 3]) < 0.15, (rot, T, ref)
+    T2 = ransac(g["p04_src_corr_points"], g["p04_ref_corr_points"], distance_threshold=0.3, ransac_n=4, num_iterations=50000)
+    assert np.array_equal(T, T2), "deterministic for a fixed seed"
+    # synthetic: exact rigid motion + 40 % outliers
+    rng = np.random.default_rng(3)
+    src = rng.normal(size=(600, 3)).astype(np.float32) * 20
+    ang = 0.4
+    R = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]], np.float32)
+    refp = src @ R.T + np.array([3.0, -1.0, 0.5], np.float32)
+    refp[:240] = rng.normal(size=(240, 3)).astype(np.float32) * 20
+    T3 = ransac(src, refp, distance_threshold=0.05, ransac_n=3, num_iterations=2000)
+    assert np.abs(T3[:3, :3] - R).max() < 1e-4 and np.abs(T3[:3, 3] - [3.0, -1.0, 0.5]).max() < 1e-3
+
+
+def test_unmodified_infer_py_runs_end_to_end(golden_pairs, tmp_path):
+    """BASELINE.json config 1: experiments/infer.py, unchanged, over the drop-in (subprocess: it owns argv / cwd)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "run_reference_infer.py"), "--workdir", str(tmp_path),
+                        "--all-pairs"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    print(res["ended"], res["neighbor_limits"])
+    assert res["neighbor_limits"] == [65, 63, 69, 70, 81]
+    assert len(res["poses"]) == 2
+    for pose, tag in zip(res["poses"], ("p04", "p07")):
+        ref = golden_pairs[f"{tag}_estimated_transform"].reshape(-1)[:12]
+        assert np.abs(np.array(pose["pose12"]) - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max()) + 1e-6  # file has 6 decimals
+    assert len(res["npz"]) == 2
+    for name, d in res["npz"].items():
+        assert {"ref_points", "src_points", "ref_points_f", "src_points_f", "ref_points_c", "src_points_c", "ref_feats_c",
+                "src_feats_c", "ref_node_corr_indices", "src_node_corr_indices", "ref_corr_points", "src_corr_points",
+                "estimated_transform", "estimated_transform_ransac"} <= set(d["keys"])  # infer.py:85-101 schema
+        Tl, Tr = np.array(d["estimated_transform"]), np.array(d["estimated_transform_ransac"])
+        assert np.linalg.norm(Tl[:3, 3] - Tr[:3, 3]) < 0.3  # RANSAC and LGR agree on the pose
