@@ -51,6 +51,11 @@ def parse():
     ap.add_argument("--no-pipeline", action="store_true",
                     help="one pair at a time (model(data_dict) / PairRegistrar.register) instead of the pair pipeline")
     ap.add_argument("--cpu-pairs", type=int, default=3, help="pairs in the bounded cpu_baseline sample")
+    ap.add_argument("--sweep", action="store_true",
+                    help="BASELINE.json configs[4]: 256 synthetic pairs, 64 per size class (4k/8k/16k/32k pts/scan), dealt "
+                         "round-robin over the ranks; reports per-class pairs/s and the per-layer gather roofline")
+    ap.add_argument("--sweep-pairs", type=int, default=256)
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference's 1-GPU eager measurement")
     return ap.parse_args()
 
 
@@ -182,41 +187,88 @@ def cpu_reference_pair(state, pair, impl):
 
 
 def cpu_arm(pairs, n_steps, n_warm, budget_s):
+    """-> (cpu_baseline dict, pairs done, seconds, info). Runs the reference's OWN code (baseline/_ref/RDMNet: its collate over
+    its C++ extension core + experiments/model_infer.RDMNet on torch CPU) when it is staged - kind "reference" -, else the
+    oracle port - kind "port"."""
     import torch
     from oracle import pyramid as OP
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     torch.set_num_threads(cores)
-    impl = "ref" if OP.ref_available() else "port"
     state, wdesc = load_state()
-    for i in range(n_warm):
-        cpu_reference_pair(state, pairs[i % len(pairs)], impl)
-    t0, done = time.perf_counter(), 0
-    for i in range(n_steps):
-        cpu_reference_pair(state, pairs[i % len(pairs)], impl)
-        done += 1
-        if time.perf_counter() - t0 > budget_s:
-            break
-    dt = time.perf_counter() - t0
-    kind = "port"  # the model half (the dominant share) is the restatement; only the pyramid can run the real C++ core
-    sample = (f"{done} pair(s) of the workload after {n_warm} warm-up; pyramid = "
-              f"{'reference C++ core (oracle/_ref), 1 thread as in a DataLoader worker' if impl == 'ref' else 'C restatement'}"
-              f"; model forward = torch-CPU fp32 restatement of experiments/model_infer.py on {cores} threads; {wdesc}")
-    return {"value": done / dt, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}, done, dt
+    info = {}
+    try:
+        from baseline import reference_runner as RR
+        ok, why = RR.available()
+    except Exception as e:  # pragma: no cover
+        ok, why = False, repr(e)
+    if ok:
+        model, cfg = RR.build_model(state, LIMITS, "cpu")
+        done, dt, T, n0 = RR.run_cpu(model, cfg, pairs, n_steps, n_warm, budget_s)
+        info = {"last_pair": (n_warm + done - 1) % len(pairs), "estimated_transform": T}
+        kind = "reference"
+        sample = (f"{done} pair(s) of the workload after {n_warm} warm-up through the UNMODIFIED reference (baseline/_ref/RDMNet): "
+                  f"registration_collate_fn_stack_mode over its C++ extension core (1 thread, as in a DataLoader worker) + "
+                  f"experiments/model_infer.RDMNet.forward on torch CPU with {cores} threads; {wdesc}")
+    else:
+        impl = "ref" if OP.ref_available() else "port"
+        for i in range(n_warm):
+            cpu_reference_pair(state, pairs[i % len(pairs)], impl)
+        t0, done, T = time.perf_counter(), 0, None
+        for i in range(n_warm, n_warm + n_steps):
+            T = cpu_reference_pair(state, pairs[i % len(pairs)], impl)
+            done += 1
+            if time.perf_counter() - t0 > budget_s:
+                break
+        dt = time.perf_counter() - t0
+        info = {"last_pair": (n_warm + done - 1) % len(pairs), "estimated_transform": T.numpy()}
+        kind = "port"
+        sample = (f"{done} pair(s) of the workload after {n_warm} warm-up ({why}); pyramid = "
+                  f"{'reference C++ core (oracle/_ref), 1 thread' if impl == 'ref' else 'C restatement'}"
+                  f"; model forward = torch-CPU fp32 restatement of experiments/model_infer.py on {cores} threads; {wdesc}")
+    return {"value": done / dt, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}, done, dt, info
+
+
+def reference_gpu_eager(pairs, n_steps=48, n_warm=8, workers=8):
+    """BASELINE.md 3.4 / the north star's denominator: the unmodified reference, PyTorch-eager on ONE GPU, fed by 8 CPU
+    collate workers. None when the reference tree is not staged or there is no GPU."""
+    import torch
+    if not torch.cuda.is_available():
+        return None
+    try:
+        from baseline import reference_runner as RR
+        ok, why = RR.available()
+        if not ok:
+            return {"unavailable": why}
+        state, wdesc = load_state()
+        model, cfg = RR.build_model(state, LIMITS, "cuda")
+        done, dt, fwd_ms, T = RR.run_gpu_eager(model, cfg, pairs, n_steps, n_warm, workers)
+        del model
+        torch.cuda.empty_cache()
+        return {"value": done / dt, "unit": UNIT, "forward_ms_cuda_events": fwd_ms, "pairs": done, "warmup": n_warm,
+                "collate_workers": workers,
+                "what": "unmodified experiments/model_infer.RDMNet, PyTorch eager fp32 on 1 GPU, CPU collate (its C++ ext core) in "
+                        f"{workers} DataLoader workers, wall clock over the timed pairs (BASELINE.md 3.4); {wdesc}"}
+    except Exception as e:
+        return {"unavailable": repr(e)[:300]}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    pairs = make_pairs(min(args.pairs, 2), 0)
-    cb, done, dt = cpu_arm(pairs, args.steps, min(args.warmup, 1), budget_s=150.0)
+    pairs = make_pairs(args.pairs, 0)  # the same pairs, step count and warm-up as the repo arm
+    cb, done, dt, _ = cpu_arm(pairs, args.steps, args.warmup, budget_s=240.0)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": done,
-            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / max(done, 1), "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(done, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "neighbor_limits": LIMITS, "pairs_per_step": 1,
+            "config": {"workload": WORKLOAD, "pairs_per_step": 1, "distinct_pairs_per_rank": len(pairs),
+                       "points_per_pair": [int(len(p["ref_points"]) + len(p["src_points"])) for p in pairs],
+                       "neighbor_limits": LIMITS,
                        "note": "CPU path of the reference (it ships no GPU kernels); rank 0 only"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if not args.no_reference_gpu:
+        line["reference_gpu_eager"] = reference_gpu_eager(pairs)
     emit(json.dumps(line))
 
 
@@ -379,17 +431,32 @@ def run_ours(args, rank, world, local_rank):
         gc.enable()
         api_name = "rdmnet_b200.api.PairRegistrar.register (host numpy in, host numpy out)"
 
+    # ---- untimed extra pass (rank 0): the KPConv weight GEMMs bracketed with CUDA events for the tensor-pipe roofline entry
+    # (the brackets break the programmatic-dependent-launch chain, which is why they are off inside the timed regions),
+    # and one plain forward per distinct pair whose pose / correspondence count the cpu_baseline leg is compared with
+    gemm_prof, my_poses = [], {}
+    if rank == 0 and not args.no_cpu_baseline:
+        L.prof_enable(2)
+        for i in range(len(d_pairs)):
+            o = step(i)
+            my_poses[i] = (o["estimated_transform"].cpu().numpy(), int(o["corr_scores"].shape[0]))
+        torch.cuda.synchronize()
+        gemm_prof = [r for r in L.prof_read() if r[0] == 2]
+        L.prof_enable(False)
+
     # max over ranks
     tm = torch.tensor([total_ms, e2e_s * 1e3, t_wall * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms, wall_ms = tm.tolist()
 
-    # pose sanity on the last pair (synthetic ground truth): not part of the metric, reported for context
-    T = res["estimated_transform"]
-    Tg = pairs[(args.steps - 1) % len(pairs)]["transform"]
-    rre = float(np.degrees(np.arccos(np.clip((np.trace(T[:3, :3].T @ Tg[:3, :3]) - 1) / 2, -1, 1))))
-    rte = float(np.linalg.norm(T[:3, 3] - Tg[:3, 3]))
+    # registration quality on the last pair against the synthetic ground truth (the reference's success criterion is
+    # RRE < 5 deg and RTE < 2 m, experiments/config.py:66-67)
+    def pose_err(T, Tg):
+        T, Tg = np.asarray(T, np.float64), np.asarray(Tg, np.float64)
+        return (float(np.degrees(np.arccos(np.clip((np.trace(T[:3, :3].T @ Tg[:3, :3]) - 1) / 2, -1, 1)))),
+                float(np.linalg.norm(T[:3, 3] - Tg[:3, 3])))
+    rre, rte = pose_err(res["estimated_transform"], pairs[(args.steps - 1) % len(pairs)]["transform"])
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -431,25 +498,165 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": reg.d2h_bytes, "ms_per_step": e2e_ms / args.steps,
                     "api": api_name},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "kpconv_gather_kernel (+row_positive prepass), 14 launches/step", "bound": "hbm",
+            "roofline": {"kernel": "kpconv_gather_sparse_kernel (13 launches/step) + kpconv_gather_c1_kernel (1)", "bound": "hbm",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                          "peak_source": peak_src, "launches": g["launches"],
                          "avg_launch_us": 1e3 * g["ms"] / max(g["launches"], 1),
                          "algorithmic_bytes_per_launch": g["bytes"] / max(g["launches"], 1),
                          "definition": "G = M*H*(C_in*4+12+4) + M*(C_out*4+12) per launch (SURVEY 8(d), fp32, int32 idx)",
-                         "kpconv_weight_gemm_ms_per_step": (w["ms"] / args.steps) if w["launches"] else None,
-                         "kpconv_gather_ms_per_step": g["ms"] / args.steps,
+                         # the look-ahead pair's gathers are bracketed too: normalise by the launches recorded, not by K
+                         "kpconv_gather_ms_per_step": g["ms"] / max(g["launches"] / 14.0, 1e-9),
                          "per_layer_GBps": {k: (v[1] / 1e9) / (v[0] / 1e3) for k, v in per_layer.items() if v[0] > 0}},
             "clocks": clk,
-            # context only, not a quality metric: the pretrained KITTI weights do not register the self-similar procedural
-            # corridor - the reference's own CPU path returns poses 9-14 m off on the same pairs. Pose PARITY with
-            # the reference is what tests/test_model_gpu.py pins, on the bundled KITTI scans.
             "pose_vs_synthetic_gt": {"rre_deg": rre, "rte_m": rte, "n_corr": int(res["corr_scores"].shape[0]),
-                                     "note": "the reference path itself fails on this synthetic scene; see DESIGN.md"},
+                                     "registered": bool(rre < 5.0 and rte < 2.0)},
         }
+        if gemm_prof:
+            # tensor-pipe roofline of the KPConv weight contraction (M x 15 C_in) . (15 C_in x C_out), tcgen05 kind::tf32 with
+            # the 3-term split: `achieved` counts the useful fp32-equivalent flops 2 M K N; the tensor pipe issues 3x that in
+            # tf32 MMAs. Peak: MEASURED_PEAKS.json has no tf32 figure; dense tf32 is half the bf16 rate on this part
+            # (B200_PROFILING.md: 1.1 vs 2.25 PFLOP/s nominal), so peak = bf16_tflops_sustained / 2 (assumption stated).
+            fl = sum(2.0 * m_ * n_ * c_ for _, _, m_, n_, _, c_ in gemm_prof)
+            ms = sum(r[1] for r in gemm_prof)
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                    bf16 = float(json.load(f)["bf16_tflops_sustained"])
+                psrc = "measured bf16_tflops_sustained / 2 (tf32 dense = half the bf16 rate: assumption)"
+            except Exception:
+                bf16, psrc = 1400.0, "fallback 1.4 PFLOP/s sustained bf16 / 2"
+            ach = fl / 1e12 / (ms / 1e3)
+            line["roofline_gemm"] = {"kernel": "gemm_tf32x3 (tcgen05 kind::tf32, A in TMEM), KPConv weight contraction, 14 launches/step",
+                                     "bound": "tensor", "achieved": ach, "issued_tf32_tflops": 3.0 * ach, "peak": bf16 / 2.0,
+                                     "unit": "TFLOP/s", "frac": ach / (bf16 / 2.0), "frac_issued": 3.0 * ach / (bf16 / 2.0),
+                                     "peak_source": psrc, "launches": len(gemm_prof),
+                                     "kpconv_weight_gemm_ms_per_step": ms / max(len(gemm_prof) / 14.0, 1e-9),
+                                     "note": "measured in an untimed extra pass with event brackets around each launch"}
         if world == 1 and not args.no_cpu_baseline:
-            cb, _, _ = cpu_arm(pairs, args.cpu_pairs, 1, budget_s=60.0)
+            cb, _, _, info = cpu_arm(pairs, args.cpu_pairs, 1, budget_s=60.0)
             line["cpu_baseline"] = cb
+            # parity on the BENCHED pairs: this arm's pose vs the CPU reference's on the same pair
+            if info.get("estimated_transform") is not None and info["last_pair"] in my_poses:
+                Tm, nc = my_poses[info["last_pair"]]
+                Tc = np.asarray(info["estimated_transform"], np.float64)
+                d_rre, d_rte = pose_err(Tm, Tc)
+                line["parity_vs_cpu"] = {"pair": int(info["last_pair"]), "pose_max_abs_err": float(np.abs(Tm - Tc).max()),
+                                         "pose_rel_err": float(np.abs(Tm - Tc).max() / np.abs(Tc).max()),
+                                         "rre_between_deg": d_rre, "rte_between_m": d_rte, "n_corr_gpu": nc,
+                                         "cpu_kind": cb["kind"]}
+            if not args.no_reference_gpu:
+                rg = reference_gpu_eager(pairs)
+                line["reference_gpu_eager"] = rg
+                if rg and "value" in rg:
+                    line["vs_reference_gpu_eager"] = {"e2e_ratio": line["e2e"]["value"] / rg["value"],
+                                                      "value_ratio": line["value"] / rg["value"],
+                                                      "target": ">= 10x (BASELINE.json north_star)"}
+        emit(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------- config 5: size sweep
+def run_sweep(args, rank, world, local_rank):
+    """BASELINE.json configs[4] / SURVEY 8(d) config 5: `--sweep-pairs` synthetic pairs, a quarter per size class (4k / 8k /
+    16k / 32k points per scan), pair ids dealt round-robin over the ranks (rdmnet_b200.sharding.shard_pair_ids, no
+    collective on the data path). Per class: pairs/s (device time: CUDA events per pair inside the pair pipeline, L2 flushed
+    between pairs; whole job = pairs of all ranks / slowest rank) and the KPConv gather roofline on G."""
+    import torch
+    import torch.distributed as dist
+    from rdmnet_b200 import _lib as L
+    from rdmnet_b200 import synthetic
+    from rdmnet_b200.model import PairPipeline, create_model
+    from rdmnet_b200.ops import kpconv_gather_bytes
+    from rdmnet_b200.sharding import shard_pair_ids
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: rdmnet_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    L.lib()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model = create_model()
+    if os.path.exists(CKPT):
+        model.load_state_dict(torch.load(CKPT, map_location="cpu", weights_only=True), strict=True)
+    model = model.to(dev).eval()
+    classes = list(synthetic.SIZE_CLASSES)
+    per_class = args.sweep_pairs // len(classes)
+    distinct = 4  # distinct scene geometries per class (ray casting a scene costs seconds of host time); cycled
+    mine = shard_pair_ids(args.sweep_pairs, rank, world)  # pair id p: class p // per_class
+    geo = {}
+    for c in classes:
+        ne, na = synthetic.SIZE_CLASSES[c]
+        for g_ in range(distinct):
+            pr = synthetic.make_pair(pair_id=5000 + g_, n_elev=ne, n_azim=na)
+            pts = torch.from_numpy(np.concatenate([pr["ref_points"], pr["src_points"]])).to(dev)
+            lens = torch.tensor([len(pr["ref_points"]), len(pr["src_points"])], dtype=torch.int64, device=dev)
+            geo[(c, g_)] = (pts, lens)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    pipe = PairPipeline(model, dev)
+    peak, peak_src = peaks()
+    res = {}
+    import gc
+    for ci, c in enumerate(classes):
+        ids = [p_ for p_ in mine if p_ // per_class == ci]
+        items = [geo[(c, p_ % distinct)] for p_ in ids]
+        for _ in pipe.run(items[:3] + [geo[(c, g_)] for g_ in range(distinct)] * 2, before_step=lambda i: flush.fill_(i & 0xFF)):
+            pass  # warm-up + allocator priming for this size class
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        L.prof_enable(1)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in items]
+        for a, b in ev:
+            a.record(); b.record()
+        torch.cuda.synchronize()
+        gc.collect(); gc.disable()
+
+        def before(i, ev=ev):
+            if i < len(ev):
+                flush.fill_(i & 0xFF)
+                ev[i][0].record()
+        gen = pipe.run(items + items[:1], before_step=before)
+        n_corr = 0
+        for i in range(len(items)):
+            out = next(gen)
+            ev[i][1].record()
+            n_corr += int(out["corr_scores"].shape[0])
+        torch.cuda.synchronize()
+        for _ in gen:
+            pass
+        gc.enable()
+        prof = [r for r in L.prof_read() if r[0] == 1]
+        L.prof_enable(False)
+        ms = float(sum(a.elapsed_time(b) for a, b in ev))
+        gb = sum(kpconv_gather_bytes(m_, h_, c_, 64 if c_ == 1 else c_, 4) for _, _, m_, _, h_, c_ in prof)
+        gms = sum(r[1] for r in prof)
+        t = torch.tensor([float(len(items)), ms, float(gb), gms, float(n_corr), float(sum(int(x[0].shape[0]) for x in items))],
+                         dtype=torch.float64, device=dev)
+        if world > 1:
+            allt = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            allt = torch.stack(allt).cpu().numpy()
+        else:
+            allt = t.cpu().numpy()[None]
+        n_tot, t_max = float(allt[:, 0].sum()), float(allt[:, 1].max())
+        res[c] = {"pairs": int(n_tot), "pairs_per_s": n_tot / (t_max / 1e3), "ms_per_pair_per_gpu": float(allt[:, 1].sum() / n_tot),
+                  "mean_points_per_pair": float(allt[:, 5].sum() / n_tot), "mean_corr": float(allt[:, 4].sum() / n_tot),
+                  "gather_GBps": float(allt[:, 2].sum() / 1e9 / (allt[:, 3].sum() / 1e3)),
+                  "gather_frac": float(allt[:, 2].sum() / 1e9 / (allt[:, 3].sum() / 1e3) / peak),
+                  "per_rank_ms": [float(x) for x in allt[:, 1]]}
+    if rank == 0:
+        n_all = sum(v["pairs"] for v in res.values())
+        t_all = sum(max(v["per_rank_ms"]) for v in res.values())
+        line = {"metric": METRIC, "value": n_all / (t_all / 1e3), "unit": UNIT, "n_gpus": world, "steps": n_all, "warmup": 3 + 2 * distinct,
+                "ms_per_step": t_all / max(n_all / world, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "config 5: %d-pair synthetic sweep, %d pairs per size class %s (points/scan), round-robin over ranks"
+                                       % (args.sweep_pairs, per_class, classes),
+                           "distinct_geometries_per_class": distinct, "neighbor_limits": LIMITS,
+                           "l2": "256 MiB flush write between pairs (untimed)",
+                           "timing": "CUDA events per pair on the launch stream; per class: all pairs / slowest rank"},
+                "sweep": res, "roofline_peak": {"hbm_gbs": peak, "source": peak_src}}
         emit(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -478,6 +685,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.sweep:
+        run_sweep(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

@@ -13,6 +13,12 @@
  *    or int32 (index_bytes = 4); neighbour tables are padded with the number of support rows, exactly as
  *    radius_neighbors_cpu.cpp:85 does.
  *
+ *  - process model: ONE device and ONE host thread driving it per process (the reference's own arrangement: one process per
+ *    GPU, geotransformer/engine/base_tester.py:70-76). The stateless operator entry points are re-entrant; the runners
+ *    (rdm_build_pyramid*, rdm_encoder/decoder/backbone/match_forward) keep per-process scratch state (a pinned result
+ *    buffer, a side stream with its events, the default pyramid job) bound to the device that was current at their first
+ *    call, and must not be called concurrently from several threads or for several devices of one process.
+ *
  * Each entry point names the reference interface (file:line under /root/reference) it replaces.
  */
 #ifndef RDM_SM100_H

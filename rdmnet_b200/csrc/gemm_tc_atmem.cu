@@ -249,11 +249,8 @@ template <int BN, int STAGES>
 int launch_tca(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, float* C, int ldc, int M, int N, int K, int act,
               int splits, int kb_per_split, double* gn_stats, int gn_cpg, cudaStream_t stream, long long* dbg = nullptr) {
   const size_t smem = sizeof(TcaSmem<BN, STAGES>) + 1024;
-  static bool attr = false;
-  if (!attr) {
-    RDM_CUDA(cudaFuncSetAttribute(gemm_tf32x3_atmem_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  // per-device attribute: set on every launch (sub-microsecond), never cached per process
+  RDM_CUDA(cudaFuncSetAttribute(gemm_tf32x3_atmem_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(N, BN), cdiv(M, TC_BM), splits);
   RDM_CUDA(rdm_launch_pdl(gemm_tf32x3_atmem_kernel<BN, STAGES>, grid, dim3(TC_THREADS), smem, stream, ma, mb, bias, C, ldc, M, N, K, act,
                           kb_per_split, gn_stats, gn_cpg, dbg));

@@ -446,7 +446,15 @@ __global__ void __launch_bounds__(1024) rs_bounds_kernel(const float* __restrict
     } else {
       // cell edge slightly above the radius: a neighbour (fp32 d2 < r2) is then always within +-1 cell
       float cs = radius * 1.001f;
-      while (true) {
+      const float ext = fmaxf(hi[0] - lo[0], fmaxf(hi[1] - lo[1], hi[2] - lo[2]));
+      if (!(ext < 3.0e38f) || !(cs > 0.f)) {
+        // non-finite extent (a NaN / Inf coordinate; the reference's KD-tree returns garbage there, it does not hang):
+        // one cell holding everything, so the search degenerates to brute force over the cloud instead of never ending
+        c.nx = c.ny = c.nz = 1;
+        lo[0] = lo[1] = lo[2] = -3.0e38f;
+        cs = 3.0e38f;
+      } else
+      for (int grow = 0; grow < 512; grow++) {  // 1.25^512 overflows long before: the loop always ends
         double dx = floor((double)(hi[0] - lo[0]) / cs) + 1, dy = floor((double)(hi[1] - lo[1]) / cs) + 1,
                dz = floor((double)(hi[2] - lo[2]) / cs) + 1;
         if (dx <= RS_DIM_CAP && dy <= RS_DIM_CAP && dz <= RS_DIM_CAP && dx * dy * dz <= (double)RS_CELL_CAP) {
@@ -456,6 +464,7 @@ __global__ void __launch_bounds__(1024) rs_bounds_kernel(const float* __restrict
           break;
         }
         cs *= 1.25f;
+        if (grow == 511) c.nx = c.ny = c.nz = 1;
       }
       c.ox = lo[0];
       c.oy = lo[1];

@@ -116,11 +116,7 @@ extern "C" int rdm_tf_project(const rdm_tf_proj_job* h_jobs, int num_jobs, cudaS
   }
   if (maxn == 0) return RDM_OK;
   const size_t smem = (size_t)(TF_D * TF_D + TF_D * TF_R) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    RDM_CUDA(cudaFuncSetAttribute(tf_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  RDM_CUDA(cudaFuncSetAttribute(tf_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device
   RDM_CUDA(rdm_launch_pdl(tf_project_kernel, dim3(cdiv(maxn, TF_R), num_jobs), dim3(256), smem, stream, pj));
   RDM_LAUNCH_CHECK();
   return RDM_OK;
@@ -355,11 +351,7 @@ extern "C" int rdm_tf_attend(const rdm_tf_attn_job* h_jobs, int num_jobs, cudaSt
     maxn = max(maxn, h_jobs[i].nq);
   }
   if (maxn == 0) return RDM_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RDM_CUDA(cudaFuncSetAttribute(tf_attend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmem)));
-    attr_set = true;
-  }
+  RDM_CUDA(cudaFuncSetAttribute(tf_attend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmem)));  // per device
   RDM_CUDA(rdm_launch_pdl(tf_attend_kernel, dim3(cdiv(maxn, TF_R), num_jobs), dim3(256), sizeof(AttnSmem), stream, aj));
   RDM_LAUNCH_CHECK();
   return RDM_OK;

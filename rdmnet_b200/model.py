@@ -258,6 +258,11 @@ class PairPipeline:
             if before_step is not None:
                 before_step(i)
             main.wait_event(ready)
+            # the pyramid buffer, its workspace and the staged points were allocated under the side stream but are read by
+            # main-stream kernels (and by the caller through views in the output dict): tell the caching allocator, or
+            # the blocks could be handed to the next side-stream pyramid while the main stream still reads them
+            for t in (gp.buf, gp._points0) + tuple(gp._keep):
+                t.record_stream(main)
             state = self.model.forward_head(None, gp=gp)  # asynchronous launches on the main stream
             cur = None
             if nxt_item is not None:
@@ -513,7 +518,7 @@ class RDMNet(_Module):
     def _backbone(self, desc, nc_ref, feats):
         """rdm_backbone_forward: encoder + transformer 1 + n2p head + decoder + p2p head, one asynchronous host call.
         Returns (tf (nc, 256), n2p (nc,), dec (nf, 257) view with row stride 260, p2p (nf,))."""
-        key = cache_key(self)
+        key = self._fwd_key if getattr(self, "_fwd_key", None) is not None else cache_key(self)
         if getattr(self, "_bdesc_key", None) != key:
             blocks, dec, t1 = self.encoder._block_descs(), self.decoder.unary_descs(), self.transformer.runner_desc()
             d = L.BackboneDesc()
@@ -545,7 +550,7 @@ class RDMNet(_Module):
 
     def _match_desc(self):
         """rdm_match_desc over this model's vote / score / transformer2 / matching parameters (cached; see _Module)."""
-        key = cache_key(self)
+        key = self._fwd_key if getattr(self, "_fwd_key", None) is not None else cache_key(self)
         if getattr(self, "_mdesc_key", None) != key:
             v, cfg = self.vote, self.cfg
             mods = list(v.mlp_modules)
@@ -577,6 +582,9 @@ class RDMNet(_Module):
     def _match_tail(self, out, points_c, lengths_c, nc_ref, tf, n2p, points_f, nf_ref, feats_f):
         """model_infer.py:180-354 through rdm_match_forward (one host call, two internal synchronisations)."""
         d = self._match_desc()
+        if feats_f.shape[1] != d.c:
+            raise RuntimeError(f"rdm_match_forward gathers {d.c}-channel fine features (the vote / transformer width) and scales "
+                               f"the patch scores by 1/sqrt({d.c}); got backbone.output_dim = {feats_f.shape[1]}")
         dev = tf.device
         nc, nf, c, K, P = points_c.shape[0], points_f.shape[0], d.c, d.point_limit, d.num_correspondences
         f32, i64, u8 = torch.float32, torch.int64, torch.uint8
@@ -629,6 +637,7 @@ class RDMNet(_Module):
         """Pyramid (unless `gp`, a ready GpuPyramid, or a reference-style data_dict is given) + encoder + first
         transformer + decoder: asynchronous launches only once the pyramid exists. Returns the state forward_tail needs."""
         out = {}
+        self._fwd_key = cache_key(self)  # one fingerprint walk per forward, shared by the backbone / match descriptors
         data_dict = data_dict if data_dict is not None else {}
         if gp is not None or "neighbors" not in data_dict:  # raw stacked points in: build the pyramid here, on the GPU
             if gp is None:

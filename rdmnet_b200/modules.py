@@ -38,9 +38,12 @@ _WEIGHTS_EPOCH = [0]
 
 class _Module(nn.Module):
     """nn.Module whose device moves / dtype casts / state-dict loads / train-eval switches bump a process-wide epoch.
-    Derived data (transposed weight copies, packed layer blobs, C descriptor structs) are cached against that epoch
-    in eval mode, so the per-call cost of a cache check is one integer compare instead of a walk over ~500 tensors.
-    In training mode the caches fall back to (data_ptr, version) keys, which also see in-place optimizer updates."""
+    Derived data (transposed weight copies, packed layer blobs, C descriptor structs) are cached against
+    (mode, epoch, fingerprint): the epoch catches structural changes cheaply, the fingerprint - (storage pointer, in-place
+    version) of every parameter and buffer of the module - catches what the epoch cannot see: `p.copy_()`, `p.data = ...`,
+    an EMA swap, pruning, `load_state_dict` called directly on a plain nn.Linear child, an optimizer step. The tensor
+    list behind the fingerprint is itself cached per epoch, so a check costs two attribute reads per tensor (~50 us for
+    the whole 497-tensor model, once per forward: RDMNet.forward_head shares it with the runners)."""
 
     def _apply(self, fn, *args, **kwargs):
         _WEIGHTS_EPOCH[0] += 1
@@ -55,13 +58,22 @@ class _Module(nn.Module):
         return super().train(mode)
 
 
+def invalidate_caches():
+    """Drops every cached derived copy / descriptor (they are rebuilt on the next forward). The (pointer, version)
+    fingerprint makes this unnecessary for ordinary in-place edits; it remains for exotic cases (storage edited through a
+    raw pointer by foreign code)."""
+    _WEIGHTS_EPOCH[0] += 1
+
+
 def cache_key(module, tensors=None):
     """Cache key for data derived from `module`'s parameters (see _Module)."""
-    if not module.training:
-        return ("eval", _WEIGHTS_EPOCH[0])
     if tensors is None:
-        tensors = list(module.parameters()) + list(module.buffers())
-    return tuple((t.data_ptr(), t._version) for t in tensors)
+        cached = module.__dict__.get("_fp_tensors")
+        if cached is None or cached[0] != _WEIGHTS_EPOCH[0]:
+            cached = (_WEIGHTS_EPOCH[0], list(module.parameters()) + list(module.buffers()))
+            module.__dict__["_fp_tensors"] = cached
+        tensors = cached[1]
+    return (module.training, _WEIGHTS_EPOCH[0], tuple([(t.data_ptr(), t._version) for t in tensors]))
 
 
 class KPConv(_Module):
@@ -393,8 +405,6 @@ class ThDRoFormer(_Module):
         L = ops.L
         tr = self.transformer
         key = cache_key(self)
-        if key[0] != "eval":
-            key = key + tuple(layer.fused_blob().data_ptr() for layer in tr.layers)
         if getattr(self, "_desc_key", None) != key:
             blobs = [layer.fused_blob() for layer in tr.layers]
             d = L.ThdroformerDesc()

@@ -10,12 +10,21 @@ from oracle import pyramid as OP
 pytestmark = pytest.mark.gpu
 
 
+ACHIEVED = {}
+
+
 def close(got, ref, tol=1e-4, what=""):
+    """North-star bar: max|got - ref| <= tol * max|ref| (relative to the TENSOR MAXIMUM, no `max(1, .)` floor). The achieved
+    figure is printed (pytest -s / the captured-output section of a failure) and collected in ACHIEVED."""
     got = got.detach().cpu().double() if torch.is_tensor(got) else torch.as_tensor(got).double()
     ref = ref.detach().cpu().double() if torch.is_tensor(ref) else torch.as_tensor(ref).double()
     assert got.shape == ref.shape, (what, got.shape, ref.shape)
     err = (got - ref).abs().max().item()
-    assert err <= tol * max(1.0, ref.abs().max().item()), f"{what}: max abs err {err} (ref max {ref.abs().max().item()})"
+    scale = ref.abs().max().item()
+    rel = err / scale if scale > 0 else err
+    ACHIEVED[what] = max(ACHIEVED.get(what, 0.0), rel)
+    print(f"[parity] {what}: max|err| {err:.3e} / max|ref| {scale:.3e} = {rel:.2e} (bar {tol:.0e})")
+    assert rel <= tol, f"{what}: max abs err {err} = {rel:.2e} of max|ref| {scale} (bar {tol})"
 
 
 def assert_node_corr_equal(ri, si, sc, ref_ri, ref_si, rel=2e-5):
@@ -54,8 +63,11 @@ def test_forward_vs_reference_outputs(model, scans, golden_pairs, tag, a, b):
     out = run_pair(model, scans, a, b)
     assert np.array_equal(out["mask"].cpu().numpy(), g[f"{tag}_nms"]), "NMS mask"
     close(out["ref_points_c"], g[f"{tag}_ref_points_c"], 1e-4, "ref_points_c")
-    close(out["ref_feats_c"], g[f"{tag}_ref_feats_c"], 5e-4, "ref_feats_c")
-    close(out["src_feats_c"], g[f"{tag}_src_feats_c"], 5e-4, "src_feats_c")
+    close(out["src_points_c"], g[f"{tag}_src_points_c"], 1e-4, "src_points_c")
+    close(out["ref_feats_c"], g[f"{tag}_ref_feats_c"], 1e-4, "ref_feats_c")
+    close(out["src_feats_c"], g[f"{tag}_src_feats_c"], 1e-4, "src_feats_c")
+    close(out["shifted_ref_points_c"], g[f"{tag}_shifted"][:out["shifted_ref_points_c"].shape[0]], 1e-4, "shifted_points_c")
+    close(out["ref_feats_f"][:64, :64], g[f"{tag}_feats_f_head"], 1e-4, "feats_f (64x64 head)")
     same_order = assert_node_corr_equal(out["ref_node_corr_indices"].cpu().numpy(), out["src_node_corr_indices"].cpu().numpy(),
                                         out["node_corr_scores"].cpu().numpy(), g[f"{tag}_ref_node_corr_indices"],
                                         g[f"{tag}_src_node_corr_indices"])
@@ -66,7 +78,7 @@ def test_forward_vs_reference_outputs(model, scans, golden_pairs, tag, a, b):
         go, ro = np.lexsort(got_c.T[::-1]), np.lexsort(ref_c.T[::-1])
         got_c, ref_c, got_s, ref_s = got_c[go], ref_c[ro], got_s[go], ref_s[ro]
     assert np.array_equal(got_c, ref_c), "correspondence set (bit-exact points)"
-    close(got_s, ref_s, 2e-3, "corr_scores")
+    close(got_s, ref_s, 1e-4, "corr_scores")
     close(out["estimated_transform"], g[f"{tag}_estimated_transform"], 1e-4, "estimated_transform")
 
 
@@ -83,11 +95,12 @@ def test_forward_stages_vs_oracle(model, scans, pretrained_state):
     dd["features"] = torch.ones(tp["points"][0].shape[0], 1).cuda()
     out = model(dd)
     feats = model.encoder(dd["features"], dd)
-    close(feats[-1], ref["feats_s5"], 2e-4, "encoder stage 5")
+    close(feats[-1], ref["feats_s5"], 1e-4, "encoder stage 5")
     close(out["shifted_ref_points_c"], ref["shifted_points_c"][:431], 1e-4, "vote xyz")
     assert np.array_equal(out["mask"].cpu().numpy(), ref["nms_masks"].numpy())
-    close(out["ref_feats_c"], ref["ref_feats_c"], 5e-4, "ref_feats_c")
-    close(out["ref_feats_f"], ref["feats_f"][:out["ref_feats_f"].shape[0]], 5e-4, "feats_f")
+    close(out["ref_feats_c"], ref["ref_feats_c"], 1e-4, "ref_feats_c")
+    close(out["src_feats_c"], ref["src_feats_c"], 1e-4, "src_feats_c")
+    close(out["ref_feats_f"], ref["feats_f"][:out["ref_feats_f"].shape[0]], 1e-4, "feats_f")
     # knn tables: the node coordinates fed to the partition are GPU-computed (vote MLP: equal to the oracle's within
     # eps_pos, far inside the 1e-4 relative tolerance), so squared distances that tie in the oracle may order
     # differently here: rows must hold the same point sets, and positions may differ only between points whose
@@ -122,7 +135,10 @@ def test_forward_stages_vs_oracle(model, scans, pretrained_state):
         pc = np.concatenate([perms["src"][sci[b]], [K]])
         ms[b] = ms[b][pr][:, pc]
     live = ref["matching_scores"].numpy() > -1e11
-    close(ms[live], ref["matching_scores"].numpy()[live], 2e-3, "matching_scores")
+    # log-domain Sinkhorn output: entries reach -60, the bar is relative to that maximum; the probabilities exp(ms) are
+    # checked at the same bar
+    close(ms[live], ref["matching_scores"].numpy()[live], 1e-4, "matching_scores (log domain)")
+    close(np.exp(ms[live]), np.exp(ref["matching_scores"].numpy()[live]), 1e-4, "matching_scores (probabilities)")
     assert np.array_equal(out["ref_corr_points"].cpu().numpy(), ref["ref_corr_points"].numpy())
     close(out["estimated_transform"], ref["estimated_transform"], 1e-4, "estimated_transform")
 
@@ -212,3 +228,52 @@ def test_forward_size_sweep_runners_equal_stepwise(model, size_class):
     R = T[:3, :3]
     assert torch.allclose(R @ R.T, torch.eye(3, dtype=torch.float64), atol=1e-4) and abs(torch.det(R).item() - 1) < 1e-4
     assert torch.equal(T[3], torch.tensor([0, 0, 0, 1], dtype=torch.float64))
+
+
+# ---- parity on the BENCHMARKED workload: the synthetic pairs bench.py times (pair ids 0, 1 of rank 0) and the four config-5
+# size classes, GPU path vs the CPU oracle on the same points (the bundled-pair tests above never see this regime: ~3400
+# correspondences instead of 413-504)
+SYNTH_CASES = [("bench-pair-0", 0, None), ("bench-pair-1", 1, None), ("4k", 11, "4k"), ("8k", 11, "8k"), ("16k", 11, "16k"),
+               ("32k", 11, "32k")]
+
+
+@pytest.mark.parametrize("name,pair_id,size_class", SYNTH_CASES)
+def test_forward_vs_oracle_on_synthetic_pairs(model, pretrained_state, name, pair_id, size_class):
+    from rdmnet_b200 import synthetic
+    kw = {}
+    if size_class is not None:
+        kw["n_elev"], kw["n_azim"] = synthetic.SIZE_CLASSES[size_class]
+    p = synthetic.make_pair(pair_id=pair_id, **kw)
+    pts = np.concatenate([p["ref_points"], p["src_points"]])
+    lens = [len(p["ref_points"]), len(p["src_points"])]
+    pyr = OP.precompute_pyramid(pts, lens, 5, 0.3, 4.25 * 0.3, MO.DEFAULT_LIMITS, "ref" if OP.ref_available() else "port")
+    tp = MO.pyramid_to_torch(pyr)
+    torch.set_num_threads(16)
+    with torch.no_grad():
+        ref = MO.forward(pretrained_state, tp,
+                         lambda q, l: OP.radius_search(q.numpy(), q.numpy(), l.numpy(), l.numpy(), 2.4, 81, "port"))
+    out = model({"points": torch.from_numpy(pts).cuda(), "lengths": torch.tensor(lens, dtype=torch.int64).cuda()})
+    # discrete outputs: exact
+    assert np.array_equal(out["mask"].cpu().numpy(), ref["nms_masks"].numpy()), "NMS mask"
+    same_order = assert_node_corr_equal(out["ref_node_corr_indices"].cpu().numpy(), out["src_node_corr_indices"].cpu().numpy(),
+                                        out["node_corr_scores"].cpu().numpy(), ref["ref_node_corr_indices"].numpy(),
+                                        ref["src_node_corr_indices"].numpy())
+    got_c = np.concatenate([out["ref_corr_points"].cpu().numpy(), out["src_corr_points"].cpu().numpy()], 1)
+    ref_c = np.concatenate([ref["ref_corr_points"].numpy(), ref["src_corr_points"].numpy()], 1)
+    # correspondences: the same point pairs. A near-tie of two Sinkhorn scores (float noise ~1e-6) can move a single pair in
+    # or out on a pair with thousands of them; report the symmetric difference and allow at most 0.2 % of the set.
+    gs, rs = {tuple(r) for r in got_c.tolist()}, {tuple(r) for r in ref_c.tolist()}
+    diff = len(gs ^ rs)
+    print(f"[parity] {name}: {len(rs)} correspondences in the oracle, symmetric difference {diff}; coarse order identical: {same_order}")
+    assert diff <= max(2, int(0.002 * len(rs))), (diff, len(rs))
+    close(out["ref_feats_c"], ref["ref_feats_c"], 1e-4, f"{name} ref_feats_c")
+    close(out["src_feats_c"], ref["src_feats_c"], 1e-4, f"{name} src_feats_c")
+    close(out["ref_feats_f"], ref["feats_f"][:out["ref_feats_f"].shape[0]], 1e-4, f"{name} feats_f")
+    close(out["estimated_transform"], ref["estimated_transform"], 1e-4, f"{name} estimated_transform")
+    # and the pose is the true one: the benchmark exercises a registering regime (RRE < 5 deg, RTE < 2 m = the reference's
+    # success criterion, experiments/config.py:66-67)
+    T, Tg = out["estimated_transform"].cpu().numpy().astype(np.float64), p["transform"].astype(np.float64)
+    rre = np.degrees(np.arccos(np.clip((np.trace(T[:3, :3].T @ Tg[:3, :3]) - 1) / 2, -1, 1)))
+    rte = np.linalg.norm(T[:3, 3] - Tg[:3, 3])
+    print(f"[parity] {name}: RRE {rre:.3f} deg, RTE {rte:.3f} m vs synthetic ground truth")
+    assert rre < 5.0 and rte < 2.0
