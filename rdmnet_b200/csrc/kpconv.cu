@@ -582,6 +582,111 @@ static int launch_sparse(const float* feats, const unsigned char* rowpos, const 
   return RDM_OK;
 }
 
+// CTA-cooperative form of the sparse gather for the deep stages (C_in % 128 == 0, H <= 256), where the queries are few
+// (500 - 4000) and a warp-per-query kernel is bound by the LATENCY of its serial chain (index -> point -> influence ->
+// lists -> rows), not by throughput. One CTA of 256 threads owns one query:
+//   (A) thread = neighbour slot: ALL slots of the query in one step (no chunk loop); per kernel point the 8 warps ballot,
+//       publish their counts, and scatter their (row, w) entries behind the exclusive prefix over the warps (slot order
+//       kept: same summation order as the dense kernels);
+//   (B) the 15 x (C/128) (kernel point, 128-channel slice) tasks are dealt round-robin to the 8 warps; a task issues all
+//       its row loads at once (lists padded to a multiple of 8 with zero-weight entries) and stores one 512-byte row.
+template <typename IdxT>
+__global__ void __launch_bounds__(256) kpconv_gather_sparse_cta_kernel(const float* __restrict__ feats,
+                                                                       const unsigned char* __restrict__ rowpos,
+                                                                       const float* __restrict__ q_pts, const float* __restrict__ s_pts,
+                                                                       const IdxT* __restrict__ idx, const KPts kp, float inv_sigma,
+                                                                       int M, int N, int H, int C, int HC,
+                                                                       const int* __restrict__ order, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ int2 s_lists[];  // [15][HC]
+  __shared__ int s_wcnt[8][16];      // entries of warp w in list k
+  __shared__ int s_npos[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m = order != nullptr ? order[blockIdx.x] : blockIdx.x;
+  const float qx = q_pts[3 * (size_t)m], qy = q_pts[3 * (size_t)m + 1], qz = q_pts[3 * (size_t)m + 2];
+  int j = -1;
+  if (tid < H) {
+    const long long jj = (long long)idx[(size_t)m * H + tid];
+    if (jj < N) j = (int)jj;
+  }
+  float w[16];
+  int np = 0;
+  if (j >= 0) {
+    influences16(s_pts[3 * (size_t)j] - qx, s_pts[3 * (size_t)j + 1] - qy, s_pts[3 * (size_t)j + 2] - qz, kp, inv_sigma, w);
+    np = rowpos[j];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; k++) w[k] = 0.f;
+  }
+  const unsigned lt = (1u << lane) - 1u;
+  int mypos[KP_K];  // position of this thread's entry inside its warp's run of list k
+#pragma unroll
+  for (int k = 0; k < KP_K; k++) {
+    const unsigned mk = __ballot_sync(FULL_MASK, w[k] > 0.f);
+    mypos[k] = __popc(mk & lt);
+    if (lane == 0) s_wcnt[warp][k] = __popc(mk);
+  }
+  np = warp_sum_i(np);
+  if (lane == 0) s_npos[warp] = np;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < KP_K; k++) {
+    if (w[k] > 0.f) {
+      int base = 0;
+      for (int ww = 0; ww < warp; ww++) base += s_wcnt[ww][k];
+      s_lists[k * HC + base + mypos[k]] = make_int2(j, __float_as_int(w[k]));
+    }
+  }
+  if (tid < KP_K * 7) {  // pad every list with seven no-op entries (row 0 exists: N >= 1; weight 0)
+    const int k = tid / 7, i = tid - k * 7;
+    int tot = 0;
+#pragma unroll
+    for (int ww = 0; ww < 8; ww++) tot += s_wcnt[ww][k];
+    s_lists[k * HC + tot + i] = make_int2(0, 0);
+  }
+  __syncthreads();
+  int npos = 0;
+#pragma unroll
+  for (int ww = 0; ww < 8; ww++) npos += s_npos[ww];
+  const float inv = 1.f / (float)max(npos, 1);  // kpconv.py:113-116
+  const int NS = C >> 7, ntask = KP_K * NS;
+  for (int t = warp; t < ntask; t += 8) {
+    const int k = t % KP_K, slice = t / KP_K;
+    int n = 0;
+#pragma unroll
+    for (int ww = 0; ww < 8; ww++) n += s_wcnt[ww][k];
+    const int2* lk = s_lists + k * HC;
+    const float* fb = feats + (size_t)slice * 128 + 4 * lane;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int e = 0; e < n; e += 8) {
+      int2 en[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) en[u] = lk[e + u];
+      float4 f[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) f[u] = __ldg((const float4*)(fb + (size_t)en[u].x * C));
+#pragma unroll
+      for (int u = 0; u < 8; u++) gv_fma(__int_as_float(en[u].y), f[u], acc);
+    }
+    gv_store(out + (size_t)m * KP_K * C + (size_t)k * C + (size_t)slice * 128 + 4 * lane, acc, inv, float4());
+  }
+}
+
+template <typename IdxT>
+static int launch_sparse_cta(const float* feats, const unsigned char* rowpos, const float* q, const float* s, const IdxT* idx,
+                             const KPts& kp, float inv_sigma, int M, int N, int H, int C, const int* order, float* out,
+                             cudaStream_t stream) {
+  const int HC = H + 7;
+  const size_t smem = (size_t)KP_K * HC * sizeof(int2);
+  if (smem > 40 * 1024)
+    RDM_CUDA(cudaFuncSetAttribute(kpconv_gather_sparse_cta_kernel<IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RDM_CUDA(rdm_launch_pdl(kpconv_gather_sparse_cta_kernel<IdxT>, dim3(M), dim3(256), smem, stream, feats, rowpos, q, s, idx, kp, inv_sigma,
+                          M, N, H, C, HC, order, out));
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
+
 template <int L, bool SPLIT, typename IdxT>
 static int launch_v4(long long warps, const float* feats, const unsigned char* rowpos, const float* q, const float* s,
                      const IdxT* idx, const KPts& kp, float inv_sigma, int M, int N, int H, int C, int NS, const int* order,
@@ -617,13 +722,16 @@ static int launch_gather(const float* feats, const unsigned char* rowpos, const 
   if (C == 32 || C == 64 || (C % 128 == 0 && C <= 4096)) {
     // candidates from the cheapest mapping (largest L, groups = different queries) to the most parallel one
     // (small L, groups split one query's neighbour list); take the first that puts >= `wps` warps on each of 148 SMs.
-    static int dense = -1;
-    if (dense < 0) {
-      const char* e = getenv("RDM_GATHER_DENSE");  // A/B knob: 1 selects the dense cp.async/FFMA2 kernels below
-      dense = (e && e[0] == '1') ? 1 : 0;
+    // RDM_GATHER_MODE (A/B knob): "auto" (default) = CTA-cooperative sparse kernel for C_in % 128 == 0, dense cp.async /
+    // FFMA2 kernels for C_in = 32 / 64 (a 128-byte row is one FFMA per lane and entry: the per-entry bookkeeping of the
+    // sparse forms costs more than the zero FMAs it saves - measured 1.6 vs 4.1 TB/s on G); "dense" / "sparse" / "sparsew"
+    // force the dense, the CTA-cooperative sparse and the warp-per-query sparse kernels wherever they apply.
+    static int mode = -1;
+    if (mode < 0) {
+      const char* e = getenv("RDM_GATHER_MODE");
+      mode = (e == nullptr || e[0] == 'a') ? 0 : (e[0] == 'd' ? 1 : (e[6] == 'w' ? 3 : 2));
     }
-    if (!dense && H <= 1024) {
-      // widest slice per warp (influences computed once per row) that still puts >= 8 warps on every SM
+    if (mode == 3 && H <= 1024) {
       const long long want_w = 148LL * 8;
 #define SPARSE(CPLv, NVv) \
   return launch_sparse<CPLv, NVv, IdxT>(feats, rowpos, q, s, idx, kp, inv_sigma, M, N, H, C, order, out, stream)
@@ -634,25 +742,30 @@ static int launch_gather(const float* feats, const unsigned char* rowpos, const 
       SPARSE(4, 1);
 #undef SPARSE
     }
-    static int wps = 0;
-    if (wps == 0) {
-      const char* e = getenv("RDM_GATHER_WPS");  // tuning knob: warps per SM a mapping must reach before it is taken
-      wps = (e && atoi(e) > 0) ? atoi(e) : 8;  // measured (profiles/r01e): 8 beats 16 on the strided / deep layers
-    }
-    const long long want = 148LL * wps;
+    if ((mode == 0 || mode == 2) && C % 128 == 0 && H <= 256)
+      return launch_sparse_cta<IdxT>(feats, rowpos, q, s, idx, kp, inv_sigma, M, N, H, C, order, out, stream);
+    // dense mappings: candidates from the cheapest (largest L, groups = different queries) to the most parallel (small L,
+    // groups split one query's neighbour list). The kernel keeps 16 warps resident per SM (128 registers), so a launch
+    // runs in ceil(warps / 2368) waves and a split mapping's warps are 1/G as long: take the mapping with the lowest
+    // waves x length product (the strided layers sat at 1.05 waves = 2 passes of full-length warps with the old
+    // "first mapping that fills the machine" rule).
+    auto cost = [](long long warps, double len) { return (double)((warps + 2367) / 2368) * len; };
 #define GATHER4(Lv, SPLITv, warps, NSv) \
   return launch_v4<Lv, SPLITv, IdxT>((warps), feats, rowpos, q, s, idx, kp, inv_sigma, M, N, H, C, (NSv), order, out, stream)
-      if (C == 32) {
-        if (cdiv(M, 4) >= want) GATHER4(8, false, cdiv(M, 4), 1);
+      if (C == 32) {  // split warps: 1/4 of the rows each + the final shuffle reduction (~10 %)
+        if (cost(cdiv(M, 4), 1.0) <= cost(M, 0.275)) GATHER4(8, false, cdiv(M, 4), 1);
         GATHER4(8, true, M, 1);
       } else if (C == 64) {
-        if (cdiv(M, 2) >= want) GATHER4(16, false, cdiv(M, 2), 1);
-        if (M >= want) GATHER4(16, true, M, 1);
+        const double c0 = cost(cdiv(M, 2), 1.0), c1 = cost(M, 0.55), c2 = cost(2LL * M, 0.3);
+        if (c0 <= c1 && c0 <= c2) GATHER4(16, false, cdiv(M, 2), 1);
+        if (c1 <= c2) GATHER4(16, true, M, 1);
         GATHER4(8, true, 2LL * M, 2);
       } else {
-        if ((long long)M * (C / 128) >= want) GATHER4(32, false, (long long)M * (C / 128), C / 128);
-        if ((long long)M * (C / 64) >= want) GATHER4(16, true, (long long)M * (C / 64), C / 64);
-        GATHER4(8, true, (long long)M * (C / 32), C / 32);
+        const long long w0 = (long long)M * (C / 128);
+        const double c0 = cost(w0, 1.0), c1 = cost(2 * w0, 0.55), c2 = cost(4 * w0, 0.3);
+        if (c0 <= c1 && c0 <= c2) GATHER4(32, false, w0, C / 128);
+        if (c1 <= c2) GATHER4(16, true, 2 * w0, C / 64);
+        GATHER4(8, true, 4 * w0, C / 32);
       }
 #undef GATHER4
   }

@@ -27,16 +27,21 @@ for s_ in range(1, 5):
     c = 32 * 2 ** (s_ - 1)
     layers += [(c, c, s_, s_ - 1, SUB[s_ - 1]), (2 * c, 2 * c, s_, s_, NB[s_]), (2 * c, 2 * c, s_, s_, NB[s_])]
 torch.manual_seed(0)
-kp = (torch.randn(15, 3) * 0.4).cuda()
+# kernel points of the pretrained checkpoint, layer by layer (their spread scales with the stage: the sparsity of the
+# influences - ~1.7 non-zero of 15 per neighbour - depends on it; a fixed random set made the deep stages dense)
+CK = os.path.join(ROOT, "tests", "golden", "_big", "rdmnet_state.pt")
+SD = torch.load(CK, map_location="cpu", weights_only=True) if os.path.exists(CK) else None
+NAMES = ["encoder1_1", "encoder1_2"] + [f"encoder{s}_{j}" for s in range(2, 6) for j in (1, 2, 3)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 tot_b = tot_t = 0.0
-print(f"RDM_GATHER_VEC={os.environ.get('RDM_GATHER_VEC', '4')} BG_ORDER={os.environ.get('BG_ORDER', '1')} source={src}")
-for (cin, cout, qs, ss, tab) in layers:
+print(f"RDM_GATHER_MODE={os.environ.get('RDM_GATHER_MODE', 'auto')} BG_ORDER={os.environ.get('BG_ORDER', '1')} source={src}")
+for li, (cin, cout, qs, ss, tab) in enumerate(layers):
     m, h = tab.shape
     n = P[ss].shape[0]
     feats = torch.randn(n, cin, device="cuda") if cin > 1 else torch.ones(n, 1, device="cuda")
     w = torch.zeros(15, cin, 1, device="cuda")
     sigma = 0.6 * 2 ** ss
+    kp = (SD[f'encoder.{NAMES[li]}.KPConv.kernel_points'] if SD is not None else torch.randn(15, 3) * 0.66 * sigma).cuda().contiguous()
     out = torch.empty((m, 15 * cin), device="cuda")
     rowpos = torch.empty(n, dtype=torch.uint8, device="cuda")
     hk = ops._host_copy(kp)

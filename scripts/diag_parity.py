@@ -108,7 +108,7 @@ def main():
     print("== isolated stages on the oracle's inputs")
     with torch.no_grad():
         pc = tp["points"][-1]
-        r1, s1 = model.transformer(pc[:nc].cuda(), pc[nc:].cuda(), ref["feats_s5"][:nc].cuda(), ref["feats_s5"][nc:].cuda())
+        r1, s1 = model.transformer(pc[:nc].cuda(), pc[nc:].cuda(), ref["feats_s5"][:nc].contiguous().cuda(), ref["feats_s5"][nc:].contiguous().cuda())
         print(f"transformer1 ref/src   {rel(r1, ref['ref_feats_t1']):.2e} {rel(s1, ref['src_feats_t1']):.2e}")
         tfc = torch.cat([ref["ref_feats_t1"], ref["src_feats_t1"]], 0)
         sh, vf = model.vote(pc.cuda(), tfc.cuda())
