@@ -445,6 +445,16 @@ int rdm_ransac_correspondences(const float* src_points, const float* ref_points,
                                float* out_transform, int* out_meta, void* workspace, size_t workspace_bytes,
                                rdm_stream_t stream);
 
+/* ---- constant-weight pre-split for the tcgen05 3-term-split GEMM: out_split [2][rows][ld] = tf32 hi / lo of an nn.Linear
+ * weight [rows, ld]. rdm_presplit_register(weight, split) makes the module runners (rdm_encoder/decoder/backbone/
+ * thdroformer/match_forward) feed `split` to the GEMM through two TMA streams instead of splitting the weight tile in
+ * every CTA and k-block; split = NULL unregisters, rdm_presplit_clear() forgets all. The caller owns the buffers and must
+ * re-split after changing a weight (rdmnet_b200.modules does, keyed on the parameters' (pointer, version) fingerprint).
+ * The plain operator rdm_linear never consults the registry. */
+int rdm_presplit_weight(const float* weight, int rows, int ld, float* out_split, rdm_stream_t stream);
+int rdm_presplit_register(const float* weight, const float* split);
+void rdm_presplit_clear(void);
+
 #ifdef __cplusplus
 }
 #endif

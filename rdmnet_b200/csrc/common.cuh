@@ -73,6 +73,10 @@ void rdm_prof_end(int id, cudaStream_t stream);
 int rdm_linear_gn(const float* A, int lda, const float* B, int ldb, int b_is_nk, const float* bias, float* C, int ldc, int M,
                   int N, int K, int act, void* workspace, size_t workspace_bytes, double* gn_stats, int gn_cpg,
                   int* stats_fused, cudaStream_t stream);
+int rdm_linear_gn_ps(const float* A, int lda, const float* B, int ldb, int b_is_nk, const float* bias, float* C, int ldc, int M,
+                     int N, int K, int act, void* workspace, size_t workspace_bytes, double* gn_stats, int gn_cpg,
+                     int* stats_fused, const float* B_split, cudaStream_t stream);
+const float* rdm_presplit_lookup(const float* weight);  // dense.cu: NULL unless registered (rdm_presplit_register)
 int rdm_groupnorm_stats(const float* x, int N, int C, int groups, double* stats_zeroed, cudaStream_t stream);
 int rdm_groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta, const float* residual,
                         float* y, int N, int C, int groups, float eps, int act, float slope, unsigned char* rowpos_out,

@@ -258,12 +258,40 @@ int rdm_linear_tc(const float* A, int lda, const float* B, int ldb, const float*
 // experimental A-in-TMEM variant of the same kernel (gemm_tc_atmem.cu): -1 unless RDM_GEMM_ATMEM=1
 int rdm_linear_tc_atmem(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N, int K,
                         int act, void* workspace, size_t workspace_bytes, int* out_splits, double* gn_stats, int gn_cpg,
-                        int* out_stats_fused, cudaStream_t stream);
+                        int* out_stats_fused, const float* B_split, cudaStream_t stream);
+
+// Registry of pre-split constant weights (weight pointer -> [2][N][ld] tf32 hi / lo copy). ONLY the module runners look
+// weights up here (runtime.cu `linear`): they are entered through the host caches that re-register after any weight change
+// (rdmnet_b200/modules.py cache_key); the public rdm_linear never does, so an in-place weight edit followed by a direct
+// operator call cannot read a stale split.
+#include <unordered_map>
+static std::unordered_map<const void*, const float*> g_presplit;
+extern "C" int rdm_presplit_register(const float* weight, const float* split) {
+  if (split == nullptr) g_presplit.erase(weight);
+  else g_presplit[weight] = split;
+  return RDM_OK;
+}
+extern "C" void rdm_presplit_clear(void) { g_presplit.clear(); }
+const float* rdm_presplit_lookup(const float* weight) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("RDM_GEMM_PRESPLIT");  // A/B knob: 0 ignores the registered splits
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!on) return nullptr;
+  auto it = g_presplit.find(weight);
+  return it == g_presplit.end() ? nullptr : it->second;
+}
 
 extern "C" int rdm_linear(const float* A, int lda, const float* B, int ldb, int b_is_nk, const float* bias, float* C,
                           int ldc, int M, int N, int K, int act, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  return rdm_linear_gn(A, lda, B, ldb, b_is_nk, bias, C, ldc, M, N, K, act, workspace, workspace_bytes, nullptr, 0, nullptr,
-                       stream);
+  static int use_registry = -1;  // RDM_LINEAR_USE_REGISTRY=1 (micro-benchmarks only): the operator consults the registry too
+  if (use_registry < 0) {
+    const char* e = getenv("RDM_LINEAR_USE_REGISTRY");
+    use_registry = (e && e[0] == '1') ? 1 : 0;
+  }
+  return rdm_linear_gn_ps(A, lda, B, ldb, b_is_nk, bias, C, ldc, M, N, K, act, workspace, workspace_bytes, nullptr, 0, nullptr,
+                          (use_registry && b_is_nk) ? rdm_presplit_lookup(B) : nullptr, stream);
 }
 
 // rdm_linear + optional fused GroupNorm statistics of the output: when the shape qualifies, {sum, sumsq} of every group
@@ -272,6 +300,13 @@ extern "C" int rdm_linear(const float* A, int lda, const float* B, int ldb, int 
 int rdm_linear_gn(const float* A, int lda, const float* B, int ldb, int b_is_nk, const float* bias, float* C, int ldc, int M,
                   int N, int K, int act, void* workspace, size_t workspace_bytes, double* gn_stats, int gn_cpg,
                   int* stats_fused, cudaStream_t stream) {
+  return rdm_linear_gn_ps(A, lda, B, ldb, b_is_nk, bias, C, ldc, M, N, K, act, workspace, workspace_bytes, gn_stats, gn_cpg, stats_fused,
+                          nullptr, stream);
+}
+
+int rdm_linear_gn_ps(const float* A, int lda, const float* B, int ldb, int b_is_nk, const float* bias, float* C, int ldc, int M,
+                     int N, int K, int act, void* workspace, size_t workspace_bytes, double* gn_stats, int gn_cpg,
+                     int* stats_fused, const float* B_split, cudaStream_t stream) {
   RDM_CHECK_ARG(M >= 0 && N >= 1 && K >= 1, "rdm_linear: bad shape M=%d N=%d K=%d", M, N, K);
   if (stats_fused) *stats_fused = 0;
   if (M == 0) return RDM_OK;
@@ -284,7 +319,7 @@ int rdm_linear_gn(const float* A, int lda, const float* B, int ldb, int b_is_nk,
   if (use_tc && b_is_nk && M >= 64) {
     int tc_splits = 1;
     int rc = rdm_linear_tc_atmem(A, lda, B, ldb, bias, C, ldc, M, N, K, act, workspace, workspace_bytes, &tc_splits, gn_stats,
-                                 gn_cpg, stats_fused, stream);
+                                 gn_cpg, stats_fused, B_split, stream);
     if (rc == -1)
       rc = rdm_linear_tc(A, lda, B, ldb, bias, C, ldc, M, N, K, act, workspace, workspace_bytes, &tc_splits, gn_stats, gn_cpg,
                          stats_fused, stream);

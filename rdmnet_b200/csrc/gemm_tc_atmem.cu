@@ -50,9 +50,13 @@ struct TcaSmem {
   uint32_t tmem_base;
 };
 
-template <int BN, int STAGES>
+// PS = true: B arrives PRE-SPLIT (constant weights split into tf32 hi / lo once per weights epoch, rdm_presplit_weight):
+// two TMA streams fill b_hi / b_lo directly and the converter warps touch A only - 48 KB less shared-memory traffic and
+// half the converter instructions per k-block of a 128-wide tile.
+template <int BN, int STAGES, bool PS>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_atmem_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                    const __grid_constant__ CUtensorMap map_b,
+                                                                   const __grid_constant__ CUtensorMap map_b_lo,
                                                                    const float* __restrict__ bias, float* __restrict__ C,
                                                                    int ldc, int M, int N, int K, int act, int kb_per_split,
                                                                    double* __restrict__ gn_stats, int gn_cpg,
@@ -77,6 +81,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_atmem_kernel(const 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");  // hide the descriptor fetch behind the set-up
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    if (PS) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
     for (int s = 0; s < STAGES; s++) {
       mbar_init(&sm.raw_full[s], 1);
       mbar_init(&sm.conv_full[s], 4);  // one arrival per converter warp
@@ -102,13 +107,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_atmem_kernel(const 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      constexpr uint32_t bytes = (TC_BM + BN) * TC_BK * sizeof(float);
+      constexpr uint32_t bytes = (TC_BM + (PS ? 2 : 1) * BN) * TC_BK * sizeof(float);
       for (int kb = 0; kb < nk; kb++) {
         const int s = kb % STAGES;
         mbar_wait(&sm.empty[s], ((kb / STAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(&sm.raw_full[s], bytes);
         tma_load_2d(sm.a_raw[s], &map_a, &sm.raw_full[s], (kb0 + kb) * TC_BK, m0);
         tma_load_2d(sm.b_hi[s], &map_b, &sm.raw_full[s], (kb0 + kb) * TC_BK, n0);
+        if (PS) tma_load_2d(sm.b_lo[s], &map_b_lo, &sm.raw_full[s], (kb0 + kb) * TC_BK, n0);
         if (kb == 0) TC_STAMP(2);
       }
     }
@@ -163,16 +169,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_atmem_kernel(const 
         tmem_st32(ta + 32, lo);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
-      float4* bh = reinterpret_cast<float4*>(sm.b_hi[s]);
-      float4* bl = reinterpret_cast<float4*>(sm.b_lo[s]);
+      if (!PS) {
+        float4* bh = reinterpret_cast<float4*>(sm.b_hi[s]);
+        float4* bl = reinterpret_cast<float4*>(sm.b_lo[s]);
 #pragma unroll
-      for (int i = 0; i < BN * TC_BK / 4 / 128; i++) {
-        const float4 v = bh[t + i * 128];
-        const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-        bh[t + i * 128] = h;
-        bl[t + i * 128] = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+        for (int i = 0; i < BN * TC_BK / 4 / 128; i++) {
+          const float4 v = bh[t + i * 128];
+          const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+          bh[t + i * 128] = h;
+          bl[t + i * 128] = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes (B) -> visible to the UMMA reads
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes (B) -> visible to the UMMA reads
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // TMEM stores (A) ordered before the arrive
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.conv_full[s]);
@@ -245,28 +253,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_atmem_kernel(const 
   }
 }
 
-template <int BN, int STAGES>
-int launch_tca(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, float* C, int ldc, int M, int N, int K, int act,
-              int splits, int kb_per_split, double* gn_stats, int gn_cpg, cudaStream_t stream, long long* dbg = nullptr) {
+template <int BN, int STAGES, bool PS>
+int launch_tca(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbl, const float* bias, float* C, int ldc, int M, int N,
+              int K, int act, int splits, int kb_per_split, double* gn_stats, int gn_cpg, cudaStream_t stream,
+              long long* dbg = nullptr) {
   const size_t smem = sizeof(TcaSmem<BN, STAGES>) + 1024;
   // per-device attribute: set on every launch (sub-microsecond), never cached per process
-  RDM_CUDA(cudaFuncSetAttribute(gemm_tf32x3_atmem_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RDM_CUDA(cudaFuncSetAttribute(gemm_tf32x3_atmem_kernel<BN, STAGES, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(N, BN), cdiv(M, TC_BM), splits);
-  RDM_CUDA(rdm_launch_pdl(gemm_tf32x3_atmem_kernel<BN, STAGES>, grid, dim3(TC_THREADS), smem, stream, ma, mb, bias, C, ldc, M, N, K, act,
-                          kb_per_split, gn_stats, gn_cpg, dbg));
+  RDM_CUDA(rdm_launch_pdl(gemm_tf32x3_atmem_kernel<BN, STAGES, PS>, grid, dim3(TC_THREADS), smem, stream, ma, mb, mbl, bias, C, ldc, M, N,
+                          K, act, kb_per_split, gn_stats, gn_cpg, dbg));
   RDM_LAUNCH_CHECK();
   __atomic_fetch_add(&g_tc_launches_ext, 1ull, __ATOMIC_RELAXED);
   return RDM_OK;
 }
 }  // namespace
 
+// ---- constant-weight pre-split: hi = tf32(w), lo = tf32(w - hi), written as [2][rows][ld]
+namespace {
+__global__ void __launch_bounds__(256) presplit_kernel(const float* __restrict__ w, long long n, float* __restrict__ hi, float* __restrict__ lo) {
+  const long long i = blockIdx.x * 256LL + threadIdx.x;
+  if (i >= n) return;
+  const float v = w[i], h = to_tf32(v);
+  hi[i] = h;
+  lo[i] = to_tf32(v - h);
+}
+}  // namespace
+
+extern "C" int rdm_presplit_weight(const float* w, int rows, int ld, float* out_split, cudaStream_t stream) {
+  RDM_CHECK_ARG(rows >= 1 && ld >= 1 && w != nullptr && out_split != nullptr, "rdm_presplit_weight: bad arguments");
+  const long long n = (long long)rows * ld;
+  presplit_kernel<<<cdiv(n, 256), 256, 0, stream>>>(w, n, out_split, out_split + n);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
+
 // Same contract as rdm_linear_tc (gemm_tc.cu). Returns -1 when the variant is off or the shape does not qualify.
 int g_gemm_variant = -1;  // -1 unknown (read RDM_GEMM_ATMEM, default on), 0 off, 1 on
 extern "C" void rdm_debug_gemm_variant(int v) { g_gemm_variant = v ? 1 : 0; }
 
+// B_split (optional): the tf32 hi / lo split of B, [2][N][ldb] floats (rdm_presplit_weight): selects the PS kernels.
 int rdm_linear_tc_atmem(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N, int K,
                         int act, void* workspace, size_t workspace_bytes, int* out_splits, double* gn_stats, int gn_cpg,
-                        int* out_stats_fused, cudaStream_t stream) {
+                        int* out_stats_fused, const float* B_split, cudaStream_t stream) {
   if (g_gemm_variant < 0) {
     const char* e = getenv("RDM_GEMM_ATMEM");
     g_gemm_variant = (e && e[0] == '0') ? 0 : 1;
@@ -292,9 +321,15 @@ int rdm_linear_tc_atmem(const float* A, int lda, const float* B, int ldb, const 
   }
   const int kps = cdiv(nk, splits);
   splits = cdiv(nk, kps);
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mbl;
   if (!make_map(&ma, A, M, K, lda, TC_BM)) return -1;
-  if (!make_map(&mb, B, N, K, ldb, BN)) return -1;
+  if (B_split != nullptr) {
+    if (((uintptr_t)B_split & 15) || !make_map(&mb, B_split, N, K, ldb, BN) || !make_map(&mbl, B_split + (size_t)N * ldb, N, K, ldb, BN))
+      return -1;
+  } else {
+    if (!make_map(&mb, B, N, K, ldb, BN)) return -1;
+    mbl = mb;
+  }
   *out_splits = splits;
   float* out = splits > 1 ? (float*)workspace : C;
   const int ldo = splits > 1 ? N : ldc;
@@ -306,6 +341,10 @@ int rdm_linear_tc_atmem(const float* A, int lda, const float* B, int ldb, const 
     st = gn_stats;
     if (out_stats_fused) *out_stats_fused = 1;
   }
-  if (narrow) return launch_tca<64, 4>(ma, mb, b, out, ldo, M, N, K, a, splits, kps, st, gn_cpg, stream);
-  return launch_tca<128, 3>(ma, mb, b, out, ldo, M, N, K, a, splits, kps, st, gn_cpg, stream);
+  if (B_split != nullptr) {
+    if (narrow) return launch_tca<64, 4, true>(ma, mb, mbl, b, out, ldo, M, N, K, a, splits, kps, st, gn_cpg, stream);
+    return launch_tca<128, 3, true>(ma, mb, mbl, b, out, ldo, M, N, K, a, splits, kps, st, gn_cpg, stream);
+  }
+  if (narrow) return launch_tca<64, 4, false>(ma, mb, mbl, b, out, ldo, M, N, K, a, splits, kps, st, gn_cpg, stream);
+  return launch_tca<128, 3, false>(ma, mb, mbl, b, out, ldo, M, N, K, a, splits, kps, st, gn_cpg, stream);
 }

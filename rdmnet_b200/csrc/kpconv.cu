@@ -742,30 +742,33 @@ static int launch_gather(const float* feats, const unsigned char* rowpos, const 
       SPARSE(4, 1);
 #undef SPARSE
     }
-    if ((mode == 0 || mode == 2) && C % 128 == 0 && H <= 256)
+    // measured on the bench pyramid with the checkpoint's kernel points (profiles/README.md r2c): the CTA-cooperative sparse
+    // kernel wins for C_in >= 256 (M <= ~1300 queries: 31.7 vs 39.9 us, 23.6 vs 28 us) and loses at C_in = 128, M = 3600
+    // (42 vs 35.6 us), where the dense kernel already fills the machine
+    if (((mode == 0 && C >= 256) || mode == 2) && C % 128 == 0 && H <= 256)
       return launch_sparse_cta<IdxT>(feats, rowpos, q, s, idx, kp, inv_sigma, M, N, H, C, order, out, stream);
     // dense mappings: candidates from the cheapest (largest L, groups = different queries) to the most parallel (small L,
-    // groups split one query's neighbour list). The kernel keeps 16 warps resident per SM (128 registers), so a launch
-    // runs in ceil(warps / 2368) waves and a split mapping's warps are 1/G as long: take the mapping with the lowest
-    // waves x length product (the strided layers sat at 1.05 waves = 2 passes of full-length warps with the old
-    // "first mapping that fills the machine" rule).
-    auto cost = [](long long warps, double len) { return (double)((warps + 2367) / 2368) * len; };
+    // groups split one query's neighbour list); take the first that puts >= `wps` warps on each of 148 SMs. (A wave-count
+    // cost model that preferred split mappings for the strided layers measured 10-40 % SLOWER: r2c.)
+    static int wps = 0;
+    if (wps == 0) {
+      const char* e = getenv("RDM_GATHER_WPS");  // tuning knob: warps per SM a mapping must reach before it is taken
+      wps = (e && atoi(e) > 0) ? atoi(e) : 8;  // measured (profiles/r01e): 8 beats 16 on the strided / deep layers
+    }
+    const long long want = 148LL * wps;
 #define GATHER4(Lv, SPLITv, warps, NSv) \
   return launch_v4<Lv, SPLITv, IdxT>((warps), feats, rowpos, q, s, idx, kp, inv_sigma, M, N, H, C, (NSv), order, out, stream)
-      if (C == 32) {  // split warps: 1/4 of the rows each + the final shuffle reduction (~10 %)
-        if (cost(cdiv(M, 4), 1.0) <= cost(M, 0.275)) GATHER4(8, false, cdiv(M, 4), 1);
+      if (C == 32) {
+        if (cdiv(M, 4) >= want) GATHER4(8, false, cdiv(M, 4), 1);
         GATHER4(8, true, M, 1);
       } else if (C == 64) {
-        const double c0 = cost(cdiv(M, 2), 1.0), c1 = cost(M, 0.55), c2 = cost(2LL * M, 0.3);
-        if (c0 <= c1 && c0 <= c2) GATHER4(16, false, cdiv(M, 2), 1);
-        if (c1 <= c2) GATHER4(16, true, M, 1);
+        if (cdiv(M, 2) >= want) GATHER4(16, false, cdiv(M, 2), 1);
+        if (M >= want) GATHER4(16, true, M, 1);
         GATHER4(8, true, 2LL * M, 2);
       } else {
-        const long long w0 = (long long)M * (C / 128);
-        const double c0 = cost(w0, 1.0), c1 = cost(2 * w0, 0.55), c2 = cost(4 * w0, 0.3);
-        if (c0 <= c1 && c0 <= c2) GATHER4(32, false, w0, C / 128);
-        if (c1 <= c2) GATHER4(16, true, 2 * w0, C / 64);
-        GATHER4(8, true, 4 * w0, C / 32);
+        if ((long long)M * (C / 128) >= want) GATHER4(32, false, (long long)M * (C / 128), C / 128);
+        if ((long long)M * (C / 64) >= want) GATHER4(16, true, (long long)M * (C / 64), C / 64);
+        GATHER4(8, true, (long long)M * (C / 32), C / 32);
       }
 #undef GATHER4
   }

@@ -41,7 +41,9 @@ int linear(Arena& a, const float* A, int lda, const float* W, int ldw, int nk, c
     ws = a.raw(wsb);
   }
   int rc = RDM_OK;
-  if (!a.dry) rc = rdm_linear_gn(A, lda, W, ldw, nk, bias, C, ldc > 0 ? ldc : N, M, N, K, 0, ws, wsb, gn_stats, gn_cpg, stats_fused, st);
+  if (!a.dry)
+    rc = rdm_linear_gn_ps(A, lda, W, ldw, nk, bias, C, ldc > 0 ? ldc : N, M, N, K, 0, ws, wsb, gn_stats, gn_cpg, stats_fused,
+                          nk ? rdm_presplit_lookup(W) : nullptr, st);
   a.off = mark;
   return rc;
 }

@@ -287,7 +287,29 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-def _unary_desc(u, keep=None):
+def _presplit_reset(owner):
+    """Unregisters the pre-split weights `owner` registered earlier (their buffers are about to be dropped)."""
+    for key in getattr(owner, "_ps_keys", []):
+        L.lib().rdm_presplit_register(key, None)
+    owner._ps_keys = []
+
+
+def _presplit(owner, w, keep):
+    """Registers the tf32 hi / lo split of a constant nn.Linear-layout weight (rows, ld) with the library, so that the
+    runners' tcgen05 GEMMs stream it through two TMA descriptors instead of splitting the tile in every CTA (include/
+    rdm_sm100.h: rdm_presplit_weight). Called only from the fingerprint-guarded descriptor builders."""
+    if w is None or not w.is_cuda or w.dtype != torch.float32 or w.ndim != 2 or not w.is_contiguous():
+        return
+    if w.shape[1] % 4 != 0 or w.data_ptr() % 16 != 0 or w.shape[0] < 8 or w.shape[1] < 8:
+        return  # not TMA-eligible: the GEMM dispatcher takes the SIMT kernel for it anyway
+    split = torch.empty((2,) + tuple(w.shape), dtype=torch.float32, device=w.device)
+    L.call("rdm_presplit_weight", w.data_ptr(), w.shape[0], w.shape[1], split.data_ptr(), L.stream())
+    L.lib().rdm_presplit_register(w.data_ptr(), split.data_ptr())
+    keep.append(split)
+    owner._ps_keys.append(w.data_ptr())
+
+
+def _unary_desc(u, keep=None, owner=None):
     """rdm_unary_desc of a UnaryBlock / LastUnaryBlock (NULL weight for nn.Identity / None). With `keep` (a list that
     outlives the descriptor) a weight whose in_features is not a multiple of 4 is passed as a zero-padded copy with a
     16-byte row stride, which qualifies the layer for the TMA-fed tensor-core GEMM."""
@@ -301,6 +323,8 @@ def _unary_desc(u, keep=None):
         wp[:, :u.mlp.in_features] = w.detach()
         keep.append(wp)
         w = wp
+    if owner is not None and keep is not None:
+        _presplit(owner, w.detach(), keep)
     return L.UnaryDesc(_p(w), _p(u.mlp.bias), _p(norm.norm.weight) if norm is not None else None,
                        _p(norm.norm.bias) if norm is not None else None, u.mlp.in_features, u.mlp.out_features, ldw)
 
@@ -364,6 +388,7 @@ class Encoder(_Module):
             names = ["encoder1_1", "encoder1_2"] + [f"encoder{s}_{j}" for s in range(2, 6) for j in (1, 2, 3)]
             arr = (L.BlockDesc * len(names))()
             keep = []
+            _presplit_reset(self)
             for i, name in enumerate(names):
                 b, stage = getattr(self, name), int(name[7]) - 1
                 kp = b.KPConv
@@ -374,11 +399,13 @@ class Encoder(_Module):
                     d.norm_conv_w, d.norm_conv_b = _p(b.norm.norm.weight), _p(b.norm.norm.bias)
                     d.c_in, d.c_out, d.strided = b.in_channels, b.out_channels, 0
                 else:
-                    d.unary1, d.unary2, d.shortcut = _unary_desc(b.unary1), _unary_desc(b.unary2), _unary_desc(b.unary_shortcut)
+                    d.unary1, d.unary2, d.shortcut = (_unary_desc(b.unary1, keep, self), _unary_desc(b.unary2, keep, self),
+                                                      _unary_desc(b.unary_shortcut, keep, self))
                     d.norm_conv_w, d.norm_conv_b = _p(b.norm_conv.norm.weight), _p(b.norm_conv.norm.bias)
                     d.c_in, d.c_out, d.strided = b.in_channels, b.out_channels, 1 if b.strided else 0
                 wt = kp.weights.detach().reshape(-1, kp.out_channels).t().contiguous()  # [C_out, 15*C_in]
                 keep.append(wt)
+                _presplit(self, wt, keep)
                 d.kpconv_w, d.kpconv_wt, d.kpconv_b = _p(kp.weights), _p(wt), _p(kp.bias)
                 d.kernel_points, d.h_kernel_points = _p(kp.kernel_points), hk.data_ptr()
                 d.c_mid_in, d.c_mid_out, d.stage, d.sigma = kp.in_channels, kp.out_channels, stage, float(kp.sigma)
@@ -436,8 +463,9 @@ class Decoder(_Module):
         key = _state_key(self)
         if getattr(self, "_desc_key", None) != key:
             keep = []
-            arr = (L.UnaryDesc * 3)(_unary_desc(self.decoder4, keep), _unary_desc(self.decoder3, keep),
-                                    _unary_desc(self.decoder2, keep))
+            _presplit_reset(self)
+            arr = (L.UnaryDesc * 3)(_unary_desc(self.decoder4, keep, self), _unary_desc(self.decoder3, keep, self),
+                                    _unary_desc(self.decoder2, keep, self))
             self._descs, self._desc_keep, self._desc_key = arr, keep, key
         return self._descs
 
@@ -557,6 +585,10 @@ class RDMNet(_Module):
             if len(mods) != 6 or v.max_offset_limit is None:
                 raise RuntimeError("rdm_match_forward expects the RDMNet vote head: two (Linear, LayerNorm, ReLU) stages")
             d = L.MatchDesc()
+            ps_keep = []
+            _presplit_reset(self)
+            for w_ in (mods[0].weight, mods[3].weight, v.ctr_reg.weight):
+                _presplit(self, w_.detach(), ps_keep)
             d.v_w0, d.v_b0, d.v_g0, d.v_e0 = _p(mods[0].weight), _p(mods[0].bias), _p(mods[1].weight), _p(mods[1].bias)
             d.v_w1, d.v_b1, d.v_g1, d.v_e1 = _p(mods[3].weight), _p(mods[3].bias), _p(mods[4].weight), _p(mods[4].bias)
             d.v_wr, d.v_br = _p(v.ctr_reg.weight), _p(v.ctr_reg.bias)
@@ -576,7 +608,7 @@ class RDMNet(_Module):
             d.dual_normalization = 1 if self.coarse_matching.dual_normalization else 0
             d.sinkhorn_iterations, d.correspondence_threshold = int(ot.num_iterations), int(fm.correspondence_threshold)
             d.refinement_steps = int(fm.num_refinement_steps)
-            self._mdesc, self._mdesc_keep, self._mdesc_key = d, (t2, alpha), key
+            self._mdesc, self._mdesc_keep, self._mdesc_key = d, (t2, alpha, ps_keep), key
         return self._mdesc
 
     def _match_tail(self, out, points_c, lengths_c, nc_ref, tf, n2p, points_f, nf_ref, feats_f):

@@ -407,6 +407,11 @@ class ThDRoFormer(_Module):
         key = cache_key(self)
         if getattr(self, "_desc_key", None) != key:
             blobs = [layer.fused_blob() for layer in tr.layers]
+            from .model import _presplit, _presplit_reset
+            ps_keep = []
+            _presplit_reset(self)
+            _presplit(self, self.in_proj.weight.detach(), ps_keep)
+            _presplit(self, self.out_proj.weight.detach(), ps_keep)
             d = L.ThdroformerDesc()
             d.emb_w, d.emb_b = self.embedding.proj.weight.data_ptr(), self.embedding.proj.bias.data_ptr()
             d.in_w, d.in_b = self.in_proj.weight.data_ptr(), self.in_proj.bias.data_ptr()
@@ -414,7 +419,7 @@ class ThDRoFormer(_Module):
             for i, (b, kind) in enumerate(zip(blobs, tr.blocks)):
                 d.layer_blobs[i], d.is_self[i] = b.data_ptr(), 1 if kind == "self" else 0
             d.num_layers, d.c_in, d.c_out = len(blobs), self.in_proj.in_features, self.out_proj.out_features
-            self._desc, self._desc_key = d, key
+            self._desc, self._desc_key, self._desc_keep = d, key, ps_keep
         return self._desc
 
     def _forward_runner(self, rp, sp, rf, sf):

@@ -132,7 +132,7 @@ def isotropic_transform_error(gt_transforms, transforms, reduction="mean"):
 
 # ------------------------------------------------------------------------------------------------------------ RANSAC
 def registration_with_ransac_from_correspondences(src_points, ref_points, correspondences=None, distance_threshold=0.05,
-                                                  ransac_n=3, num_iterations=10000, seed=7351):
+                                                  ransac_n=3, num_iterations=10000, seed=7351, return_info=False):
     """geotransformer/utils/open3d.py:173-203 with the hypotheses evaluated on the GPU (rdm_ransac_correspondences):
     numpy (or tensor) points in, (4,4) float64 numpy transform from src to ref out, like the open3d call it replaces.
     Sampling is a counter-based generator, so results are reproducible for a given `seed` (open3d's are not)."""
@@ -147,11 +147,15 @@ def registration_with_ransac_from_correspondences(src_points, ref_points, corres
     src, ref = src.contiguous(), ref.contiguous()
     c = src.shape[0]
     if c < ransac_n:
-        return np.eye(4)
+        return (np.eye(4), {"inliers": 0, "iteration": -1}) if return_info else np.eye(4)
     T = torch.empty((4, 4), dtype=torch.float32, device=dev)
     meta = torch.empty(2, dtype=torch.int32, device=dev)
     wsb = int(L.lib().rdm_ransac_workspace(c))
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     L.call("rdm_ransac_correspondences", L.ptr(src), L.ptr(ref), c, float(distance_threshold), int(ransac_n), int(num_iterations),
            int(seed), L.ptr(T), L.ptr(meta), L.ptr(ws), wsb, L.stream())
-    return T.cpu().numpy().astype(np.float64)
+    Th = T.cpu().numpy().astype(np.float64)
+    if return_info:
+        inl, it = meta.tolist()
+        return Th, {"inliers": int(inl), "iteration": int(it)}
+    return Th

@@ -9,12 +9,16 @@ shapes = [(23319, 32, 64), (23319, 32, 480), (23319, 128, 32), (23319, 128, 64),
           (8841, 257, 768), (3078, 128, 1920), (3078, 512, 1536), (3078, 512, 128), (1106, 256, 3840), (1106, 1024, 256),
           (494, 512, 7680), (494, 2048, 512), (494, 1024, 1284), (431, 128, 2048), (128, 64, 32), (128, 64, 128)]
 iters = int(os.environ.get("BG_ITERS", "20"))
-print("RDM_GEMM_TC=", os.environ.get("RDM_GEMM_TC", "1"))
+print("RDM_GEMM_TC=", os.environ.get("RDM_GEMM_TC", "1"), "presplit registry:", os.environ.get("RDM_LINEAR_USE_REGISTRY", "0"))
 tot = 0.0
 for m, n, k in shapes:
     x = torch.randn(m, k, device="cuda")
     w = torch.randn(n, k, device="cuda") / k ** 0.5
     b = torch.randn(n, device="cuda")
+    if os.environ.get("RDM_LINEAR_USE_REGISTRY", "0") == "1" and k % 4 == 0:  # pre-split weights (what the runners use)
+        split = torch.empty((2, n, k), device="cuda")
+        L.call("rdm_presplit_weight", w.data_ptr(), n, k, split.data_ptr(), L.stream())
+        L.lib().rdm_presplit_register(w.data_ptr(), split.data_ptr())
     for _ in range(2 if iters > 1 else 0):
         ops.linear(x, w, b)
     torch.cuda.synchronize()

@@ -27,12 +27,19 @@ def rel(got, ref):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pair", default="p04")
+    ap.add_argument("--synthetic", default=None, help="size class (4k/8k/16k/32k) of a synthetic pair instead of a bundled one")
+    ap.add_argument("--pair-id", type=int, default=11)
     args = ap.parse_args()
     from rdmnet_b200 import ops
     from rdmnet_b200.model import create_model
     scans = dict(np.load(os.path.join(ROOT, "tests", "golden", "scans.npz")))
     sd = torch.load(os.path.join(ROOT, "tests", "golden", "_big", "rdmnet_state.pt"), map_location="cpu", weights_only=True)
     a, b = scans["s000000"], scans["s000004" if args.pair == "p04" else "s000007"]
+    if args.synthetic:
+        from rdmnet_b200 import synthetic
+        ne, na = synthetic.SIZE_CLASSES[args.synthetic]
+        pr = synthetic.make_pair(pair_id=args.pair_id, n_elev=ne, n_azim=na)
+        a, b = pr["ref_points"], pr["src_points"]
     pyr = OP.precompute_pyramid(np.concatenate([a, b]), [len(a), len(b)], 5, 0.3, 4.25 * 0.3, MO.DEFAULT_LIMITS,
                                 "ref" if OP.ref_available() else "port")
     tp = MO.pyramid_to_torch(pyr)
