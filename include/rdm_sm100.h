@@ -455,6 +455,15 @@ int rdm_presplit_weight(const float* weight, int rows, int ld, float* out_split,
 int rdm_presplit_register(const float* weight, const float* split);
 void rdm_presplit_clear(void);
 
+/* ---- ingest: voxel-barycentre downsample of a raw scan on the GPU, what the reference does offline with open3d
+ * (preporcess/downsample_pcd_kitti.py:20-36, voxel_down_sample(0.3)): voxel index = floor((p - (min_bound - voxel/2)) / voxel),
+ * output = mean of the points (and of the 4th column, the intensity, when stride = 4) of every occupied voxel, emitted in
+ * the order of each voxel's first point in the input (open3d's own order is its hash map's, i.e. unspecified).
+ * points [n, stride] with stride 3 or 4; out [n, stride] capacity; *out_count = number of voxels. Deterministic. */
+size_t rdm_voxel_downsample_workspace(int n);
+int rdm_voxel_downsample(const float* points, int stride, int n, float voxel, float* out, int* out_count, void* workspace,
+                         size_t workspace_bytes, rdm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

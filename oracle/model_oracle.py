@@ -327,9 +327,11 @@ def lgr(ref_knn_pts, src_knn_pts, ref_knn_masks, src_knn_masks, score_mat, cfg=C
 
 
 # ----------------------------------------------------------------------------- whole forward
-def forward(sd, pyr, nms_search, cfg=CFG):
+def forward(sd, pyr, nms_search, cfg=CFG, use_vote=True):
     """experiments/model_infer.py:109-354. pyr = tensors of oracle.pyramid.precompute_pyramid;
-    nms_search(points (N,3) tensor, lengths) -> (N,H) int64 neighbour table (vote.py:24-31)."""
+    nms_search(points (N,3) tensor, lengths) -> (N,H) int64 neighbour table (vote.py:24-31).
+    use_vote=False: the Mulran configuration (experiments/infer.py:119-120, model_infer.py:59,180): vote layer, NMS and the
+    second transformer are skipped, the superpoints are the coarsest pyramid level."""
     out = {}
     P, L = pyr["points"], pyr["lengths"]
     nc, nf = int(L[-1][0]), int(L[1][0])
@@ -346,13 +348,16 @@ def forward(sd, pyr, nms_search, cfg=CFG):
     feats_f = dec[:, :-1]
     out["feats_f"] = feats_f
     out["p2p_logit"] = dec[:, -1]
-    shifted, fc = vote_layer(sd, "vote.", pts_c, torch.cat([rf, sf], 0))
-    out["shifted_points_c"], out["vote_feats_c"] = shifted, fc
-    masks = nms_greedy(nms_search(shifted, L[-1]))
-    out["nms_masks"] = masks
-    rm, sm = masks[:nc], masks[nc:]
-    ref_pc, src_pc = shifted[:nc][rm], shifted[nc:][sm]
-    rf2, sf2 = thdroformer(sd, "transformer2.", ref_pc, src_pc, fc[:nc][rm], fc[nc:][sm])
+    if use_vote:
+        shifted, fc = vote_layer(sd, "vote.", pts_c, torch.cat([rf, sf], 0))
+        out["shifted_points_c"], out["vote_feats_c"] = shifted, fc
+        masks = nms_greedy(nms_search(shifted, L[-1]))
+        out["nms_masks"] = masks
+        rm, sm = masks[:nc], masks[nc:]
+        ref_pc, src_pc = shifted[:nc][rm], shifted[nc:][sm]
+        rf2, sf2 = thdroformer(sd, "transformer2.", ref_pc, src_pc, fc[:nc][rm], fc[nc:][sm])
+    else:
+        ref_pc, src_pc, rf2, sf2 = pts_c[:nc], pts_c[nc:], rf, sf
     rfn, sfn = F.normalize(rf2, p=2, dim=1), F.normalize(sf2, p=2, dim=1)
     out["ref_points_c"], out["src_points_c"], out["ref_feats_c"], out["src_feats_c"] = ref_pc, src_pc, rfn, sfn
     ref_pf, src_pf = pts_f[:nf], pts_f[nf:]

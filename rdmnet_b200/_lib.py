@@ -81,6 +81,8 @@ SIGNATURES = {
     "rdm_index_select": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_int, c_i64, c_void_p, c_void_p, c_void_p]),
     "rdm_apply_transform": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdm_neighbor_histogram": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "rdm_voxel_downsample_workspace": (c_size_t, [c_int]),
+    "rdm_voxel_downsample": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "rdm_presplit_weight": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "rdm_presplit_register": (c_int, [c_void_p, c_void_p]),
     "rdm_presplit_clear": (None, []),

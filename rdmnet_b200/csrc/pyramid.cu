@@ -705,3 +705,72 @@ extern "C" int rdm_radius_search(const float* q_points, const float* s_points, c
                                 out_indices, index_bytes, out_counts, out_max_count, nullptr, workspace, workspace_bytes,
                                 stream);
 }
+
+
+// ---------------------------------------------------------------------------------------------- walk order by load
+// order_out = order_in stably partitioned into 4 classes of neighbourhood fill (>= 3/4, >= 1/2, >= 1/4 of the H slots valid,
+// less), heaviest class first. Rows of the table are valid-first, so a class test is one probe. The KPConv gather walks
+// its queries in this order: neighbours in space stay neighbours inside a class (L1 reuse), and the partial last wave of
+// the launch is made of the cheapest queries. One CTA; two passes over <= ~40 k entries.
+__device__ __forceinline__ int load_class(const int* __restrict__ nb, int q, int H, int N) {
+  const int* row = nb + (size_t)q * H;
+  if (row[(3 * H) / 4 - 1 < 0 ? 0 : (3 * H) / 4 - 1] < N) return 0;
+  if (row[H / 2 - 1 < 0 ? 0 : H / 2 - 1] < N) return 1;
+  if (row[H / 4 - 1 < 0 ? 0 : H / 4 - 1] < N) return 2;
+  return 3;
+}
+__global__ void __launch_bounds__(1024) order_by_load_kernel(const int* __restrict__ order_in, const int* __restrict__ nb, int n, int H,
+                                                             int N, int* __restrict__ order_out) {
+  __shared__ int s_cnt[4], s_base[4], s_warp[32][4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 4) s_cnt[tid] = 0;
+  __syncthreads();
+  int local[4] = {0, 0, 0, 0};
+  for (int i = tid; i < n; i += 1024) local[load_class(nb, order_in[i], H, N)]++;
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const int v = warp_sum_i(local[c]);
+    if (lane == 0 && v) atomicAdd(&s_cnt[c], v);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int c = 0; c < 4; c++) {
+      s_base[c] = acc;
+      acc += s_cnt[c];
+    }
+  }
+  __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += 1024) {
+    const int i = i0 + tid;
+    const int q = i < n ? order_in[i] : 0;
+    const int c = i < n ? load_class(nb, q, H, N) : -1;
+    int pos = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const unsigned m = __ballot_sync(FULL_MASK, c == k);
+      if (c == k) pos = __popc(m & ((1u << lane) - 1u));
+      if (lane == 0) s_warp[warp][k] = __popc(m);
+    }
+    __syncthreads();
+    if (c >= 0) {
+      int before = 0;
+      for (int w = 0; w < warp; w++) before += s_warp[w][c];
+      order_out[s_base[c] + before + pos] = q;
+    }
+    __syncthreads();
+    if (tid < 4) {
+      int tot = 0;
+      for (int w = 0; w < 32; w++) tot += s_warp[w][tid];
+      s_base[tid] += tot;
+    }
+    __syncthreads();
+  }
+}
+
+int rdm_order_by_load(const int* order_in, const int* neighbors, int n, int H, int n_support, int* order_out, cudaStream_t stream) {
+  if (n <= 0) return RDM_OK;
+  order_by_load_kernel<<<1, 1024, 0, stream>>>(order_in, neighbors, n, H, n_support, order_out);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}

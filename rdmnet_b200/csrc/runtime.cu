@@ -390,7 +390,7 @@ size_t pyramid_bytes(int64_t n0, const rdm_pyramid_cfg& c) {
   b += align_up(sizeof(int) * 64, 256);  // max counts
   for (int s = 1; s < c.num_stages; s++) b += align_up(n * 12, 256);
   for (int s = 0; s < c.num_stages; s++) {
-    b += align_up(n * 4, 256);                       // order
+    b += 2 * align_up(n * 4, 256);                   // order (cell-sorted) + order by load
     b += align_up(n * 4 * (size_t)c.limits[s], 256);  // neighbors
     if (s + 1 < c.num_stages) {
       b += align_up(n * 4 * (size_t)c.limits[s], 256);  // subsampling
@@ -523,6 +523,20 @@ extern "C" int rdm_build_pyramid_finish(void* job, rdm_pyramid_desc* h_desc, int
     d.nb_width[s] = c.limits[s];
     RDM_TRY(rdm_radius_search_impl(pts[s], pts[s], h_d_lengths[s], h_d_lengths[s], B, n, n, n, radius, c.limits[s], nb, 4, nullptr,
                                    d_maxc + nsearch++, order, workspace, workspace_bytes, stream));
+    {
+      // heaviest-first walk order for the KPConv gathers: the cell-sorted order stably partitioned by neighbourhood fill,
+      // so that the last (partial) wave of gather CTAs holds the light queries (RDM_GATHER_HEAVY_FIRST=0 keeps cell order)
+      int* order2 = out.get<int>((size_t)(n > 0 ? n : 1));
+      static int heavy = -1;
+      if (heavy < 0) {
+        const char* e = getenv("RDM_GATHER_HEAVY_FIRST");
+        heavy = (e && e[0] == '0') ? 0 : 1;
+      }
+      if (heavy && n > 0 && out.ok) {
+        RDM_TRY(rdm_order_by_load(order, nb, n, c.limits[s], n, order2, stream));
+        d.order[s] = order2;
+      }
+    }
     if (s + 1 < S) {
       const int m = d.n[s + 1];
       int* sub = out.get<int>((size_t)(m > 0 ? m : 1) * c.limits[s]);

@@ -246,7 +246,10 @@ def test_forward_vs_oracle_on_synthetic_pairs(model, pretrained_state, name, pai
     p = synthetic.make_pair(pair_id=pair_id, **kw)
     pts = np.concatenate([p["ref_points"], p["src_points"]])
     lens = [len(p["ref_points"]), len(p["src_points"])]
-    pyr = OP.precompute_pyramid(pts, lens, 5, 0.3, 4.25 * 0.3, MO.DEFAULT_LIMITS, "ref" if OP.ref_available() else "port")
+    # "port" = the C restatement with the canonical (d2, index) order inside exact-distance ties, which is also the GPU's:
+    # the reference core leaves such ties in KD-tree / introsort order, and on voxel-barycentre clouds a tie that straddles
+    # the neighbour limit changes WHICH neighbour is kept - a different, equally valid table
+    pyr = OP.precompute_pyramid(pts, lens, 5, 0.3, 4.25 * 0.3, MO.DEFAULT_LIMITS, "port")
     tp = MO.pyramid_to_torch(pyr)
     torch.set_num_threads(16)
     with torch.no_grad():
@@ -277,3 +280,30 @@ def test_forward_vs_oracle_on_synthetic_pairs(model, pretrained_state, name, pai
     rte = np.linalg.norm(T[:3, 3] - Tg[:3, 3])
     print(f"[parity] {name}: RRE {rre:.3f} deg, RTE {rte:.3f} m vs synthetic ground truth")
     assert rre < 5.0 and rte < 2.0
+
+
+def test_forward_without_vote_branch_vs_oracle(pretrained_state, scans):
+    """The Mulran configuration (experiments/infer.py:119-120: cfg.Vote.inference_use_vote = False; model_infer.py:59,180): no
+    vote layer / NMS / second transformer, superpoints = the coarsest pyramid level. Same checkpoint, same bars."""
+    from rdmnet_b200.model import create_model, make_cfg
+    cfg = make_cfg()
+    cfg.Vote.inference_use_vote = False
+    m = create_model(cfg)
+    m.load_state_dict(pretrained_state, strict=True)
+    m = m.cuda().eval()
+    assert not m.use_vote
+    a, b = scans["s000000"], scans["s000004"]
+    pts = np.concatenate([a, b])
+    pyr = OP.precompute_pyramid(pts, [len(a), len(b)], 5, 0.3, 4.25 * 0.3, MO.DEFAULT_LIMITS, "port")
+    with torch.no_grad():
+        ref = MO.forward(pretrained_state, MO.pyramid_to_torch(pyr), None, use_vote=False)
+    out = m({"points": torch.from_numpy(pts).cuda(), "lengths": torch.tensor([len(a), len(b)], dtype=torch.int64).cuda()})
+    assert out["ref_points_c"].shape[0] == 431 and "mask" not in out
+    assert_node_corr_equal(out["ref_node_corr_indices"].cpu().numpy(), out["src_node_corr_indices"].cpu().numpy(),
+                           out["node_corr_scores"].cpu().numpy(), ref["ref_node_corr_indices"].numpy(),
+                           ref["src_node_corr_indices"].numpy())
+    got_c = np.concatenate([out["ref_corr_points"].cpu().numpy(), out["src_corr_points"].cpu().numpy()], 1)
+    ref_c = np.concatenate([ref["ref_corr_points"].numpy(), ref["src_corr_points"].numpy()], 1)
+    assert {tuple(r) for r in got_c.tolist()} == {tuple(r) for r in ref_c.tolist()}, "correspondence set"
+    close(out["ref_feats_c"], ref["ref_feats_c"], 1e-4, "no-vote ref_feats_c")
+    close(out["estimated_transform"], ref["estimated_transform"], 1e-4, "no-vote estimated_transform")

@@ -153,3 +153,21 @@ def test_end_to_end_vs_reference_pair04(scans, golden_pairs, pretrained_state):
     assert np.array_equal(out["src_corr_points"].numpy(), g["p04_src_corr_points"])
     close(out["corr_scores"], g["p04_corr_scores"], 1e-3)
     close(out["estimated_transform"], g["p04_estimated_transform"], 1e-4)
+
+
+def test_ingest_oracle_properties():
+    """oracle/ingest_oracle.py (open3d voxel_down_sample semantics, parity unpinned against open3d itself: the package is absent):
+    one output per occupied voxel, each the mean of exactly its points, voxels in first-occurrence order."""
+    from oracle import ingest_oracle as IO
+    rng = np.random.default_rng(5)
+    p = np.concatenate([rng.normal(0, 3, (4000, 3)), rng.random((4000, 1))], 1).astype(np.float32)
+    out = IO.voxel_downsample(p, 0.3)
+    o = p[:, :3].min(0) - np.float32(0.15)
+    idx = np.floor((p[:, :3] - o) / np.float32(0.3)).astype(np.int64)
+    uniq, first, inv = np.unique(idx, axis=0, return_index=True, return_inverse=True)
+    assert out.shape == (uniq.shape[0], 4)
+    order = np.argsort(first)
+    k = order[0]  # the first voxel of the output is the voxel of point 0
+    assert np.array_equal(idx[0], uniq[k])
+    assert np.allclose(out[0], p[inv.reshape(-1) == k].astype(np.float64).mean(0), atol=1e-6)
+    assert abs(out[:, 3].mean() - 0.5) < 0.05  # intensities are averaged like coordinates
