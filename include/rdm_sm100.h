@@ -464,6 +464,33 @@ size_t rdm_voxel_downsample_workspace(int n);
 int rdm_voxel_downsample(const float* points, int stride, int n, float voxel, float* out, int* out_count, void* workspace,
                          size_t workspace_bytes, rdm_stream_t stream);
 
+/* ---- training path: backward of the KPConv backbone operators (the reference differentiates its ~15-launch ATen graphs
+ * per operator with autograd: geotransformer/modules/kpconv/kpconv.py:79-122, modules.py:33-225, functional.py:6-67;
+ * experiments/trainval.py:43-50 -> loss.backward(), engine/epoch_based_trainer.py:104). Gradients are fp32. */
+/* d s_feats [N, C_in] of rdm_kpconv_gather given d out_weighted [M, 15*C_in] (the neighbour count is a constant of the
+ * backward pass, as in the reference: it comes from a comparison). d_s_feats is zeroed here; rowpos_scratch: N bytes. */
+int rdm_kpconv_gather_bwd(const float* d_weighted, const float* s_feats, const float* q_points, const float* s_points,
+                          const void* neighbor_indices, int index_bytes, const float* h_kernel_points, float sigma, int M, int N,
+                          int H, int C_in, unsigned char* rowpos_scratch, float* d_s_feats, rdm_stream_t stream);
+/* y [cols, rows] = x^T for x [rows, cols] with row stride ldx (dW = dY^T X and dX = dY W go through rdm_linear). */
+int rdm_transpose(const float* x, int rows, int cols, int ldx, float* y, rdm_stream_t stream);
+/* out[c] += sum_r x[r, c] (bias gradient); the caller zeroes out for a plain sum. */
+int rdm_colsum(const float* x, int rows, int cols, int ldx, float* out_zeroed_or_accum, rdm_stream_t stream);
+/* GroupNorm (+ LeakyReLU act = 1) backward (kpconv/modules.py:33-50, 78-83): dx [N,C], dgamma [C], dbeta [C]; dz_scratch [N,C]
+ * receives dy * act'(.) = the gradient of the residual input; scratch: 2*groups and 2*C doubles. */
+int rdm_groupnorm_bwd(const float* x, const float* y, const float* dy, const float* gamma, int N, int C, int groups, float eps,
+                      int act, float slope, double* stats_scratch, double* dgamma_dbeta_scratch, float* dz_scratch, float* dx,
+                      float* dgamma, float* dbeta, rdm_stream_t stream);
+/* LayerNorm (+ residual, + ReLU act = 2) backward: dx [N,C] (= d residual); dgamma / dbeta are ACCUMULATED into. */
+int rdm_layernorm_bwd(const float* x, const float* residual, const float* y, const float* dy, const float* gamma, int N, int C,
+                      float eps, int act, float* dx, float* dgamma_accum, float* dbeta_accum, rdm_stream_t stream);
+int rdm_maxpool_bwd(const float* feats, const void* neighbor_indices, int index_bytes, const float* d_out, int M, int N, int H,
+                    int C, float* d_feats_zeroed, rdm_stream_t stream);
+int rdm_upsample_concat_bwd(const float* d_out, const void* upsample_indices, int index_bytes, int index_stride, int M, int N,
+                            int C1, int C2, float* d_feats_zeroed, float* d_skip, rdm_stream_t stream);
+/* act: 1 LeakyReLU(slope), 2 ReLU, 3 clamp(sigmoid(x), 0, 1); y = the forward OUTPUT. */
+int rdm_activation_bwd(const float* y, const float* dy, int64_t n, int act, float slope, float* dx, rdm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,17 @@ SIGNATURES = {
     "rdm_index_select": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_int, c_i64, c_void_p, c_void_p, c_void_p]),
     "rdm_apply_transform": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdm_neighbor_histogram": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "rdm_kpconv_gather_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_float, c_int, c_int, c_int,
+                                      c_int, c_void_p, c_void_p, c_void_p]),
+    "rdm_transpose": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "rdm_colsum": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "rdm_groupnorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_float, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rdm_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_void_p]),
+    "rdm_maxpool_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "rdm_upsample_concat_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "rdm_activation_bwd": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_float, c_void_p, c_void_p]),
     "rdm_voxel_downsample_workspace": (c_size_t, [c_int]),
     "rdm_voxel_downsample": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "rdm_presplit_weight": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),

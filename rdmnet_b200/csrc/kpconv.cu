@@ -26,6 +26,13 @@ __global__ void row_positive_kernel(const float* __restrict__ f, int n, int c, u
   if (lane == 0) flag[row] = s > 0.f ? 1 : 0;
 }
 
+int rdm_row_positive(const float* f, int n, int c, unsigned char* flag, cudaStream_t stream) {
+  if (n <= 0) return RDM_OK;
+  row_positive_kernel<<<cdiv(n, 8), 256, 0, stream>>>(f, n, c, flag);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
+
 struct KPts {
   float x[16], y[16], z[16];  // 15 kernel points + one far-away dummy (influence 0): pairs feed the packed f32x2 math
 };

@@ -533,7 +533,7 @@ extern "C" int rdm_build_pyramid_finish(void* job, rdm_pyramid_desc* h_desc, int
         heavy = (e && e[0] == '0') ? 0 : 1;
       }
       if (heavy && n > 0 && out.ok) {
-        RDM_TRY(rdm_order_by_load(order, nb, n, c.limits[s], n, order2, stream));
+        RDM_TRY(rdm_order_by_load(order, nb, n, c.limits[s], n, order2, workspace, workspace_bytes, stream));
         d.order[s] = order2;
       }
     }

@@ -739,8 +739,9 @@ class RDMNet(_Module):
             out["ref_n2p_scores_c"], out["src_n2p_scores_c"] = ref_n2p[ref_sel], src_n2p[src_sel]
             out["ref_n2n_scores_c"], out["src_n2n_scores_c"] = n2n[:nc][ref_sel], n2n[nc:][src_sel]
             ref_feats_c, src_feats_c = self.transformer2(ref_points_c, src_points_c, ref_feats_c, src_feats_c)
-        else:
+        else:  # cfg.Vote.inference_use_vote = False (the Mulran configuration, experiments/infer.py:119-120)
             ref_points_c, src_points_c = points_c[:nc].contiguous(), points_c[nc:].contiguous()
+            ref_feats_c, src_feats_c = tf[:nc], tf[nc:]
             out["ref_n2p_scores_c"], out["src_n2p_scores_c"] = ref_n2p, src_n2p
         out["ref_points_c"], out["src_points_c"] = ref_points_c, src_points_c
         ref_feats_c_norm = torch.nn.functional.normalize(ref_feats_c, p=2, dim=1)

@@ -256,6 +256,18 @@ def test_forward_vs_oracle_on_synthetic_pairs(model, pretrained_state, name, pai
         ref = MO.forward(pretrained_state, tp,
                          lambda q, l: OP.radius_search(q.numpy(), q.numpy(), l.numpy(), l.numpy(), 2.4, 81, "port"))
     out = model({"points": torch.from_numpy(pts).cuda(), "lengths": torch.tensor(lens, dtype=torch.int64).cuda()})
+    # the GPU-built pyramid is the oracle's: points bit-exact, tables equal (canonical tie order on both sides)
+    gp = out["pyramid"]
+    for s_ in range(5):
+        assert np.array_equal(gp.points(s_).cpu().numpy().view(np.uint32), pyr["points"][s_].view(np.uint32)), f"points[{s_}]"
+        t_gpu, t_ref = gp.table("neighbors", s_).cpu().numpy(), pyr["neighbors"][s_]
+        w = t_ref.shape[1]
+        bad = int((t_gpu[:, :w] != t_ref).any(1).sum())
+        assert bad == 0, f"neighbors[{s_}]: {bad} rows differ"
+        if s_ < 4:
+            t_gpu, t_ref = gp.table("subsampling", s_).cpu().numpy(), pyr["subsampling"][s_]
+            bad = int((t_gpu[:, :t_ref.shape[1]] != t_ref).any(1).sum())
+            assert bad == 0, f"subsampling[{s_}]: {bad} rows differ"
     # discrete outputs: exact
     assert np.array_equal(out["mask"].cpu().numpy(), ref["nms_masks"].numpy()), "NMS mask"
     same_order = assert_node_corr_equal(out["ref_node_corr_indices"].cpu().numpy(), out["src_node_corr_indices"].cpu().numpy(),
