@@ -488,6 +488,27 @@ int rdm_maxpool_bwd(const float* feats, const void* neighbor_indices, int index_
                     int C, float* d_feats_zeroed, rdm_stream_t stream);
 int rdm_upsample_concat_bwd(const float* d_out, const void* upsample_indices, int index_bytes, int index_stride, int M, int N,
                             int C1, int C2, float* d_feats_zeroed, float* d_skip, rdm_stream_t stream);
+/* out_accum[index[i], :] += src[i, :] (backward of rdm_index_select); rows of row_floats fp32. */
+int rdm_scatter_add_rows(const float* src, const void* index, int index_bytes, int64_t count, int row_floats, int64_t rows,
+                         float* out_accum, rdm_stream_t stream);
+/* ---- matcher-side backward kernels (csrc/train.cu). The reference: autograd over rdmnet/thdroformer/thdroformer.py:20-85 and
+ * geotransformer/modules/sinkhorn/learnable_sinkhorn.py:13-66.
+ * rdm_rope_bwd: dx [N,C] (dense), demb [N,C/2] (dense, may be NULL) of y = rope(x, emb).
+ * rdm_attention_bwd: gradients of O = softmax(Q K^T / sqrt(d)) V per head; Q/K/V/O/dO row-strided (strides multiples of 4 floats,
+ *   16-byte aligned), dQ/dK/dV with row stride ldd; head_dim 16 or 32; deterministic (no atomics).
+ * rdm_sinkhorn_bwd: d scores [P,R,C] and per-patch partial sums of d alpha [P] from d out [P,R+1,C+1]; patch-level masks [P,R]/[P,C]
+ *   (1 = live). Re-runs the forward iterations (exact expf/logf), keeps every iterate in the workspace, then walks them backwards.
+ *   Gradient arriving on masked entries is ignored (they are the constant -inf in the forward). */
+int rdm_rope_bwd(const float* x, int ldx, const float* emb, int lde, const float* dy, int ldy, int N, int C, float* dx, float* demb,
+                 rdm_stream_t stream);
+size_t rdm_attention_bwd_workspace(int Nq, int heads);
+int rdm_attention_bwd(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const float* O, int ldo,
+                      const float* dO, int ldg, int Nq, int Nk, int heads, int head_dim, void* workspace, size_t workspace_bytes,
+                      float* dQ, float* dK, float* dV, int ldd, rdm_stream_t stream);
+size_t rdm_sinkhorn_bwd_workspace(int num_patches, int R, int C, int num_iterations);
+int rdm_sinkhorn_bwd(const float* scores, int num_patches, int R, int C, const unsigned char* row_masks,
+                     const unsigned char* col_masks, const float* alpha, int num_iterations, float inf, const float* d_out,
+                     void* workspace, size_t workspace_bytes, float* d_scores, float* d_alpha_partial, rdm_stream_t stream);
 /* act: 1 LeakyReLU(slope), 2 ReLU, 3 clamp(sigmoid(x), 0, 1); y = the forward OUTPUT. */
 int rdm_activation_bwd(const float* y, const float* dy, int64_t n, int act, float slope, float* dx, rdm_stream_t stream);
 

@@ -91,6 +91,14 @@ SIGNATURES = {
                                   c_void_p, c_void_p]),
     "rdm_maxpool_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "rdm_upsample_concat_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "rdm_scatter_add_rows": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_int, c_i64, c_void_p, c_void_p]),
+    "rdm_rope_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "rdm_attention_bwd_workspace": (c_size_t, [c_int, c_int]),
+    "rdm_attention_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                  c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "rdm_sinkhorn_bwd_workspace": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "rdm_sinkhorn_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p,
+                                 c_size_t, c_void_p, c_void_p, c_void_p]),
     "rdm_activation_bwd": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_float, c_void_p, c_void_p]),
     "rdm_voxel_downsample_workspace": (c_size_t, [c_int]),
     "rdm_voxel_downsample": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

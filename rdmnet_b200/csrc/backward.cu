@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restric
   long long bj = -1;
   for (int h = 0; h < H; h++) {
     const long long j = (long long)idx[(size_t)m * H + h];
+    if (j > N) continue;  // column beyond the reference's row width
     const float v = j < N ? f[(size_t)j * C + c] : 0.f;
     if (v > best) {
       best = v;
@@ -394,6 +395,35 @@ extern "C" int rdm_activation_bwd(const float* y, const float* dy, int64_t n, in
   RDM_CHECK_ARG(act >= 1 && act <= 3, "rdm_activation_bwd: act must be 1 (LeakyReLU), 2 (ReLU) or 3 (clamped sigmoid)");
   if (n == 0) return RDM_OK;
   activation_bwd_kernel<<<cdiv(n, 256), 256, 0, stream>>>(y, dy, (long long)n, act, slope, dx);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
+
+// out[index[i], :] += src[i, :]  (backward of index_select along dim 0, geotransformer/modules/ops/index_select.py:4-30)
+namespace {
+template <typename IdxT>
+__global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __restrict__ src, const IdxT* __restrict__ index, long long count,
+                                                               int C, long long rows, float* __restrict__ out) {
+  const long long e = blockIdx.x * 256LL + threadIdx.x;
+  if (e >= count * C) return;
+  const long long i = e / C;
+  const long long j = (long long)index[i];
+  if (j >= 0 && j < rows) atomicAdd(&out[j * C + (e - i * C)], src[e]);
+}
+}  // namespace
+
+extern "C" int rdm_scatter_add_rows(const float* src, const void* index, int index_bytes, int64_t count, int row_floats, int64_t rows,
+                                    float* out_accum, cudaStream_t stream) {
+  RDM_CHECK_ARG(index_bytes == 4 || index_bytes == 8, "rdm_scatter_add_rows: index_bytes must be 4 or 8");
+  RDM_CHECK_ARG(count >= 0 && row_floats >= 1 && rows >= 0, "rdm_scatter_add_rows: bad sizes");
+  if (count == 0) return RDM_OK;
+  const long long total = (long long)count * row_floats;
+  if (index_bytes == 8)
+    scatter_add_rows_kernel<int64_t><<<cdiv(total, 256), 256, 0, stream>>>(src, (const int64_t*)index, (long long)count, row_floats,
+                                                                          (long long)rows, out_accum);
+  else
+    scatter_add_rows_kernel<int><<<cdiv(total, 256), 256, 0, stream>>>(src, (const int*)index, (long long)count, row_floats, (long long)rows,
+                                                                      out_accum);
   RDM_LAUNCH_CHECK();
   return RDM_OK;
 }

@@ -87,6 +87,7 @@ int rdm_kpconv_gather_impl(const float* s_feats, const float* q_points, const fl
                            int H, int C_in, const int* query_order, float* out_weighted, unsigned char* rowpos_scratch,
                            int rowpos_ready, cudaStream_t stream);
 
+int rdm_mark_reference_width(int* table, long long rows, int H, int n_support, const int* d_max_count, cudaStream_t stream);
 int rdm_row_positive(const float* f, int n, int c, unsigned char* flag, cudaStream_t stream);  // kpconv.cu: (sum_c f[n,c] > 0)
 int rdm_order_by_load(const int* order_in, const int* neighbors, int n, int H, int n_support, int* order_out, void* scratch,
                       size_t scratch_bytes, cudaStream_t stream);

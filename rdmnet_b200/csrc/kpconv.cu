@@ -857,6 +857,7 @@ __global__ void maxpool_kernel(const float* __restrict__ f, const IdxT* __restri
   const IdxT* row = idx + (size_t)m * H;
   for (int h = 0; h < H; h++) {
     long long j = (long long)row[h];
+    if (j > N) continue;  // column beyond the reference's row width (rdm_mark_reference_width): not part of the tensor
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (j < N) v = *(const float4*)(f + (size_t)j * C + 4 * c4);
     best.x = fmaxf(best.x, v.x);

@@ -793,3 +793,25 @@ int rdm_order_by_load(const int* order_in, const int* neighbors, int n, int H, i
   RDM_LAUNCH_CHECK();
   return RDM_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------- reference row width
+// The reference's table has width min(max_count, limit) (radius_neighbors_cpu.cpp:59-68 + ops/radius_search.py:25-26);
+// ours has the fixed width `limit`. For every consumer but one the extra columns are ordinary padding. The exception is
+// the strided max-pool (kpconv/functional.py:54-67): padding reads the appended ZERO row, so a row that fills the whole
+// reference width competes with 0 only if a padded column exists. Columns >= max_count therefore get the sentinel N + 1
+// = "this column does not exist in the reference's tensor"; rdm_maxpool skips it, the gathers treat it as padding.
+__global__ void __launch_bounds__(256) rs_mark_width_kernel(int* __restrict__ table, long long rows, int H, int N,
+                                                            const int* __restrict__ max_count) {
+  const int w = *max_count;
+  if (w >= H) return;
+  const long long e = blockIdx.x * 256LL + threadIdx.x;
+  if (e >= rows * H) return;
+  if ((int)(e % H) >= w) table[e] = N + 1;
+}
+int rdm_mark_reference_width(int* table, long long rows, int H, int n_support, const int* d_max_count, cudaStream_t stream) {
+  if (rows <= 0) return RDM_OK;
+  rs_mark_width_kernel<<<cdiv(rows * H, 256), 256, 0, stream>>>(table, rows, H, n_support, d_max_count);
+  RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}

@@ -543,7 +543,9 @@ extern "C" int rdm_build_pyramid_finish(void* job, rdm_pyramid_desc* h_desc, int
       d.subsampling[s] = sub;
       d.sub_width[s] = c.limits[s];
       RDM_TRY(rdm_radius_search_impl(pts[s + 1], pts[s], h_d_lengths[s + 1], h_d_lengths[s], B, m, n, n, radius, c.limits[s], sub, 4,
-                                     nullptr, d_maxc + nsearch++, nullptr, workspace, workspace_bytes, stream));
+                                     nullptr, d_maxc + nsearch, nullptr, workspace, workspace_bytes, stream));
+      RDM_TRY(rdm_mark_reference_width(sub, m, c.limits[s], n, d_maxc + nsearch, stream));  // the max-pool's view of the width
+      nsearch++;
       if (!(c.skip_up0 && s == 0)) {
         const int w = c.up_nearest_only ? 1 : c.limits[s + 1];
         int* up = out.get<int>((size_t)(n > 0 ? n : 1) * w);

@@ -16,6 +16,8 @@ What it registers in sys.modules (every name the reference's experiments/*.py im
     geotransformer.modules.transformer           -> TransformerLayer, AttentionLayer, MultiHeadAttention, AttentionOutput
     geotransformer.utils.data                    -> rdmnet_b200.data           (GPU pyramid instead of CPU collate workers)
     geotransformer.utils.open3d                  -> GPU RANSAC                 (utils/open3d.py:173-203)
+    geotransformer.utils.registration            -> GPU ground-truth ball query get_correspondences (utils/registration.py:203-217;
+                                                    other names fall through to the reference's file)
     rdmnet.thdroformer, rdmnet.vote              -> ThDRoFormer / Vote_layer, NMS
     rdmnet.utils.visualization                   -> headless no-ops (the reference module cannot be imported: SURVEY 3.1)
 
@@ -187,6 +189,22 @@ def install(reference_root=None, third_party_stubs=True):
     _module("geotransformer.utils.open3d", {"registration_with_ransac_from_correspondences":
                                             _registration.registration_with_ransac_from_correspondences})
 
+    reg_mod = _module("geotransformer.utils.registration", {"get_correspondences": _registration.get_correspondences})
+    if reference_root:  # every other name of that module (offline evaluation helpers) comes from the reference's own file
+        ref_file = os.path.join(reference_root, "geotransformer", "utils", "registration.py")
+
+        def _fallback(name, _cache={}):
+            if "m" not in _cache:
+                import importlib.util
+                spec = importlib.util.spec_from_file_location("geotransformer.utils._reference_registration", ref_file)
+                _cache["m"] = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(_cache["m"])
+            try:
+                return getattr(_cache["m"], name)
+            except AttributeError:
+                raise AttributeError("module 'geotransformer.utils.registration' has no attribute %r" % name) from None
+
+        reg_mod.__getattr__ = _fallback
     _module("rdmnet.thdroformer", {"ThDRoFormer": _modules.ThDRoFormer}, path=[])
     _module("rdmnet.thdroformer.thdroformer", {"ThDRoFormer": _modules.ThDRoFormer})
     _module("rdmnet.vote", _pick(_modules, ["Vote_layer", "NMS"]), path=[])

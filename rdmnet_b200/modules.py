@@ -316,7 +316,8 @@ class RPEConditionalTransformer(_Module):
             [TransformerLayer(d_model, num_heads, dropout, activation_fn, rotary=(b == "self")) for b in blocks])
 
     def forward(self, feats0, feats1, embeddings0, embeddings1, masks0=None, masks1=None):
-        if all(layer.fusable() for layer in self.layers) and feats0.shape[0] > 0 and feats1.shape[0] > 0:
+        if (all(layer.fusable() for layer in self.layers) and feats0.shape[0] > 0 and feats1.shape[0] > 0
+                and not ops.AG.needs_grad(feats0, feats1, *self.parameters())):
             return self._forward_fused(feats0.contiguous(), feats1.contiguous(), embeddings0.contiguous(),
                                        embeddings1.contiguous())
         for layer, block in zip(self.layers, self.blocks):
@@ -388,7 +389,8 @@ class ThDRoFormer(_Module):
                 raise RuntimeError("ThDRoFormer processes one pair per call (as the reference: thdroformer.py:76)")
             ref_points, src_points, ref_feats, src_feats = ref_points[0], src_points[0], ref_feats[0], src_feats[0]
         tr = self.transformer
-        if all(layer.fusable() for layer in tr.layers) and ref_feats.shape[0] > 0 and src_feats.shape[0] > 0:
+        training_grad = ops.AG.needs_grad(ref_feats, src_feats, *self.parameters())  # per-operator (differentiable) path
+        if all(layer.fusable() for layer in tr.layers) and ref_feats.shape[0] > 0 and src_feats.shape[0] > 0 and not training_grad:
             f0, f1 = self._forward_runner(ref_points.contiguous(), src_points.contiguous(), ref_feats, src_feats)
             return (f0[None], f1[None]) if batched else (f0, f1)
         e0, e1 = self.embedding(ref_points.contiguous()), self.embedding(src_points.contiguous())

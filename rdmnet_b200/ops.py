@@ -3,10 +3,12 @@ parts of ``geotransformer.modules.kpconv`` (same names, argument meaning and err
 through librdm_sm100.so. Reference citations are relative to /root/reference.
 """
 import ctypes
+import weakref
 
 import torch
 
 from . import _lib as L
+from . import autograd as AG
 
 
 def _chk(t, dtype, name, ndim=None):
@@ -122,6 +124,8 @@ def linear(x, weight, bias=None, weight_is_kn=False, act=0):
     weight_is_kn, (in,out)."""
     x = x.contiguous()
     _chk(x, torch.float32, "x", 2)
+    if AG.needs_grad(x, weight, bias):
+        return AG.Linear.apply(x, weight, bias, bool(weight_is_kn), int(act))
     m, k = x.shape
     n = weight.shape[1] if weight_is_kn else weight.shape[0]
     out = torch.empty((m, n), dtype=torch.float32, device=x.device)
@@ -136,15 +140,17 @@ _HOST_COPIES = {}
 
 
 def _host_copy(t):
-    """Host mirror of a small constant device tensor (KPConv kernel points), cached per (storage, version): the one
-    D2H happens the first time a module runs, not per call."""
+    """Host mirror of a small constant device tensor (KPConv kernel points). Cached per tensor OBJECT (weak reference) and
+    version: a module buffer pays the one D2H the first time it runs; a temporary that merely re-uses a freed tensor's
+    address does not hit the entry of its predecessor."""
     key = (t.data_ptr(), t._version, t.device)
-    h = _HOST_COPIES.get(key)
-    if h is None:
-        if len(_HOST_COPIES) > 4096:
-            _HOST_COPIES.clear()
-        h = t.detach().to("cpu", torch.float32).contiguous()
-        _HOST_COPIES[key] = h
+    hit = _HOST_COPIES.get(key)
+    if hit is not None and hit[0]() is t:
+        return hit[1]
+    if len(_HOST_COPIES) > 4096:
+        _HOST_COPIES.clear()
+    h = t.detach().to("cpu", torch.float32).contiguous()
+    _HOST_COPIES[key] = (weakref.ref(t), h)
     return h
 
 
@@ -158,6 +164,10 @@ def kpconv(s_feats, q_points, s_points, neighbor_indices, weights, kernel_points
     if kk != 15 or cin != c:
         raise RuntimeError("kpconv: weights must be (15, C_in, C_out)")
     dev = s_feats.device
+    if AG.needs_grad(s_feats, weights, bias):
+        gathered = AG.KPConvGather.apply(s_feats, q_points.contiguous(), s_points.contiguous(), neighbor_indices, kernel_points,
+                                         _host_copy(kernel_points), float(sigma), query_order)
+        return linear(gathered, weights.reshape(kk * c, cout), bias, weight_is_kn=True)
     gathered = torch.empty((m, kk * c), dtype=torch.float32, device=dev)
     rowpos = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
     L.call("rdm_kpconv_gather", L.ptr(s_feats), L.ptr(q_points), L.ptr(s_points), L.ptr(neighbor_indices),
@@ -175,6 +185,8 @@ def kpconv_gather_bytes(m, h, c_in, c_out, index_bytes, feat_bytes=4):
 def maxpool(x, neighbor_indices):
     """geotransformer/modules/kpconv/functional.py:54-67."""
     x, neighbor_indices = x.contiguous(), neighbor_indices.contiguous()
+    if AG.needs_grad(x):
+        return AG.MaxPool.apply(x, neighbor_indices)
     m, h = neighbor_indices.shape
     n, c = x.shape
     out = torch.empty((m, c), dtype=torch.float32, device=x.device)
@@ -187,9 +199,11 @@ def nearest_upsample_concat(x, upsample_indices, skip):
     m = upsample_indices.shape[0]
     n, c1 = x.shape
     c2 = skip.shape[1] if skip is not None else 0
-    out = torch.empty((m, c1 + c2), dtype=torch.float32, device=x.device)
     if upsample_indices.stride(1) != 1:
         raise RuntimeError("upsample_indices must be row-major")
+    if AG.needs_grad(x, skip):
+        return AG.UpsampleConcat.apply(x.contiguous(), upsample_indices, None if skip is None else skip.contiguous())
+    out = torch.empty((m, c1 + c2), dtype=torch.float32, device=x.device)
     L.lib()  # ensure loaded
     L.call("rdm_upsample_concat", L.ptr(x), upsample_indices.data_ptr(), _idx_bytes(upsample_indices),
            upsample_indices.stride(0), L.ptr(skip), m, n, c1, c2, L.ptr(out), L.stream())
@@ -204,6 +218,9 @@ def group_norm(x, weight, bias, groups, residual=None, act=0, slope=0.1, eps=1e-
     """GroupNorm over stacked (N,C) features (kpconv/modules.py:33-50) + optional residual add + LeakyReLU."""
     x = x.contiguous()
     _chk(x, torch.float32, "x", 2)
+    if AG.needs_grad(x, weight, bias, residual):
+        return AG.GroupNorm.apply(x, weight, bias, None if residual is None else residual.contiguous(), int(groups), int(act),
+                                  float(slope), float(eps))
     n, c = x.shape
     y = torch.empty_like(x)
     stats = torch.empty(2 * groups, dtype=torch.float64, device=x.device)
@@ -214,6 +231,8 @@ def group_norm(x, weight, bias, groups, residual=None, act=0, slope=0.1, eps=1e-
 
 def layer_norm(x, weight, bias, residual=None, relu=False, eps=1e-5):
     _chk(x, torch.float32, "x", 2)
+    if AG.needs_grad(x, weight, bias, residual):
+        return AG.LayerNorm.apply(x, None if residual is None else residual.contiguous(), weight, bias, float(eps), 2 if relu else 0)
     n, c = x.shape
     y = torch.empty_like(x)
     L.call("rdm_layernorm", L.ptr(x), L.ptr(residual), L.ptr(weight), L.ptr(bias), L.ptr(y), n, c, eps, 2 if relu else 0,
@@ -224,6 +243,8 @@ def layer_norm(x, weight, bias, residual=None, relu=False, eps=1e-5):
 def activation(x, act, slope=0.1):
     """act: 1 LeakyReLU(slope), 2 ReLU, 3 clamp(sigmoid(x), 0, 1)."""
     x = x.contiguous()
+    if AG.needs_grad(x):
+        return AG.Activation.apply(x, int(act), float(slope))
     y = torch.empty_like(x)
     L.call("rdm_activation", L.ptr(x), L.ptr(y), x.numel(), act, slope, L.stream())
     return y
@@ -232,6 +253,8 @@ def activation(x, act, slope=0.1):
 # ----------------------------------------------------------------------------------------------- transformer
 def rope(x, emb):
     """RotaryPositionalEmbedding.forward (rdmnet/thdroformer/thdroformer.py:56-85). x (N,C), emb (N,C/2) -> (N,C)."""
+    if AG.needs_grad(x, emb):
+        return AG.Rope.apply(x, emb)
     n, c = x.shape
     y = torch.empty((n, c), dtype=torch.float32, device=x.device)
     L.call("rdm_rope", x.data_ptr(), x.stride(0), emb.data_ptr(), emb.stride(0), L.ptr(y), c, n, c, L.stream())
@@ -243,6 +266,10 @@ def attention(q, k, v, heads):
     q (Nq,C), k/v (Nk,C): row-strided views are allowed (e.g. slices of a fused projection)."""
     nq, c = q.shape
     nk = k.shape[0]
+    if AG.needs_grad(q, k, v):
+        if (c // heads) not in (16, 32):
+            raise RuntimeError("attention backward: head_dim must be 16 or 32 (rdm_attention_bwd)")
+        return AG.Attention.apply(q, k, v, int(heads))
     for t in (q, k, v):
         if t.stride(1) != 1:
             raise RuntimeError("attention: channel dimension must be contiguous")
@@ -306,6 +333,16 @@ def nms(neighbor_indices, split=None):
 
 def pairwise_distance(x, y, normalized=False, channel_first=False):
     """geotransformer/modules/ops/pairwise_distance.py:4-31 (2-D inputs), on the GEMM kernel."""
+    if x.ndim != 2 or x.dtype != torch.float32 or AG.needs_grad(x, y):
+        # batched / double / differentiable uses (experiments/loss.py:27-31, 82, 166-171, 211, 243): the literal expression
+        xt, yt = (x.transpose(-1, -2), y) if channel_first else (x, y.transpose(-1, -2))
+        xy = torch.matmul(xt, yt)
+        if normalized:
+            d = 2.0 - 2.0 * xy
+        else:
+            ax = -2 if channel_first else -1
+            d = (x ** 2).sum(ax).unsqueeze(-1) - 2 * xy + (y ** 2).sum(ax).unsqueeze(-2)
+        return d.clamp(min=1e-12)
     if channel_first:
         x, y = x.t(), y.t()
     xy = linear(x.contiguous(), y.contiguous())
@@ -372,6 +409,11 @@ def patch_scores(ref_feats_f, src_feats_f, ref_knn_indices, src_knn_indices, ref
 
 def sinkhorn(scores, row_masks, col_masks, alpha, num_iterations, inf=1e12, row_gather=None, col_gather=None):
     """LearnableLogOptimalTransport.forward (geotransformer/modules/sinkhorn/learnable_sinkhorn.py:13-66)."""
+    if AG.needs_grad(scores, alpha):
+        if row_gather is not None or col_gather is not None:
+            raise RuntimeError("sinkhorn: the differentiable path takes patch-level masks (no gather tables)")
+        return AG.Sinkhorn.apply(scores, row_masks.to(torch.uint8).contiguous(), col_masks.to(torch.uint8).contiguous(), alpha,
+                                 int(num_iterations), float(inf))
     scores = scores.contiguous()
     b, r, c = scores.shape
     rm = row_masks.to(torch.uint8).contiguous()
@@ -445,6 +487,13 @@ def index_select(data, index, dim):
     rows = moved.shape[0]
     words = int(moved.numel() // rows) if rows > 0 else 0
     flat = index.reshape(-1).contiguous()
+    if AG.needs_grad(data) and data.dtype == torch.float32:
+        out = AG.IndexSelectRows.apply(moved, flat)
+        out = out.view(tuple(index.shape) + tuple(moved.shape[1:]))
+        if dim != 0:
+            m_ = index.ndim
+            out = out.permute(*(list(range(m_, m_ + dim)) + list(range(m_)) + list(range(m_ + dim, out.ndim))))
+        return out
     out = torch.empty((flat.shape[0],) + tuple(moved.shape[1:]), dtype=data.dtype, device=data.device)
     if flat.shape[0] > 0 and words > 0:
         err = torch.zeros(1, dtype=torch.int32, device=data.device)
@@ -475,6 +524,19 @@ def apply_transform(points, transform, normals=None):
     """geotransformer/modules/ops/transformation.py:7-60: (*,3) points with a (4,4) transform, or (B,N,3) with (B,4,4)."""
     if normals is not None and points.shape != normals.shape:
         raise AssertionError("points and normals must have the same shape")
+    if points.dtype != torch.float32 or transform.dtype != torch.float32 or AG.needs_grad(points, transform, normals):
+        # differentiable / double uses of the losses (experiments/loss.py:75, 152-153, 234): the literal expression
+        R, t = transform[..., :3, :3], transform[..., :3, 3]
+        if transform.ndim == 2:
+            pts = torch.matmul(points.reshape(-1, 3), R.transpose(-1, -2)) + t
+            pts = pts.reshape(points.shape)
+            nrm = None if normals is None else torch.matmul(normals.reshape(-1, 3), R.transpose(-1, -2)).reshape(points.shape)
+        elif transform.ndim == 3 and points.ndim == 3:
+            pts = torch.matmul(points, R.transpose(-1, -2)) + t[:, None, :]
+            nrm = None if normals is None else torch.matmul(normals, R.transpose(-1, -2))
+        else:
+            raise ValueError("Incompatible shapes between points {} and transform {}.".format(tuple(points.shape), tuple(transform.shape)))
+        return (pts, nrm) if normals is not None else pts
     if transform.ndim == 2:
         batch, n, shared = 1, points.numel() // 3, 1
     elif transform.ndim == 3 and points.ndim == 3:

@@ -6,6 +6,7 @@
                                                   isotropic_transform_error (:46-111)
   geotransformer.modules.registration.procrustes weighted_procrustes, WeightedProcrustes (:6-91)
   geotransformer.utils.open3d                    registration_with_ransac_from_correspondences (:173-203)
+  geotransformer.utils.registration              get_correspondences (:203-217; the ground-truth ball query of experiments/loss.py:92,151)
 
 The ground-truth overlap / mask computations and RANSAC run as CUDA kernels of librdm_sm100.so (csrc/gt.cu, lgr.cu); the
 metrics are a handful of scalar operations on one 4x4 pose and stay in torch, like in the reference.
@@ -101,6 +102,36 @@ def compact_nonzero(mat):
     b = mat.to(torch.uint8).contiguous()
     L.call("rdm_compact_nonzero", None, L.ptr(b), rows, cols, L.ptr(idx), None, L.ptr(cnt), L.stream())
     return idx[:int(cnt.item())], None
+
+
+def get_correspondences(ref_points, src_points, transform=None, matching_radius=None):
+    """geotransformer/utils/registration.py:203-217: all (ref index, src index) pairs closer than `matching_radius` after moving
+    src by `transform`. The reference builds a scipy cKDTree on the host per call (experiments/loss.py:92 and :151 hand it
+    `.detach().cpu().numpy()` arrays every iteration); here the ball query is the uniform-grid radius search of librdm_sm100
+    at its full width and a device-side compaction. Numpy (or tensors) in, (K,2) int64 numpy out like the reference, rows in
+    (ref, ascending distance) order - the callers only scatter 1s with them. `d < r` strict (nanoflann's rule, as everywhere
+    in this library) against cKDTree's `d <= r`: differs only for a pair at exactly the radius."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("rdmnet_b200 needs a CUDA device: there is no CPU path")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    as_t = lambda a: (a if torch.is_tensor(a) else torch.as_tensor(np.asarray(a))).to(dev, torch.float32).contiguous()  # noqa: E731
+    ref, src = as_t(ref_points), as_t(src_points)
+    if transform is not None:
+        src = ops.apply_transform(src, as_t(transform))
+    m, n = ref.shape[0], src.shape[0]
+    if m == 0 or n == 0:
+        return np.zeros((0, 2), dtype=np.int64)
+    ql = torch.tensor([m], dtype=torch.int64, device=dev)
+    sl = torch.tensor([n], dtype=torch.int64, device=dev)
+    table = ops.radius_neighbors(ref, src, ql, sl, float(matching_radius))  # (m, max_count), padded with n
+    if table.shape[1] == 0:
+        return np.zeros((0, 2), dtype=np.int64)
+    pos, _ = compact_nonzero(table < n)  # (K, 2) = (row, column) of the live slots, row-major
+    if pos.shape[0] == 0:
+        return np.zeros((0, 2), dtype=np.int64)
+    flat = (pos[:, 0] * table.shape[1] + pos[:, 1]).contiguous()
+    j = ops.index_select(table.reshape(-1).contiguous(), flat, 0)
+    return torch.stack([pos[:, 0], j], 1).cpu().numpy().astype(np.int64)
 
 
 # ---------------------------------------------------------------------------------------------------------- metrics

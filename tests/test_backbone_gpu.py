@@ -140,3 +140,25 @@ def test_blocks_vs_reference_golden(golden_small):
         ub = M.UnaryBlock(40, 64, 32)
         ub.load_state_dict(sub(g, "ub."), strict=True)
         close(ub.cuda()(torch.from_numpy(g["ub_in"]).cuda()), torch.from_numpy(g["ub_out"]))
+
+
+def test_maxpool_reference_row_width():
+    """A row that fills the whole reference width (max_count < limit) must NOT compete with the zero row: columns beyond the
+    reference's tensor carry the sentinel N + 1 (rdm_mark_reference_width) and are skipped (kpconv/functional.py:54-67 on the
+    narrowed table of ops/radius_search.py:25-26)."""
+    import numpy as np
+    from oracle import model_oracle as MO
+    from rdmnet_b200 import ops
+    rng = np.random.default_rng(1)
+    n, m, w, limit, c = 50, 20, 6, 10, 8
+    x = -torch.rand(n, c) - 0.1  # all negative: the zero row wins wherever it takes part
+    narrow = torch.from_numpy(rng.integers(0, n, size=(m, w)).astype(np.int64))
+    narrow[5:, 4:] = n  # rows 5.. have real padding; rows 0..4 fill the reference width
+    wide = torch.full((m, limit), n + 1, dtype=torch.int64)
+    wide[:, :w] = narrow
+    ref = MO.maxpool(x, narrow)
+    got = ops.maxpool(x.cuda(), wide.cuda()).cpu()
+    assert torch.equal(got, ref)
+    assert (ref[:5] < 0).all() and (ref[5:] == 0).all()
+    got32 = ops.maxpool(x.cuda(), wide.to(torch.int32).cuda()).cpu()
+    assert torch.equal(got32, ref)

@@ -153,17 +153,20 @@ def test_build_pyramid_single_call_equals_oracle(scans, pair):
         order = gp.table("order", s).cpu().numpy()
         assert np.array_equal(np.sort(order), np.arange(ref["points"][s].shape[0])), f"order[{s}]"
 
-    def same(got, want, n_support, name):
+    def same(got, want, n_support, name, beyond=None):
         got = got.cpu().numpy()
         w = want.shape[1]
         assert got.shape[0] == want.shape[0] and got.shape[1] >= w, name
         assert np.array_equal(got[:, :w], want), name
-        assert (got[:, w:] == n_support).all(), name + " padding"
+        # columns beyond the reference's row width: plain padding (n_support) in the neighbour tables, the "column does not
+        # exist" sentinel n_support + 1 in the subsampling tables (what the strided max-pool needs: rdm_mark_reference_width)
+        assert (got[:, w:] == (n_support if beyond is None else beyond)).all(), name + " padding"
 
     for s in range(5):
         same(d["neighbors"][s], ref["neighbors"][s], ref["points"][s].shape[0], f"neighbors[{s}]")
         if s < 4:
-            same(d["subsampling"][s], ref["subsampling"][s], ref["points"][s].shape[0], f"subsampling[{s}]")
+            same(d["subsampling"][s], ref["subsampling"][s], ref["points"][s].shape[0], f"subsampling[{s}]",
+                 beyond=ref["points"][s].shape[0] + 1)
             if s == 0:
                 assert d["upsampling"][0] is None
             else:
