@@ -55,6 +55,13 @@ def parse():
                     help="BASELINE.json configs[4]: 256 synthetic pairs, 64 per size class (4k/8k/16k/32k pts/scan), dealt "
                          "round-robin over the ranks; reports per-class pairs/s and the per-layer gather roofline")
     ap.add_argument("--sweep-pairs", type=int, default=256)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"],
+                    help="fp32 (default, the parity mode: 3-term tf32 split) or tf32 (BASELINE config 3 reduced-precision mode: one "
+                         "tensor-core product per k-step; NOT the headline number)")
+    ap.add_argument("--train", action="store_true",
+                    help="BASELINE.json configs[3]: training steps (the reference's unmodified experiments/model.py + loss.py on the "
+                         "drop-in, Adam, bucketed bf16 gradient all-reduce over NCCL when N > 1) on synthetic KITTI-shaped pairs")
+    ap.add_argument("--train-comm", default="bf16", choices=["bf16", "f32"], help="wire format of the gradient all-reduce")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference's 1-GPU eager measurement")
     return ap.parse_args()
 
@@ -287,6 +294,8 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     L.lib()  # fail loudly if librdm_sm100.so is missing
+    import rdmnet_b200
+    rdmnet_b200.set_precision(args.precision)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -482,8 +491,10 @@ def run_ours(args, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": world * args.steps / (total_ms / 1e3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_step": 1, "distinct_pairs_per_rank": len(pairs),
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "tf32 contractions, f32 elsewhere (reduced-precision mode, config 3)",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_step": 1, "distinct_pairs_per_rank": len(pairs), "precision": args.precision,
                        "points_per_pair": [int(p[0].shape[0]) for p in d_pairs], "neighbor_limits": LIMITS,
                        "weights": wdesc, "l2": "256 MiB flush write between timed steps (untimed)",
                        "timing": "CUDA events per step on the launch stream, summed; max over ranks; kernel events recorded inside the library around the launches",
@@ -525,9 +536,12 @@ def run_ours(args, rank, world, local_rank):
             except Exception:
                 bf16, psrc = 1400.0, "fallback 1.4 PFLOP/s sustained bf16 / 2"
             ach = fl / 1e12 / (ms / 1e3)
-            line["roofline_gemm"] = {"kernel": "gemm_tf32x3 (tcgen05 kind::tf32, A in TMEM), KPConv weight contraction, 14 launches/step",
-                                     "bound": "tensor", "achieved": ach, "issued_tf32_tflops": 3.0 * ach, "peak": bf16 / 2.0,
-                                     "unit": "TFLOP/s", "frac": ach / (bf16 / 2.0), "frac_issued": 3.0 * ach / (bf16 / 2.0),
+            passes = 3.0 if args.precision == "fp32" else 1.0
+            kname = ("gemm_tf32x3 (tcgen05 kind::tf32, 3-term split, A in TMEM)" if args.precision == "fp32"
+                     else "gemm_tf32x1 (tcgen05 kind::tf32, single product, no operand split)")
+            line["roofline_gemm"] = {"kernel": kname + ", KPConv weight contraction, 14 launches/step",
+                                     "bound": "tensor", "achieved": ach, "issued_tf32_tflops": passes * ach, "peak": bf16 / 2.0,
+                                     "unit": "TFLOP/s", "frac": ach / (bf16 / 2.0), "frac_issued": passes * ach / (bf16 / 2.0),
                                      "peak_source": psrc, "launches": len(gemm_prof),
                                      "kpconv_weight_gemm_ms_per_step": ms / max(len(gemm_prof) / 14.0, 1e-9),
                                      "note": "measured in an untimed extra pass with event brackets around each launch"}
@@ -663,6 +677,132 @@ def run_sweep(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------- config 4: training
+def run_train(args, rank, world, local_rank):
+    """BASELINE.json configs[3] / SURVEY 8(f).1: one step = one synthetic KITTI-shaped pair per GPU through
+    host points -> GPU collate (pyramid) -> experiments/model.py forward in train mode (ground-truth node correspondences, 128
+    sampled patches) -> experiments/loss.py OverallLoss -> backward through the kernels of csrc/backward.cu + train.cu ->
+    bucketed gradient all-reduce (rdmnet_b200.ddp, overlapped with the backward pass) -> Adam (experiments/trainval.py:34).
+    model.py and loss.py are the reference's files, unmodified, bound to rdmnet_b200 by rdmnet_b200.dropin. Weak scaling: every
+    rank trains on its own pairs; value = pairs of all ranks / slowest rank's time."""
+    import importlib
+    import torch
+    import torch.distributed as dist
+    from rdmnet_b200 import _lib as L
+    from rdmnet_b200 import ddp, dropin
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: rdmnet_b200 has no CPU path")
+    ref_root = os.path.join(ROOT, "baseline", "_ref", "RDMNet")
+    if not os.path.isdir(os.path.join(ref_root, "experiments")):
+        raise RuntimeError("--train runs the reference's experiments/model.py + loss.py: stage them with __graft_entry__.build()")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    L.lib()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dropin.install(reference_root=ref_root)
+    config, model_mod, loss_mod = (importlib.import_module(m) for m in ("config", "model", "loss"))
+    data = importlib.import_module("geotransformer.utils.data")
+    cfg = config.make_cfg()
+    cfg.test.vis = False
+    cfg.neighbor_limits = LIMITS
+    model = model_mod.create_model(cfg)
+    if os.path.exists(CKPT):  # a trained starting point: NMS survivors / correspondence counts are those of real training steps
+        model.load_state_dict(torch.load(CKPT, map_location="cpu", weights_only=True), strict=True)
+        wdesc = "pretrained reference checkpoint as the starting point"
+    else:
+        wdesc = "random init"
+    model = model.to(dev).train()
+    loss_fn = loss_mod.OverallLoss(cfg).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-6)
+    comm_dtype = torch.bfloat16 if args.train_comm == "bf16" else torch.float32
+    red = ddp.BucketedGradAllReduce(model, comm_dtype=comm_dtype) if world > 1 else None
+    pairs = make_pairs(args.pairs, rank)
+    items = [dict(ref_points=p["ref_points"], src_points=p["src_points"], ref_feats=np.ones((len(p["ref_points"]), 1), np.float32),
+                  src_feats=np.ones((len(p["src_points"]), 1), np.float32), transform=p["transform"].astype(np.float32)) for p in pairs]
+    names = ("collate", "forward", "loss", "backward", "allreduce_exposed", "optimizer")
+    launches0 = None
+    h2d = d2h = 0
+
+    def step(i, ev=None):
+        nonlocal h2d, d2h
+        it = items[i % len(items)]
+        mark = (lambda k: ev[k].record()) if ev is not None else (lambda k: None)
+        mark(0)
+        dd = data.registration_collate_fn_stack_mode([it], 5, 0.3, 4.25 * 0.3, LIMITS)
+        dd = {k: ([t.to(dev, non_blocking=True) for t in v] if isinstance(v, list) else (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v))
+              for k, v in dd.items()}
+        dd["testing"] = False
+        mark(1)
+        np.random.seed(1000 + i)
+        out = model(dd)
+        mark(2)
+        with torch.device(dev):  # loss.py:240-243 builds index helpers with bare torch.arange (torch 1.8 tolerated the device mix)
+            losses = loss_fn(out, dd)
+        mark(3)
+        opt.zero_grad(set_to_none=True)
+        losses["loss"].backward()
+        mark(4)
+        if red is not None:
+            red.finish()
+        mark(5)
+        opt.step()
+        mark(6)
+        h2d = sum(int(v.nbytes) for v in it.values())
+        d2h = 4
+        return float(losses["loss"])  # the D2H read of the step's result (the reference logs it every iteration)
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = L.launch_count()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(7)] for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sampler.mark_begin()
+    t0 = time.perf_counter()
+    loss_vals = []
+    for i in range(args.steps):
+        loss_vals.append(step(args.warmup + i, evs[i]))
+        if i % 8 == 7:
+            sampler.sample_now()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = L.launch_count() - launches0
+    phase = np.array([[e[k].elapsed_time(e[k + 1]) for k in range(6)] for e in evs])  # ms
+    dev_ms = float(phase.sum())
+    t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max = float(t[0]), float(t[1])
+    if rank == 0:
+        per = {n: float(phase[:, k].mean()) for k, n in enumerate(names)}
+        line = {"metric": "train_pairs_per_sec", "value": world * args.steps / (wall_ms_max / 1e3), "unit": "pairs/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": wall_ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (gradients on the wire: %s)" % args.train_comm, "data": "synthetic",
+                "config": {"workload": "config 4: training step on a synthetic KITTI pair (~16k pts/scan), batch 1 per GPU, "
+                                       "experiments/model.py + loss.py unmodified on rdmnet_b200.dropin, Adam lr 1e-4",
+                           "parallelism": "dp%d" % world, "distinct_pairs_per_rank": len(items), "weights": wdesc,
+                           "timing": "wall clock over the timed steps incl. H2D of the points and the D2H read of the loss, max over ranks; "
+                                     "phases = CUDA events on the launch stream (rank 0)",
+                           "neighbor_limits": LIMITS},
+                "device_ms_per_step": dev_ms_max / args.steps, "phases_ms": per,
+                "e2e": {"value": world * args.steps / (wall_ms_max / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(launches),
+                "allreduce": {"bytes_per_step": red.bytes_per_step if red is not None else 0, "buckets": len(red.buckets) if red is not None else 0,
+                              "wire_dtype": args.train_comm, "exposed_ms": per["allreduce_exposed"],
+                              "exposed_frac_of_step": per["allreduce_exposed"] / max(dev_ms / args.steps, 1e-9),
+                              "note": "exposed = launch-stream time between the end of backward and the averaged gradients being in place"},
+                "loss_first_last": [loss_vals[0], loss_vals[-1]], "clocks": clocks}
+        emit(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 _REAL_STDOUT = None
 
 
@@ -685,6 +825,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.train:
+        run_train(args, rank, world, local_rank)
     elif args.sweep:
         run_sweep(args, rank, world, local_rank)
     else:

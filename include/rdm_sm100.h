@@ -491,6 +491,12 @@ int rdm_upsample_concat_bwd(const float* d_out, const void* upsample_indices, in
 /* out_accum[index[i], :] += src[i, :] (backward of rdm_index_select); rows of row_floats fp32. */
 int rdm_scatter_add_rows(const float* src, const void* index, int index_bytes, int64_t count, int row_floats, int64_t rows,
                          float* out_accum, rdm_stream_t stream);
+/* ---- precision of the dense contractions (BASELINE config 3). 0 (default): fp32-accurate 3-term tf32 split, the mode all parity
+ * tests run in. 1: one kind::tf32 product per k-step (10-bit mantissa, like fp16), geometry / normalisation / Sinkhorn / pose stay
+ * fp32. Process-wide; RDM_PRECISION=tf32 sets the initial value. */
+int rdm_set_precision(int mode);
+int rdm_get_precision(void);
+
 /* ---- matcher-side backward kernels (csrc/train.cu). The reference: autograd over rdmnet/thdroformer/thdroformer.py:20-85 and
  * geotransformer/modules/sinkhorn/learnable_sinkhorn.py:13-66.
  * rdm_rope_bwd: dx [N,C] (dense), demb [N,C/2] (dense, may be NULL) of y = rope(x, emb).

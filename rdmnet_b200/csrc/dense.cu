@@ -256,6 +256,9 @@ int rdm_linear_tc(const float* A, int lda, const float* B, int ldb, const float*
                   int* out_stats_fused, cudaStream_t stream);  // gemm_tc.cu
 
 // experimental A-in-TMEM variant of the same kernel (gemm_tc_atmem.cu): -1 unless RDM_GEMM_ATMEM=1
+int rdm_linear_tc_fast(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N, int K, int act,
+                       void* workspace, size_t workspace_bytes, int* out_splits, double* gn_stats, int gn_cpg, int* out_stats_fused,
+                       cudaStream_t stream);
 int rdm_linear_tc_atmem(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N, int K,
                         int act, void* workspace, size_t workspace_bytes, int* out_splits, double* gn_stats, int gn_cpg,
                         int* out_stats_fused, const float* B_split, cudaStream_t stream);
@@ -318,8 +321,12 @@ int rdm_linear_gn_ps(const float* A, int lda, const float* B, int ldb, int b_is_
   }
   if (use_tc && b_is_nk && M >= 64) {
     int tc_splits = 1;
-    int rc = rdm_linear_tc_atmem(A, lda, B, ldb, bias, C, ldc, M, N, K, act, workspace, workspace_bytes, &tc_splits, gn_stats,
-                                 gn_cpg, stats_fused, B_split, stream);
+    // reduced-precision mode (rdm_set_precision(1)): one tf32 product per k-step, no operand split (gemm_tc_fast.cu)
+    int rc = rdm_linear_tc_fast(A, lda, B, ldb, bias, C, ldc, M, N, K, act, workspace, workspace_bytes, &tc_splits, gn_stats, gn_cpg,
+                                stats_fused, stream);
+    if (rc == -1)
+      rc = rdm_linear_tc_atmem(A, lda, B, ldb, bias, C, ldc, M, N, K, act, workspace, workspace_bytes, &tc_splits, gn_stats,
+                               gn_cpg, stats_fused, B_split, stream);
     if (rc == -1)
       rc = rdm_linear_tc(A, lda, B, ldb, bias, C, ldc, M, N, K, act, workspace, workspace_bytes, &tc_splits, gn_stats, gn_cpg,
                          stats_fused, stream);

@@ -123,15 +123,17 @@ def get_correspondences(ref_points, src_points, transform=None, matching_radius=
         return np.zeros((0, 2), dtype=np.int64)
     ql = torch.tensor([m], dtype=torch.int64, device=dev)
     sl = torch.tensor([n], dtype=torch.int64, device=dev)
-    table = ops.radius_neighbors(ref, src, ql, sl, float(matching_radius))  # (m, max_count), padded with n
-    if table.shape[1] == 0:
+    _, maxc = ops.radius_search_raw(ref, src, ql, sl, float(matching_radius), 0, index_dtype=torch.int32)
+    width = int(maxc.item())  # the widest ball: the table below is complete (no neighbour limit, like the KD-tree query)
+    if width == 0:
         return np.zeros((0, 2), dtype=np.int64)
+    table, _ = ops.radius_search_raw(ref, src, ql, sl, float(matching_radius), width, index_dtype=torch.int32)  # padded with n
     pos, _ = compact_nonzero(table < n)  # (K, 2) = (row, column) of the live slots, row-major
     if pos.shape[0] == 0:
         return np.zeros((0, 2), dtype=np.int64)
     flat = (pos[:, 0] * table.shape[1] + pos[:, 1]).contiguous()
     j = ops.index_select(table.reshape(-1).contiguous(), flat, 0)
-    return torch.stack([pos[:, 0], j], 1).cpu().numpy().astype(np.int64)
+    return torch.stack([pos[:, 0], j.to(torch.int64)], 1).cpu().numpy().astype(np.int64)
 
 
 # ---------------------------------------------------------------------------------------------------------- metrics

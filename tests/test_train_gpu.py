@@ -223,10 +223,17 @@ def test_transformer_layer_gradients():
         else:
             check("TransformerLayer d memory", mg.grad, mr.grad)
         worst = 0.0
+        scale = max(sd[name].grad.abs().max().item() for name, _ in layer.named_parameters())
         for name, prm in layer.named_parameters():
             assert prm.grad is not None, name
-            e = rel(prm.grad, sd[name].grad)
-            print(f"[grad parity]   {name}: {e:.2e}")
+            rmax = sd[name].grad.abs().max().item()
+            if rmax < 1e-5 * scale:
+                # analytically zero (the key bias shifts every score of a row by the same q.b: softmax cancels it): both sides are
+                # rounding noise, compared on the scale of the other gradients
+                e = (prm.grad.detach().cpu() - sd[name].grad).abs().max().item() / scale
+            else:
+                e = rel(prm.grad, sd[name].grad)
+            print(f"[grad parity]   {name}: {e:.2e} (|ref| max {rmax:.2e})")
             worst = max(worst, e)
         assert worst <= 1e-4, worst
 
