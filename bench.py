@@ -373,22 +373,30 @@ def run_ours(args, rank, world, local_rank):
     clocks.mark_begin()
     t_wall0 = time.perf_counter()
     if pipelined:
+        # K pairs through the pair pipeline, from an idle GPU to an idle GPU (pipeline fill and drain included). Three pairs are in
+        # flight (pyramid of i+2, backbone of i+1, matching tail of i), so steps overlap: the time of the K steps is taken between
+        # one event before the first pair enters and the event after the last pair's last kernel, and the L2 flush between pairs is
+        # queued on the entering pair's stream INSIDE the timed region (it overlaps the previous pair's tail).
+        t_first = torch.cuda.Event(enable_timing=True)
+        t_first.record()
+
         def before(i):
-            if i < args.steps:
-                if i % 6 == 3:
-                    clocks.sample_now()  # under load (the side stream is building the next pyramid), outside the brackets
-                if not no_flush:
-                    flush.fill_(i & 0xFF)
-                ev[i][0].record()
-        gen = pipe.run((d_pairs[i % len(d_pairs)] for i in range(args.steps + 1)), before_step=before)
+            if i % 6 == 3:
+                clocks.sample_now()  # under load, between the queueing of two pairs
+            if not no_flush:
+                flush.fill_(i & 0xFF)
+            ev[i][0].record()
+
+        def after(i):
+            ev[i][1].record()
+        gen = pipe.run((d_pairs[i % len(d_pairs)] for i in range(args.steps)), before_step=before, after_step=after)
         for i in range(args.steps):
             out = next(gen)
-            ev[i][1].record()
+        for _ in gen:
+            pass
         barrier()
         t_wall = time.perf_counter() - t_wall0
         launches = L.launch_count() - launches0
-        for _ in gen:  # the look-ahead pair: untimed
-            pass
     else:
         for i in range(args.steps):
             if i % 6 == 3:
@@ -404,8 +412,13 @@ def run_ours(args, rank, world, local_rank):
     prof = L.prof_read()
     L.prof_enable(False)
     torch.cuda.synchronize()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(sum(step_ms))
+    if pipelined:
+        ends = [t_first] + [b for _, b in ev]
+        step_ms = [ends[i].elapsed_time(ends[i + 1]) for i in range(args.steps)]  # completion-to-completion intervals
+        total_ms = float(t_first.elapsed_time(ev[-1][1]))
+    else:
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        total_ms = float(sum(step_ms))
     clk = clocks.stop()
 
     # ---- timed region 2: end to end through the host-buffer API (pinned H2D of the points, D2H of the results)
@@ -413,8 +426,8 @@ def run_ours(args, rank, world, local_rank):
     host_pairs = [(pairs[i % len(pairs)]["ref_points"], pairs[i % len(pairs)]["src_points"]) for i in range(max(args.steps, 3))]
     if pipelined:
         reg = PairStreamRegistrar(model, max_points=maxp, device=dev)
-        for res in reg.register_stream(host_pairs[:min(args.warmup, 3)]):
-            pass
+        for res in reg.register_stream([host_pairs[i % len(host_pairs)] for i in range(max(args.warmup, 3) + len(pairs))]):
+            pass  # warm-up: every distinct pair through the host-buffer path (pinned staging + allocator blocks of its sizes)
         barrier()
         gc.collect()
         gc.disable()
@@ -496,11 +509,20 @@ def run_ours(args, rank, world, local_rank):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_step": 1, "distinct_pairs_per_rank": len(pairs), "precision": args.precision,
                        "points_per_pair": [int(p[0].shape[0]) for p in d_pairs], "neighbor_limits": LIMITS,
-                       "weights": wdesc, "l2": "256 MiB flush write between timed steps (untimed)",
-                       "timing": "CUDA events per step on the launch stream, summed; max over ranks; kernel events recorded inside the library around the launches",
+                       "weights": wdesc,
+                       "l2": ("256 MiB flush write queued before every pair enters the network, INSIDE the timed region (pairs overlap)"
+                              if pipelined else "256 MiB flush write between timed steps (untimed)"),
+                       "timing": ("K pairs through the pair pipeline from an idle GPU to an idle GPU (fill and drain included): CUDA events "
+                                  "before the first pair enters and after the last pair's last kernel; max over ranks; kernel events "
+                                  "recorded inside the library around the gather launches" if pipelined else
+                                  "CUDA events per step on the launch stream, summed; max over ranks; kernel events recorded inside the "
+                                  "library around the launches"),
                        "sharding": "pairs round-robin over ranks, no data-path collective",
                        "setup_steps_before_warmup": n_prime,
-                       "pipeline": ("pair pipeline: pyramid of pair i+1 on a side stream during the network pass of pair i"
+                       "pipeline": (("pair pipeline, three pairs in flight: pyramid of pair i+2 (side stream), backbone of pair i+1 and matching "
+                                     "tail of pair i (two network streams); the tail and the searches wait for the encoder of pair i+1, so "
+                                     "the KPConv gathers run alone" if pipe.overlap else
+                                     "pair pipeline: pyramid of pair i+1 on a side stream during the network pass of pair i")
                                     if pipelined else "off: one pair at a time")},
             "wall_ms_per_step_incl_flush": wall_ms / args.steps,
             "step_ms_stats": {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)), "max": float(np.max(step_ms)),
@@ -626,23 +648,22 @@ def run_sweep(args, rank, world, local_rank):
         torch.cuda.synchronize()
         gc.collect(); gc.disable()
 
-        def before(i, ev=ev):
-            if i < len(ev):
-                flush.fill_(i & 0xFF)
-                ev[i][0].record()
-        gen = pipe.run(items + items[:1], before_step=before)
-        n_corr = 0
-        for i in range(len(items)):
-            out = next(gen)
+        t_first = torch.cuda.Event(enable_timing=True)
+        t_first.record()
+
+        def before(i):
+            flush.fill_(i & 0xFF)
+
+        def after(i, ev=ev):
             ev[i][1].record()
+        n_corr = 0
+        for out in pipe.run(items, before_step=before, after_step=after):
             n_corr += int(out["corr_scores"].shape[0])
         torch.cuda.synchronize()
-        for _ in gen:
-            pass
         gc.enable()
         prof = [r for r in L.prof_read() if r[0] == 1]
         L.prof_enable(False)
-        ms = float(sum(a.elapsed_time(b) for a, b in ev))
+        ms = float(t_first.elapsed_time(ev[-1][1]))  # all pairs of the class through the pipeline, fill and drain included
         gb = sum(kpconv_gather_bytes(m_, h_, c_, 64 if c_ == 1 else c_, 4) for _, _, m_, _, h_, c_ in prof)
         gms = sum(r[1] for r in prof)
         t = torch.tensor([float(len(items)), ms, float(gb), gms, float(n_corr), float(sum(int(x[0].shape[0]) for x in items))],
@@ -668,8 +689,9 @@ def run_sweep(args, rank, world, local_rank):
                 "config": {"workload": "config 5: %d-pair synthetic sweep, %d pairs per size class %s (points/scan), round-robin over ranks"
                                        % (args.sweep_pairs, per_class, classes),
                            "distinct_geometries_per_class": distinct, "neighbor_limits": LIMITS,
-                           "l2": "256 MiB flush write between pairs (untimed)",
-                           "timing": "CUDA events per pair on the launch stream; per class: all pairs / slowest rank"},
+                           "l2": "256 MiB flush write queued before every pair enters the network (inside the timed region)",
+                           "timing": "per class: CUDA events around all its pairs through the pair pipeline (idle GPU to idle GPU); "
+                                     "all pairs / slowest rank"},
                 "sweep": res, "roofline_peak": {"hbm_gbs": peak, "source": peak_src}}
         emit(json.dumps(line))
     if world > 1:
@@ -714,9 +736,9 @@ def run_train(args, rank, world, local_rank):
         wdesc = "random init"
     model = model.to(dev).train()
     loss_fn = loss_mod.OverallLoss(cfg).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-6)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-6, fused=True)  # trainval.py:34 (fused = same update, one launch)
     comm_dtype = torch.bfloat16 if args.train_comm == "bf16" else torch.float32
-    red = ddp.BucketedGradAllReduce(model, comm_dtype=comm_dtype) if world > 1 else None
+    red = ddp.BucketedGradAllReduce(model, bucket_bytes=8 << 20, comm_dtype=comm_dtype) if world > 1 else None
     pairs = make_pairs(args.pairs, rank)
     items = [dict(ref_points=p["ref_points"], src_points=p["src_points"], ref_feats=np.ones((len(p["ref_points"]), 1), np.float32),
                   src_feats=np.ones((len(p["src_points"]), 1), np.float32), transform=p["transform"].astype(np.float32)) for p in pairs]
@@ -740,7 +762,10 @@ def run_train(args, rank, world, local_rank):
         with torch.device(dev):  # loss.py:240-243 builds index helpers with bare torch.arange (torch 1.8 tolerated the device mix)
             losses = loss_fn(out, dd)
         mark(3)
-        opt.zero_grad(set_to_none=True)
+        if red is not None:
+            red.zero_grad()  # gradients are views into the reducer's flat buckets: zero in place
+        else:
+            opt.zero_grad(set_to_none=True)
         losses["loss"].backward()
         mark(4)
         if red is not None:
@@ -750,7 +775,7 @@ def run_train(args, rank, world, local_rank):
         mark(6)
         h2d = sum(int(v.nbytes) for v in it.values())
         d2h = 4
-        return float(losses["loss"])  # the D2H read of the step's result (the reference logs it every iteration)
+        return float(losses["loss"].detach())  # the D2H read of the step's result (the reference logs it every iteration)
 
     for i in range(max(args.warmup, 3)):
         step(i)
@@ -773,6 +798,27 @@ def run_train(args, rank, world, local_rank):
     clocks = sampler.stop()
     launches = L.launch_count() - launches0
     phase = np.array([[e[k].elapsed_time(e[k + 1]) for k in range(6)] for e in evs])  # ms
+    # the collectives alone (ranks aligned by a barrier, nothing else in flight): separates wire time from rank skew in `exposed`
+    alone_ms = 0.0
+    if red is not None:
+        reps = 5
+        dist.barrier()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(reps):
+            for wbuf in red.wire:
+                dist.all_reduce(wbuf)
+        a1.record()
+        torch.cuda.synchronize()
+        alone_ms = a0.elapsed_time(a1) / reps
+    if rank == 0 and os.environ.get("BENCH_TRAIN_PROFILE"):  # debugging aid: kernel-time table of two more (untimed) steps -> stderr
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for i in range(2):
+                step(args.warmup + args.steps + i)
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70), file=sys.stderr)
     dev_ms = float(phase.sum())
     t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -793,9 +839,11 @@ def run_train(args, rank, world, local_rank):
                 "e2e": {"value": world * args.steps / (wall_ms_max / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches),
                 "allreduce": {"bytes_per_step": red.bytes_per_step if red is not None else 0, "buckets": len(red.buckets) if red is not None else 0,
-                              "wire_dtype": args.train_comm, "exposed_ms": per["allreduce_exposed"],
+                              "wire_dtype": args.train_comm, "exposed_ms": per["allreduce_exposed"], "collectives_alone_ms": alone_ms,
                               "exposed_frac_of_step": per["allreduce_exposed"] / max(dev_ms / args.steps, 1e-9),
-                              "note": "exposed = launch-stream time between the end of backward and the averaged gradients being in place"},
+                              "note": "exposed = launch-stream time between the end of backward and the averaged gradients being in place: the "
+                                      "wire time of the last bucket PLUS the wait for the slower rank (ranks train on different pairs and "
+                                      "are host-bound); collectives_alone_ms = all buckets back to back after a barrier"},
                 "loss_first_last": [loss_vals[0], loss_vals[-1]], "clocks": clocks}
         emit(json.dumps(line))
     if world > 1:

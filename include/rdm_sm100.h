@@ -329,6 +329,9 @@ typedef struct {
   int ld_feats_f;
   float* p2p_scores;
 } rdm_backbone_out;
+/* Optional: a cudaEvent_t that the NEXT rdm_backbone_forward calls record on their stream right after the encoder (NULL = off).
+ * Lets a caller that keeps several pairs in flight order other streams behind the KPConv gathers (rdmnet_b200.model.PairPipeline). */
+int rdm_backbone_set_encoder_event(void* cuda_event);
 size_t rdm_backbone_workspace(const rdm_backbone_desc* h_desc, const rdm_pyramid_desc* h_pyr, int nc_ref);
 int rdm_backbone_forward(const rdm_backbone_desc* h_desc, const rdm_pyramid_desc* h_pyr, int nc_ref, const float* in_feats,
                          const rdm_backbone_out* h_out, void* workspace, size_t workspace_bytes, rdm_stream_t stream);
@@ -488,6 +491,15 @@ int rdm_maxpool_bwd(const float* feats, const void* neighbor_indices, int index_
                     int C, float* d_feats_zeroed, rdm_stream_t stream);
 int rdm_upsample_concat_bwd(const float* d_out, const void* upsample_indices, int index_bytes, int index_stride, int M, int N,
                             int C1, int C2, float* d_feats_zeroed, float* d_skip, rdm_stream_t stream);
+/* Linear backward in one call (x [M,K], dy [M,N], W [N,K] when w_is_nk else [K,N]): dx [M,K] = dy W, dW (W's layout) = dy^T x or
+ * x^T dy, db [N] += column sums of dy (db must be zeroed by the caller); any of dx / dw / db may be NULL. The three products run on
+ * the tensor-core GEMM with the contraction-slow operands transposed into the workspace. torch autograd of F.linear does the same
+ * three products (the reference: loss.backward(), geotransformer/engine/epoch_based_trainer.py:104). */
+size_t rdm_linear_bwd_workspace(int M, int N, int K);
+int rdm_linear_bwd(const float* x, const float* w, int w_is_nk, const float* dy, int M, int N, int K, float* dx, float* dw,
+                   float* db_zeroed, void* workspace, size_t workspace_bytes, rdm_stream_t stream);
+/* workspace that lets rdm_linear run a [K,N]-layout B on the tensor cores (transposed copy + split-K partials) */
+size_t rdm_linear_kn_workspace(int M, int N, int K);
 /* out_accum[index[i], :] += src[i, :] (backward of rdm_index_select); rows of row_floats fp32. */
 int rdm_scatter_add_rows(const float* src, const void* index, int index_bytes, int64_t count, int row_floats, int64_t rows,
                          float* out_accum, rdm_stream_t stream);

@@ -91,7 +91,12 @@ SIGNATURES = {
                                   c_void_p, c_void_p]),
     "rdm_maxpool_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "rdm_upsample_concat_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "rdm_linear_bwd_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "rdm_linear_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                               c_void_p]),
+    "rdm_linear_kn_workspace": (c_size_t, [c_int, c_int, c_int]),
     "rdm_scatter_add_rows": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_int, c_i64, c_void_p, c_void_p]),
+    "rdm_backbone_set_encoder_event": (c_int, [c_void_p]),
     "rdm_set_precision": (c_int, [c_int]),
     "rdm_get_precision": (c_int, []),
     "rdm_rope_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

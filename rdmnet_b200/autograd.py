@@ -24,13 +24,17 @@ def _ws(n, dev):
 
 
 def _raw_linear(x, w, bias, b_is_nk, act=0):
-    """C = act(x @ (w^T if b_is_nk else w) + bias) through rdm_linear (no autograd)."""
+    """C = act(x @ (w^T if b_is_nk else w) + bias) through rdm_linear (no autograd). A [K,N]-layout weight gets the workspace that
+    lets the library transpose it and stay on the tensor cores."""
     x = x.contiguous()
     w = w.contiguous()
     m, k = x.shape
     n = w.shape[0] if b_is_nk else w.shape[1]
     out = torch.empty((m, n), dtype=torch.float32, device=x.device)
-    wsb = L.lib().rdm_linear_workspace(m, n, k) if m * n <= (1 << 20) else 0
+    if b_is_nk:
+        wsb = L.lib().rdm_linear_workspace(m, n, k) if m * n <= (1 << 20) else 0
+    else:
+        wsb = L.lib().rdm_linear_kn_workspace(m, n, k)
     ws = _ws(wsb, x.device) if wsb else None
     L.call("rdm_linear", L.ptr(x), k, L.ptr(w), w.shape[1], 1 if b_is_nk else 0, L.ptr(bias), L.ptr(out), n, m, n, k, act,
            L.ptr(ws), wsb, L.stream())
@@ -64,21 +68,19 @@ class Linear(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, w, y = ctx.saved_tensors
-        dy = dy.contiguous()
+        x, w, dy = x.contiguous(), w.contiguous(), dy.contiguous()
         if ctx.act:
             dy = _act_bwd(y, dy, ctx.act)
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            # kn: dx = dy @ W^T with W [K,N] -> "nn.Linear layout" operand (tensor-core path); else dx = dy @ W, W [N,K] as [inner, out]
-            dx = _raw_linear(dy, w, None, ctx.kn)
-        if ctx.needs_input_grad[1]:
-            if ctx.kn:  # dW [K,N] = x^T @ dy
-                dw = _raw_linear(transpose(x), dy, None, False)
-            else:       # dW [N,K] = dy^T @ x
-                dw = _raw_linear(transpose(dy), x, None, False)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = torch.zeros(dy.shape[1], dtype=torch.float32, device=dy.device)
-            L.call("rdm_colsum", L.ptr(dy), dy.shape[0], dy.shape[1], dy.shape[1], L.ptr(db), L.stream())
+        m, k = x.shape
+        n = dy.shape[1]
+        dev = dy.device
+        dx = torch.empty((m, k), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        db = torch.zeros(n, dtype=torch.float32, device=dev) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        wsb = L.lib().rdm_linear_bwd_workspace(m, n, k)
+        ws = _ws(wsb, dev)
+        L.call("rdm_linear_bwd", L.ptr(x), L.ptr(w), 0 if ctx.kn else 1, L.ptr(dy), m, n, k, L.ptr(dx), L.ptr(dw), L.ptr(db), L.ptr(ws), wsb,
+               L.stream())
         return dx, dw, db, None, None
 
 

@@ -83,14 +83,15 @@ __global__ void __launch_bounds__(256) kpconv_gather_bwd_kernel(const float* __r
   }
 }
 
-__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ x, int R, int C, int ldx, float* __restrict__ y) {
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ x, int R, int C, int ldx, float* __restrict__ y,
+                                                        int ldy) {
   __shared__ float t[32][33];
   const int bx = blockIdx.x * 32, by = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int i = ty; i < 32; i += 8)
     if (by + i < R && bx + tx < C) t[i][tx] = x[(size_t)(by + i) * ldx + bx + tx];
   __syncthreads();
   for (int i = ty; i < 32; i += 8)
-    if (bx + i < C && by + tx < R) y[(size_t)(bx + i) * R + by + tx] = t[tx][i];
+    if (bx + i < C && by + tx < R) y[(size_t)(bx + i) * ldy + by + tx] = t[tx][i];
 }
 
 // out[c] (+)= sum_r x[r, c]: grid (ceil(C/32), row chunks), fp32 partial sums, one atomicAdd per (CTA, column)
@@ -309,11 +310,83 @@ extern "C" int rdm_kpconv_gather_bwd(const float* d_weighted, const float* s_fea
   return RDM_OK;
 }
 
-extern "C" int rdm_transpose(const float* x, int rows, int cols, int ldx, float* y, cudaStream_t stream) {
-  RDM_CHECK_ARG(rows >= 0 && cols >= 0 && ldx >= cols, "rdm_transpose: bad shape");
+int rdm_transpose_ld(const float* x, int rows, int cols, int ldx, float* y, int ldy, cudaStream_t stream) {
+  RDM_CHECK_ARG(rows >= 0 && cols >= 0 && ldx >= cols && ldy >= rows, "rdm_transpose: bad shape");
   if (rows == 0 || cols == 0) return RDM_OK;
-  transpose_kernel<<<dim3(cdiv(cols, 32), cdiv(rows, 32)), 256, 0, stream>>>(x, rows, cols, ldx, y);
+  RDM_CHECK_ARG(cdiv(rows, 32) <= 65535, "rdm_transpose: more than 2M rows");  // grid.y limit
+  transpose_kernel<<<dim3(cdiv(cols, 32), cdiv(rows, 32)), 256, 0, stream>>>(x, rows, cols, ldx, y, ldy);
   RDM_LAUNCH_CHECK();
+  return RDM_OK;
+}
+extern "C" int rdm_transpose(const float* x, int rows, int cols, int ldx, float* y, cudaStream_t stream) {
+  return rdm_transpose_ld(x, rows, cols, ldx, y, rows, stream);
+}
+
+// ---- Linear backward in ONE call: y = x W^T (+ b) with W [N,K] (w_is_nk) or y = x W with W [K,N]; x [M,K], dy [M,N].
+//   dx [M,K] = dy W          db [N] = column sums of dy          dW = dy^T x  ([N,K])  or  x^T dy  ([K,N])
+// All three products run on the tensor-core GEMM: the operand that has the contraction index as its SLOW index is transposed
+// into the workspace first (dy^T and x^T for dW: the contraction runs over the M points; W^T for dx when W is [N,K]).
+extern "C" size_t rdm_linear_bwd_workspace(int M, int N, int K) {
+  const size_t Mp = (size_t)((M + 3) & ~3);
+  size_t t = align_up((size_t)N * Mp * 4, 256) + align_up((size_t)K * Mp * 4, 256) + align_up((size_t)N * ((K + 3) & ~3) * 4, 256) +
+             align_up((size_t)K * ((N + 3) & ~3) * 4, 256);
+  return t + align_up((size_t)16 * N * K * 4, 256) + ((long long)M * K <= (1 << 20) ? (size_t)16 * M * K * 4 : 0) + 1024;
+}
+
+extern "C" int rdm_linear_bwd(const float* x, const float* w, int w_is_nk, const float* dy, int M, int N, int K, float* dx, float* dw,
+                              float* db_zeroed, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  RDM_CHECK_ARG(M >= 0 && N >= 1 && K >= 1, "rdm_linear_bwd: bad shape");
+  if (workspace_bytes < rdm_linear_bwd_workspace(M, N, K)) {
+    rdm_set_error("rdm_linear_bwd: workspace too small");
+    return RDM_ERR_WORKSPACE;
+  }
+  if (M == 0) {
+    if (dw) RDM_CUDA(cudaMemsetAsync(dw, 0, (size_t)N * K * sizeof(float), stream));
+    return RDM_OK;
+  }
+  Workspace ws(workspace, workspace_bytes);
+  const int Mp = (M + 3) & ~3, Np = (N + 3) & ~3;
+  int rc;
+  if (db_zeroed) {
+    rc = rdm_colsum(dy, M, N, N, db_zeroed, stream);
+    if (rc != RDM_OK) return rc;
+  }
+  if (dx) {
+    // dx = dy [M,N] . B with B as [out = K, inner = N]
+    const float* B = w;
+    int ldb = N;
+    if (w_is_nk) {  // W [N,K] -> W^T [K, Np]
+      float* wt = ws.get<float>((size_t)K * Np);
+      // (the padding columns N..Np are never read: the GEMM's inner extent is N, the tensor maps zero-fill beyond it)
+      rc = rdm_transpose_ld(w, N, K, K, wt, Np, stream);
+      if (rc != RDM_OK) return rc;
+      B = wt;
+      ldb = Np;
+    }
+    const size_t part = (long long)M * K <= (1 << 20) ? (size_t)16 * M * K * 4 : 0;
+    void* p = part ? (void*)ws.get<char>(part) : nullptr;
+    rc = rdm_linear_gn(dy, N, B, ldb, 1, nullptr, dx, K, M, K, N, 0, p, part, nullptr, 0, nullptr, stream);
+    if (rc != RDM_OK) return rc;
+  }
+  if (dw) {
+    float* dyt = ws.get<float>((size_t)N * Mp);  // [N, Mp]
+    float* xt = ws.get<float>((size_t)K * Mp);   // [K, Mp]
+    rc = rdm_transpose_ld(dy, M, N, N, dyt, Mp, stream);
+    if (rc != RDM_OK) return rc;
+    rc = rdm_transpose_ld(x, M, K, K, xt, Mp, stream);
+    if (rc != RDM_OK) return rc;
+    const size_t part = (size_t)16 * N * K * 4;
+    void* p = ws.get<char>(part);
+    if (w_is_nk)  // dW [N,K] = dy^T [N,M] . (x^T as [out = K, inner = M])
+      rc = rdm_linear_gn(dyt, Mp, xt, Mp, 1, nullptr, dw, K, N, K, M, 0, p, part, nullptr, 0, nullptr, stream);
+    else          // dW [K,N] = x^T [K,M] . (dy^T as [out = N, inner = M])
+      rc = rdm_linear_gn(xt, Mp, dyt, Mp, 1, nullptr, dw, N, K, N, M, 0, p, part, nullptr, 0, nullptr, stream);
+    if (rc != RDM_OK) return rc;
+  }
+  if (!ws.ok) {
+    rdm_set_error("rdm_linear_bwd: workspace overflow");
+    return RDM_ERR_WORKSPACE;
+  }
   return RDM_OK;
 }
 

@@ -250,6 +250,12 @@ extern "C" size_t rdm_linear_workspace(int M, int N, int K) {
   // worst case: 16 split-K partial buffers
   return (size_t)16 * M * N * sizeof(float) + 256;
 }
+// [K,N]-layout B on the tensor cores: room for the transposed copy in front of the split-K partials (small outputs only)
+extern "C" size_t rdm_linear_kn_workspace(int M, int N, int K) {
+  const size_t t = align_up((size_t)N * ((K + 3) & ~3) * sizeof(float), 256);
+  return t + ((long long)M * N <= (1 << 20) ? rdm_linear_workspace(M, N, K) : 0);
+}
+int rdm_transpose_ld(const float* x, int rows, int cols, int ldx, float* y, int ldy, cudaStream_t stream);  // backward.cu
 
 int rdm_linear_tc(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N, int K,
                   int act, void* workspace, size_t workspace_bytes, int* out_splits, double* gn_stats, int gn_cpg,
@@ -318,6 +324,20 @@ int rdm_linear_gn_ps(const float* A, int lda, const float* B, int ldb, int b_is_
   if (use_tc < 0) {
     const char* e = getenv("RDM_GEMM_TC");  // debug knob: RDM_GEMM_TC=0 forces the SIMT kernel
     use_tc = (e && e[0] == '0') ? 0 : 1;
+  }
+  // [K,N]-layout weights (KPConv weights in the per-operator / training path, the dx and dW products of rdm_linear_bwd): when the
+  // caller's workspace has room, transpose B once into its head ([N, Kp], Kp = K rounded up to 4) and run the tensor-core
+  // kernels on that; the tail of the workspace stays available for split-K partials.
+  if (use_tc && !b_is_nk && M >= 64 && N >= 8 && K >= 8 && workspace != nullptr) {
+    const int Kp = (K + 3) & ~3;
+    const size_t need = align_up((size_t)N * Kp * sizeof(float), 256);
+    if (workspace_bytes >= need && (lda % 4 == 0) && aligned16(A) && aligned16(workspace)) {
+      float* Bt = (float*)workspace;
+      int rc = rdm_transpose_ld(B, K, N, ldb, Bt, Kp, stream);
+      if (rc != RDM_OK) return rc;
+      return rdm_linear_gn_ps(A, lda, Bt, Kp, 1, bias, C, ldc, M, N, K, act, (char*)workspace + need, workspace_bytes - need, gn_stats,
+                              gn_cpg, stats_fused, nullptr, stream);
+    }
   }
   if (use_tc && b_is_nk && M >= 64) {
     int tc_splits = 1;

@@ -577,6 +577,11 @@ extern "C" int rdm_build_pyramid(const float* points, const int64_t* lengths, in
 
 // ------------------------------------------------------------------------------------------------ backbone runner
 namespace {
+// Optional marker recorded right after the encoder inside rdm_backbone_forward (rdm_backbone_set_encoder_event): the pair
+// pipeline holds the PREVIOUS pair's matching tail and the NEXT pair's radius searches behind it, so that the KPConv gathers
+// have the machine to themselves and the latency-bound transformer / decoder / matching kernels of two pairs share it.
+cudaEvent_t g_encoder_done = nullptr;
+
 int backbone_run(Arena& a, const rdm_backbone_desc& d, const rdm_pyramid_desc& p, int nc_ref, const float* in_feats,
                  const rdm_backbone_out& o, cudaStream_t st) {
   const int S = p.num_stages, top = S - 1;
@@ -587,6 +592,7 @@ int backbone_run(Arena& a, const rdm_backbone_desc& d, const rdm_pyramid_desc& p
   for (int i = 0; i < d.num_blocks; i++) last_c[d.h_blocks[i].stage] = d.h_blocks[i].c_out;
   for (int s = 0; s < S; s++) enc_out[s] = a.f((size_t)p.n[s] * last_c[s]);
   RDM_TRY(encoder_run(a, d.h_blocks, d.num_blocks, p, d.groups, in_feats, enc_out, st));
+  if (!a.dry && g_encoder_done != nullptr) RDM_CUDA(cudaEventRecord(g_encoder_done, st));
   // first ThDRoFormer on the coarsest stage (model.py:154-159), n2p score head (:160-167)
   const float* pc = p.points[top];
   RDM_TRY(thdroformer_run(a, *d.h_transformer1, pc, nc_ref, pc + 3 * (size_t)nc_ref, nc - nc_ref, enc_out[top], last_c[top],
@@ -609,6 +615,11 @@ int backbone_run(Arena& a, const rdm_backbone_desc& d, const rdm_pyramid_desc& p
   return RDM_OK;
 }
 }  // namespace
+
+extern "C" int rdm_backbone_set_encoder_event(void* cuda_event) {
+  g_encoder_done = (cudaEvent_t)cuda_event;
+  return RDM_OK;
+}
 
 extern "C" size_t rdm_backbone_workspace(const rdm_backbone_desc* h_desc, const rdm_pyramid_desc* h_pyr, int nc_ref) {
   Arena a(nullptr, 0, true);

@@ -2,10 +2,11 @@
 torch DistributedDataParallel (geotransformer/engine/base_trainer.py:181-191: fp32 gradients, 25 MB buckets) and
 all-reduces every logged scalar separately each iteration (utils/torch.py:16-21, base_trainer.py:236). Here:
 
-  BucketedGradAllReduce   gradients are packed per bucket into a flat bf16 (or fp32) buffer as soon as the bucket's last
-                          gradient has been accumulated (post-accumulate-grad hooks), the NCCL all-reduce of the bucket is
-                          launched asynchronously - it overlaps the rest of the backward pass -, and `finish()` (before the
-                          optimizer step) waits, averages and unpacks. 25.3 M parameters = 50.6 MB in bf16 per step.
+  BucketedGradAllReduce   parameter gradients are views into flat fp32 bucket buffers; as soon as a bucket's last gradient has been
+                          accumulated (post-accumulate-grad hooks) the bucket is cast to bf16 (or sent as fp32) and its NCCL
+                          all-reduce is launched asynchronously - it overlaps the rest of the backward pass -, and `finish()`
+                          (before the optimizer step) waits, casts back and averages: two kernels per bucket, nothing per
+                          parameter. 25.3 M parameters = 50.6 MB in bf16 per step.
   all_reduce_scalars      ONE collective for all logged scalars instead of one per key.
 
 One process per GPU (torchrun); NCCL over NVLink / NVSwitch on the GPU box, gloo in the CPU tests. The hooks only pack,
@@ -15,6 +16,13 @@ import torch.distributed as dist
 
 
 class BucketedGradAllReduce:
+    """Gradients live in flat fp32 bucket buffers: every parameter's `.grad` is a VIEW into its bucket (like torch DDP's
+    gradient_as_bucket_view), so packing and unpacking cost nothing. A post-accumulate-grad hook counts the bucket down; when its
+    last gradient has been accumulated the bucket is cast to the wire dtype (one kernel; skipped for fp32) and its all-reduce is
+    launched asynchronously, overlapping the rest of the backward pass. `finish()` (before the optimizer step) waits, casts back and
+    scales by 1/world: two kernels per bucket, none per parameter. Use `zero_grad()` of this object (one memset per bucket) instead
+    of `optimizer.zero_grad(set_to_none=True)`, which would detach the views."""
+
     def __init__(self, module, bucket_bytes=25 << 20, comm_dtype=torch.bfloat16, group=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -31,16 +39,18 @@ class BucketedGradAllReduce:
                 cur, size = [], 0
         if cur:
             self.buckets.append(cur)
-        self.flat = [torch.zeros(sum(p.numel() for p in b), dtype=comm_dtype, device=b[0].device) for b in self.buckets]
+        self.flat = [torch.zeros(sum(p.numel() for p in b), dtype=torch.float32, device=b[0].device) for b in self.buckets]
+        self.wire = [f if comm_dtype == torch.float32 else torch.zeros_like(f, dtype=comm_dtype) for f in self.flat]
         self.where = {}
         for bi, b in enumerate(self.buckets):
             off = 0
             for p in b:
-                self.where[p] = (bi, off)
+                self.where[p] = bi
+                p.grad = self.flat[bi][off:off + p.numel()].view_as(p)
                 off += p.numel()
         self.pending = [0] * len(self.buckets)
         self.handles = [None] * len(self.buckets)
-        self.bytes_per_step = sum(f.numel() * f.element_size() for f in self.flat)
+        self.bytes_per_step = sum(w.numel() * w.element_size() for w in self.wire)
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
         self.reset()
 
@@ -48,35 +58,35 @@ class BucketedGradAllReduce:
         self.pending = [len(b) for b in self.buckets]
         self.handles = [None] * len(self.buckets)
 
+    def zero_grad(self):
+        for f in self.flat:
+            f.zero_()
+
+    def _launch(self, bi):
+        if self.world > 1:
+            if self.wire[bi] is not self.flat[bi]:
+                self.wire[bi].copy_(self.flat[bi])  # cast to the communication dtype
+            self.handles[bi] = dist.all_reduce(self.wire[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
     def _on_grad(self, p):
-        bi, off = self.where[p]
-        self.flat[bi][off:off + p.numel()].copy_(p.grad.reshape(-1))  # cast to the communication dtype
+        bi = self.where[p]
         self.pending[bi] -= 1
-        if self.pending[bi] == 0 and self.world > 1:
-            self.handles[bi] = dist.all_reduce(self.flat[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        if self.pending[bi] == 0:
+            self._launch(bi)
 
     def finish(self):
-        """Waits for the bucket collectives and writes the averaged gradients back. Parameters that received no gradient
-        in this step (their bucket never completed) are reduced here as zeros, so that all ranks stay in lock step."""
-        for bi, b in enumerate(self.buckets):
+        """Waits for the bucket collectives and leaves the averaged gradients in place. A bucket whose countdown did not reach zero
+        (a parameter received no gradient in this step: its slice is still zero) is reduced here, so that all ranks stay in lock
+        step."""
+        for bi in range(len(self.buckets)):
             if self.pending[bi] != 0:
-                for p in b:
-                    if p.grad is None:
-                        _, off = self.where[p]
-                        self.flat[bi][off:off + p.numel()].zero_()
-                if self.world > 1:
-                    self.handles[bi] = dist.all_reduce(self.flat[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        for bi, b in enumerate(self.buckets):
+                self._launch(bi)
+        for bi in range(len(self.buckets)):
             if self.handles[bi] is not None:
                 self.handles[bi].wait()
-            if self.world > 1:
-                for p in b:
-                    _, off = self.where[p]
-                    g = self.flat[bi][off:off + p.numel()].view_as(p).to(p.dtype) / self.world
-                    if p.grad is None:
-                        p.grad = g.clone()
-                    else:
-                        p.grad.copy_(g)
+                if self.wire[bi] is not self.flat[bi]:
+                    self.flat[bi].copy_(self.wire[bi])
+                self.flat[bi].mul_(1.0 / self.world)
         self.reset()
 
     def remove(self):

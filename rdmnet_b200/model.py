@@ -207,11 +207,21 @@ def build_pyramid_gpu(points, lengths, num_stages, voxel_size, radius, neighbor_
     return _DEFAULT_JOB.finish()
 
 
+_PIPE_STREAMS = {}
+
+
 class PairPipeline:
-    """Software pipeline over a stream of scan pairs: while pair i runs through the network on the main stream, the
-    voxel pyramid of pair i+1 is built on a side stream (what the reference's DataLoader workers do on CPU cores,
-    geotransformer/utils/data.py:223-253 with num_workers=8). Single host thread; results come out in input order and
-    are identical to model(data_dict) pair by pair."""
+    """Software pipeline over a stream of scan pairs, single host thread, results in input order and identical to
+    model(data_dict) pair by pair. Three pairs are in flight (RDM_PIPE_OVERLAP=0: two):
+
+        side stream      pyramid of pair i+2 (what the reference's DataLoader workers do on CPU cores, utils/data.py:223-253)
+        net stream A/B   encoder -> transformer 1 -> decoder of pair i+1   (forward_head, asynchronous)
+        net stream B/A   vote / NMS / transformer 2 / matching / pose of pair i   (forward_tail, two host syncs)
+
+    The path is a chain of ~330 small dependent kernels per pair (3.4 ms for a 8k-point pair, 4.3 ms for a 37k-point pair:
+    latency, not throughput), so two network passes share the GPU well - except the KPConv gathers, which are bandwidth-bound
+    and are therefore kept alone: the matching tail of pair i and the radius searches of pair i+2 wait for the event that
+    rdm_backbone_forward records after the encoder of pair i+1."""
 
     def __init__(self, model, device=None):
         self.model = model
@@ -219,13 +229,26 @@ class PairPipeline:
         # high priority: the side stream's kernels are few and small, and the host waits on the first of them (the
         # subsampling chain) before it can queue the rest of the pair in flight - they must not starve behind the
         # network's large grids
-        self.side = torch.cuda.Stream(self.device, priority=int(os.environ.get("RDM_PIPE_PRIORITY", "-1")))
+        # the streams are shared by every pipeline of a device: the caching allocator keeps one block pool per stream, and a
+        # fresh stream would start with an empty pool (cudaMalloc inside somebody's timed region)
+        res = _PIPE_STREAMS.get(self.device)
+        if res is None:
+            side = torch.cuda.Stream(self.device, priority=int(os.environ.get("RDM_PIPE_PRIORITY", "-1")))
+            nets = [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
+            enc_done = [torch.cuda.Event(), torch.cuda.Event()]
+            for e, st in zip(enc_done, nets):
+                e.record(st)  # instantiates the CUDA event (torch creates it lazily)
+            res = _PIPE_STREAMS[self.device] = (side, nets, enc_done)
+        self.side, self.nets, self.enc_done = res
         self.jobs = [PyramidJob(), PyramidJob()]
-        # the next pair's radius searches are held back until the current pair's backbone has drained, so that they share
-        # the SMs with the (latency-bound) matching tail instead of with the KPConv gathers: measured +10 % gather
+        # the next pair's radius searches are held back until the pair in the network has left its encoder, so that they share
+        # the SMs with the (latency-bound) rest instead of with the KPConv gathers: measured +10 % gather
         # bandwidth and +2 % pairs/s inside the pipelined bench region (profiles/README.md, r2a). RDM_PIPE_DEFER_SEARCH=0
         # restores the eager order.
         self.defer_searches = os.environ.get("RDM_PIPE_DEFER_SEARCH", "1") == "1"
+        self.overlap = os.environ.get("RDM_PIPE_OVERLAP", "1") == "1"
+        # RDM_PIPE_GATHER_ALONE=0 lets the matching tail of pair i start at once, on top of the encoder of pair i+1 (A/B knob)
+        self.gather_alone = os.environ.get("RDM_PIPE_GATHER_ALONE", "1") == "1"
 
     def _begin(self, item, slot):
         points, lengths = item() if callable(item) else item  # a callable may stage host data (runs on the side stream)
@@ -238,10 +261,14 @@ class PairPipeline:
         ev.record(self.side)
         return gp, ev
 
-    def run(self, items, before_step=None):
+    def run(self, items, before_step=None, after_step=None):
         """items: iterable of (points (N,3) f32 cuda, lengths (2,) i64 cuda) or of callables returning such a tuple
-        (called under the side stream). Yields the model's output dict per pair. before_step(i), if given, runs on the
-        main stream right before pair i enters the network (bench.py: L2 flush + event record)."""
+        (called under the side stream). Yields the model's output dict per pair. before_step(i), if given, runs on pair i's
+        network stream right before pair i enters the network (bench.py: L2 flush); after_step(i) right after its last
+        kernel (bench.py: timing event)."""
+        if self.overlap:
+            yield from self._run_overlapped(items, before_step, after_step)
+            return
         main = torch.cuda.current_stream(self.device)
         it = iter(items)
         first = next(it, None)
@@ -275,8 +302,75 @@ class PairPipeline:
                     if backbone_done is not None:
                         self.side.wait_event(backbone_done)  # ordered before the searches that _finish queues
                     cur = self._finish((i + 1) & 1)  # host waits for the (short) subsampling chain only
-            yield self.model.forward_tail(state)
+            out = self.model.forward_tail(state)
+            if after_step is not None:
+                after_step(i)
+            yield out
             i += 1
+
+    # ---- three pairs in flight
+    def _head(self, i, pyr, before_step):
+        """Queues encoder + transformer 1 + decoder of pair i on net stream i & 1 (asynchronous)."""
+        gp, ready = pyr
+        s = self.nets[i & 1]
+        with torch.cuda.stream(s):
+            if before_step is not None:
+                before_step(i)
+            s.wait_event(ready)
+            for t in (gp.buf, gp._points0) + tuple(gp._keep):  # allocated under the side stream, read here (see run())
+                t.record_stream(s)
+            L.call("rdm_backbone_set_encoder_event", self.enc_done[i & 1].cuda_event)
+            try:
+                state = self.model.forward_head(None, gp=gp)
+            finally:
+                L.call("rdm_backbone_set_encoder_event", None)
+        return state
+
+    def _run_overlapped(self, items, before_step, after_step):
+        caller = torch.cuda.current_stream(self.device)
+        it = iter(items)
+        first = next(it, None)
+        if first is None:
+            return
+        for s in [self.side] + self.nets:
+            s.wait_stream(caller)
+        with torch.cuda.stream(self.side):
+            self._begin(first, 0)
+            pyr = self._finish(0)
+        state = self._head(0, pyr, before_step)
+        pyr_next = None
+        nxt = next(it, None)
+        if nxt is not None:
+            with torch.cuda.stream(self.side):
+                self._begin(nxt, 1)
+                if self.defer_searches:
+                    self.side.wait_event(self.enc_done[0])
+                pyr_next = self._finish(1)
+        i = 0
+        while state is not None:
+            state_next = None
+            if pyr_next is not None:
+                state_next = self._head(i + 1, pyr_next, before_step)  # queued BEFORE the tail of pair i
+                pyr_next = None
+                nxt = next(it, None)
+                if nxt is not None:
+                    with torch.cuda.stream(self.side):
+                        self._begin(nxt, i & 1)  # job slot of pair i, whose pyramid was handed over long ago
+                        if self.defer_searches:
+                            self.side.wait_event(self.enc_done[(i + 1) & 1])
+                        pyr_next = self._finish(i & 1)
+            s = self.nets[i & 1]
+            with torch.cuda.stream(s):
+                if state_next is not None and self.gather_alone:
+                    s.wait_event(self.enc_done[(i + 1) & 1])  # the gathers of pair i+1 run alone
+                out = self.model.forward_tail(state)  # ends with a host sync of this stream
+                if after_step is not None:
+                    after_step(i)
+            for v in out.values():  # produced on a net stream, consumed by the caller on its own stream
+                if torch.is_tensor(v) and v.is_cuda:
+                    v.record_stream(caller)
+            yield out
+            state, i = state_next, i + 1
 
 
 def _state_key(module):

@@ -42,7 +42,7 @@ def _worker(rank, world, port, comm_dtype, q):
         grads = []
         for step in range(2):  # two steps: the reducer must re-arm
             x, y = _data(rank + 10 * step)
-            model.zero_grad(set_to_none=True)
+            red.zero_grad()
             out = model(x)
             if rank == 1 and step == 1:
                 loss = ((out[:, :2] - y[:, :2]) ** 2).mean() * 0.5  # rank-dependent graph: still no dead-lock
@@ -94,7 +94,7 @@ def test_bucketed_allreduce_fp32_equals_mean_of_rank_gradients():
             g = got[rank][1][step]
             for n, e in exp.items():
                 assert torch.allclose(torch.from_numpy(g[n]), e, rtol=1e-5, atol=1e-7), (step, rank, n)
-            assert "unused" in g and not g["unused"].any()  # reduced as zeros on every rank
+            assert "unused" in g and not g["unused"].any()  # never touched: stays zero on every rank
     assert got[0][2] == got[1][2]
     assert abs(got[0][2]["rank"] - 0.5) < 1e-6 and abs(got[0][2]["const"] - 3.0) < 1e-6
 

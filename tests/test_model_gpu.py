@@ -175,22 +175,34 @@ def test_match_tail_runner_equals_stepwise_path(model, scans):
     close(fast["estimated_transform_host"], fast["estimated_transform"].cpu(), 0.0, "pinned pose readback")
 
 
-def test_pair_pipeline_equals_sequential(model, scans):
-    """PairPipeline (pyramid of pair i+1 on a side stream during pair i) yields, in order, exactly model(data_dict)."""
+@pytest.mark.parametrize("overlap", [True, False])
+def test_pair_pipeline_equals_sequential(model, scans, overlap):
+    """PairPipeline yields, in order, exactly model(data_dict): with three pairs in flight (pyramid of pair i+2 on the side stream,
+    backbone of pair i+1 and matching tail of pair i on two network streams - the default) and with two (RDM_PIPE_OVERLAP=0:
+    pyramid of pair i+1 during pair i). Seven pairs, so that the steady state, the fill and the drain are all exercised; the
+    hooks fire once per pair, in order."""
     from rdmnet_b200.model import PairPipeline
     from rdmnet_b200.api import PairStreamRegistrar, PairRegistrar
-    names = [("s000000", "s000004"), ("s000000", "s000007"), ("s000004", "s000007"), ("s000007", "s000000")]
+    names = [("s000000", "s000004"), ("s000000", "s000007"), ("s000004", "s000007"), ("s000007", "s000000"), ("s000004", "s000000"),
+             ("s000007", "s000004"), ("s000000", "s000004")]
     items = []
     for a, b in names:
         pts = torch.from_numpy(np.concatenate([scans[a], scans[b]])).cuda()
         items.append((pts, torch.tensor([len(scans[a]), len(scans[b])], dtype=torch.int64).cuda()))
     seq = [model({"points": p, "lengths": l}) for p, l in items]
-    outs = list(PairPipeline(model).run(items))
-    assert len(outs) == len(seq)
-    for o, s in zip(outs, seq):
-        for k in ("mask", "ref_node_corr_indices", "src_node_corr_indices", "ref_corr_points", "src_corr_points", "corr_scores",
-                  "estimated_transform", "ref_feats_c"):
-            assert torch.equal(o[k], s[k]), k
+    pipe = PairPipeline(model)
+    pipe.overlap = overlap
+    seen = {"before": [], "after": []}
+    for n_items in (len(items), 1, 2):
+        seen["before"].clear(), seen["after"].clear()
+        outs = list(pipe.run(items[:n_items], before_step=seen["before"].append, after_step=seen["after"].append))
+        assert len(outs) == n_items and seen["before"] == list(range(n_items)) and seen["after"] == list(range(n_items))
+        for o, s in zip(outs, seq):
+            for k in ("mask", "ref_node_corr_indices", "src_node_corr_indices", "ref_corr_points", "src_corr_points", "corr_scores",
+                      "estimated_transform", "ref_feats_c", "ref_feats_f", "src_p2p_scores_c"):
+                assert torch.equal(o[k], s[k]), (n_items, k)
+    if not overlap:
+        return
     # host-buffer API: streaming form == one-pair form
     host = [(scans[a], scans[b]) for a, b in names]
     one = PairRegistrar(model, max_points=1 << 16)

@@ -3,8 +3,9 @@ contractions to ONE tensor-core product per k-step (gemm_tc_fast.cu, 10-bit mant
 Sinkhorn and the pose solver stay fp32. Checked here:
   * the tf32 GEMM against fp64 on the backbone's shapes, at the accuracy a 10-bit mantissa allows (and that it really ran);
   * the registration metrics of experiments/eval.py:221-231 (RR with RRE < 5 deg and RTE < 2 m, mean RRE / RTE over the registered
-    pairs) on synthetic KITTI-shaped pairs with known ground truth and on the bundled KITTI pairs (ground truth = the reference's
-    fp32 pose), tf32 mode vs the fp32 mode: same RR, mean RRE within 0.02 deg, mean RTE within 0.5 cm."""
+    pairs) on synthetic KITTI-shaped pairs with known ground truth, tf32 mode vs the fp32 mode: same RR, mean RRE within
+    0.02 deg, mean RTE within 0.5 cm; the bundled KITTI pairs (no ground truth) must stay registered with
+    respect to the reference's fp32 pose."""
 import numpy as np
 import pytest
 import torch

@@ -164,6 +164,31 @@ def test_residual_block_gradients(cloud, strided):
     assert worst <= 1e-4
 
 
+@pytest.mark.parametrize("case", [0, 1])
+def test_ground_truth_overlap_kernels_vs_reference_golden(case):
+    """rdm_node_correspondences / rdm_node_distance_mask through rdmnet_b200.registration against the outputs of the reference's
+    own get_node_correspondences / get_node_overlap / get_node_correspondences_disance (matching.py:252-503) on seeded patches
+    (tests/golden/gt_small.npz, generated by tests/golden/make_golden_gt.py importing the reference): the sphere-test matrix and
+    the correspondence index list exactly (row-major order), the overlap ratios to float rounding."""
+    from rdmnet_b200 import registration as R
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "gt_small.npz")))
+    p = f"c{case}_"
+    c = lambda k, dt=None: torch.from_numpy(g[p + k]).cuda() if dt is None else torch.from_numpy(g[p + k]).to(dt).cuda()  # noqa: E731
+    args = (c("ref_nodes"), c("src_nodes"), c("ref_knn"), c("src_knn"), c("T"), 0.6)
+    kw = dict(ref_masks=c("ref_masks"), src_masks=c("src_masks"), ref_knn_masks=c("ref_knn_masks"), src_knn_masks=c("src_knn_masks"))
+    mask = R.get_node_correspondences(*args, return_mask=True, **kw)
+    assert torch.equal(mask.cpu(), torch.from_numpy(g[p + "sphere_mask"])), "sphere-test matrix"
+    idx, ov = R.get_node_correspondences(*args, **kw)
+    assert idx.dtype == torch.int64 and np.array_equal(idx.cpu().numpy(), g[p + "corr_indices"]), "correspondence indices"
+    check(f"gt case {case} corr_overlaps", ov, torch.from_numpy(g[p + "corr_overlaps"]), 1e-6)
+    b = min(g[p + "ref_nodes"].shape[0], g[p + "src_nodes"].shape[0])
+    pov = R.get_node_overlap(args[0][:b], args[1][:b], args[2][:b], args[3][:b], args[4], 0.6, ref_masks=kw["ref_masks"][:b],
+                             src_masks=kw["src_masks"][:b], ref_knn_masks=kw["ref_knn_masks"][:b], src_knn_masks=kw["src_knn_masks"][:b])
+    check(f"gt case {case} pair overlaps", pov, torch.from_numpy(g[p + "pair_overlaps"]), 1e-6)
+    dmask = R.get_node_correspondences_disance(args[0], args[1], args[4], 2.0, ref_masks=kw["ref_masks"], src_masks=kw["src_masks"])
+    assert torch.equal(dmask.cpu(), torch.from_numpy(g[p + "distance_mask"])), "nearest-node distance mask"
+
+
 def test_ground_truth_ball_query_equals_brute_force():
     """registration.get_correspondences (the GPU stand-in of the cKDTree ball query, geotransformer/utils/registration.py:203-217,
     called by experiments/loss.py:92,151) against an O(MN) double-precision distance matrix: the same pair set."""
