@@ -229,3 +229,58 @@ def run_gpu_eager(model, cfg, pairs, n_steps, n_warm, workers=8):
                 T = out["estimated_transform"]
     dt = time.perf_counter() - t0
     return done, dt, fwd_ms / max(done, 1), T.cpu().numpy()
+
+
+class _TrainPairs(_Pairs):
+    def __getitem__(self, i):
+        d = super().__getitem__(i)
+        d["transform"] = self.pairs[i % len(self.pairs)]["transform"].astype(np.float32)
+        return d
+
+
+def run_gpu_train(state, limits, pairs, n_steps, n_warm, workers=8):
+    """Config 4 denominator: the reference's UNMODIFIED training step on one GPU - experiments/model.py (train-mode forward with
+    ground truth) + experiments/loss.py OverallLoss + loss.backward() + Adam (experiments/trainval.py:34, epoch_based_trainer.py:104),
+    PyTorch eager over its own modules, CPU collate (its C++ extension core) in `workers` DataLoader processes, cKDTree ground
+    truth on the host as in loss.py:92,151. The only shim beyond install(): loss.py:240-243 builds index helpers with bare
+    torch.arange and masks them with CUDA tensors, which torch 2.x rejects - the loss runs under `with torch.device('cuda')`.
+    -> (steps done, seconds, mean CUDA-event ms of forward+loss+backward+step, first and last loss)."""
+    install()
+    import config
+    import loss as loss_mod
+    import model as model_mod
+    from geotransformer.utils.torch import to_cuda
+    cfg = config.make_cfg()
+    cfg.test.vis = False
+    cfg.neighbor_limits = list(limits)
+    net = model_mod.create_model(cfg)
+    net.load_state_dict(state, strict=True)
+    net = net.cuda().train()
+    loss_fn = loss_mod.OverallLoss(cfg).cuda()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, weight_decay=1e-6)
+    loader = torch.utils.data.DataLoader(_TrainPairs(pairs, n_warm + n_steps), batch_size=1, num_workers=workers, shuffle=False,
+                                         collate_fn=_Collate(cfg), persistent_workers=False)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dev_ms, t0, done, losses = 0.0, None, 0, []
+    for i, dd in enumerate(loader):
+        if i == n_warm:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        dd = to_cuda(dd)
+        dd["testing"] = False
+        ev0.record()
+        np.random.seed(1000 + i)
+        out = net(dd)
+        with torch.device("cuda"):
+            ls = loss_fn(out, dd)
+        opt.zero_grad()
+        ls["loss"].backward()
+        opt.step()
+        ev1.record()
+        val = float(ls["loss"].detach())
+        if i >= n_warm:
+            dev_ms += ev0.elapsed_time(ev1)
+            done += 1
+            losses.append(val)
+    dt = time.perf_counter() - t0
+    return done, dt, dev_ms / max(done, 1), (losses[0], losses[-1])

@@ -259,8 +259,32 @@ def reference_gpu_eager(pairs, n_steps=48, n_warm=8, workers=8):
         return {"unavailable": repr(e)[:300]}
 
 
+def run_reference_train(args):
+    """`--train --impl reference`: the unmodified reference's training step on one GPU (baseline/reference_runner.run_gpu_train)."""
+    import torch
+    from baseline import reference_runner as RR
+    ok, why = RR.available()
+    if not ok or not torch.cuda.is_available():
+        emit(json.dumps({"impl": "reference", "unavailable": why or "no CUDA device"}))
+        return
+    pairs = make_pairs(args.pairs, 0)
+    state, wdesc = load_state()
+    done, dt, dev_ms, (l0, l1) = RR.run_gpu_train(state, LIMITS, pairs, args.steps, max(args.warmup, 3))
+    emit(json.dumps({"impl": "reference", "metric": "train_pairs_per_sec", "value": done / dt, "unit": "pairs/s", "n_gpus": 1, "steps": done,
+                     "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / max(done, 1), "higher_is_better": True, "scaling": "weak",
+                     "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                     "config": {"workload": "config 4: training step on a synthetic KITTI pair (~16k pts/scan), batch 1, the UNMODIFIED "
+                                            "reference: experiments/model.py + loss.py + Adam, PyTorch eager on one GPU, CPU collate in 8 "
+                                            "DataLoader workers", "weights": wdesc + " as the starting point", "neighbor_limits": LIMITS},
+                     "device_ms_per_step": dev_ms, "loss_first_last": [l0, l1],
+                     "e2e": {"value": done / dt, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
 def run_reference(args, rank, world):
     if rank != 0:
+        return
+    if args.train:
+        run_reference_train(args)
         return
     pairs = make_pairs(args.pairs, 0)  # the same pairs, step count and warm-up as the repo arm
     cb, done, dt, _ = cpu_arm(pairs, args.steps, args.warmup, budget_s=240.0)
@@ -342,7 +366,24 @@ def run_ours(args, rank, world, local_rank):
     # set-up, not warm-up: every distinct pair once more than the allocator needs to have a cached block for each of its
     # size classes in the pipelined interleaving (a first-time cudaMalloc inside the timed region is a 15-35 ms step)
     n_prime = 2 * len(d_pairs) + 1
-    if pipelined:
+    n_lead = n_prime + args.warmup
+    gen_main = None
+    if pipelined and not pipe.overlap:
+        # ONE generator for set-up, warm-up and the timed steps: the pipeline is not torn down and refilled at the start of the
+        # timed region (a refill puts the first pair's pyramid build, serially, into timed step 0). The barrier + synchronize
+        # between warm-up and timed steps happens with the look-ahead pyramid of the first timed pair already built - as in
+        # every later step, whose pyramid was built during its predecessor.
+        timed_before = [None]
+
+        def lead_before(i):
+            if i < n_lead:
+                warm_hook(i)
+            elif timed_before[0] is not None:
+                timed_before[0](i - n_lead)
+        gen_main = pipe.run((d_pairs[i % len(d_pairs)] for i in range(n_lead + args.steps + 1)), before_step=lead_before)
+        for _ in range(n_lead):
+            next(gen_main)
+    elif pipelined:
         for _ in pipe.run((d_pairs[i % len(d_pairs)] for i in range(n_prime + args.warmup)), before_step=warm_hook):
             pass
     else:
@@ -372,8 +413,8 @@ def run_ours(args, rank, world, local_rank):
     gc.disable()
     clocks.mark_begin()
     t_wall0 = time.perf_counter()
-    if pipelined:
-        # K pairs through the pair pipeline, from an idle GPU to an idle GPU (pipeline fill and drain included). Three pairs are in
+    if pipelined and pipe.overlap:
+        # (opt-in RDM_PIPE_OVERLAP=1) K pairs through the pair pipeline, from an idle GPU to an idle GPU (pipeline fill and drain included). Three pairs are in
         # flight (pyramid of i+2, backbone of i+1, matching tail of i), so steps overlap: the time of the K steps is taken between
         # one event before the first pair enters and the event after the last pair's last kernel, and the L2 flush between pairs is
         # queued on the entering pair's stream INSIDE the timed region (it overlaps the previous pair's tail).
@@ -397,6 +438,24 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         t_wall = time.perf_counter() - t_wall0
         launches = L.launch_count() - launches0
+    elif pipelined:
+        def before(i):
+            if i < args.steps:
+                if i % 6 == 3:
+                    clocks.sample_now()  # under load (the side stream is building the next pyramid), outside the brackets
+                if not no_flush:
+                    flush.fill_(i & 0xFF)
+                ev[i][0].record()
+        timed_before[0] = before
+        gen = gen_main
+        for i in range(args.steps):
+            out = next(gen)
+            ev[i][1].record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        launches = L.launch_count() - launches0
+        for _ in gen:  # the look-ahead pair: untimed
+            pass
     else:
         for i in range(args.steps):
             if i % 6 == 3:
@@ -412,7 +471,7 @@ def run_ours(args, rank, world, local_rank):
     prof = L.prof_read()
     L.prof_enable(False)
     torch.cuda.synchronize()
-    if pipelined:
+    if pipelined and pipe.overlap:
         ends = [t_first] + [b for _, b in ev]
         step_ms = [ends[i].elapsed_time(ends[i + 1]) for i in range(args.steps)]  # completion-to-completion intervals
         total_ms = float(t_first.elapsed_time(ev[-1][1]))
@@ -511,10 +570,10 @@ def run_ours(args, rank, world, local_rank):
                        "points_per_pair": [int(p[0].shape[0]) for p in d_pairs], "neighbor_limits": LIMITS,
                        "weights": wdesc,
                        "l2": ("256 MiB flush write queued before every pair enters the network, INSIDE the timed region (pairs overlap)"
-                              if pipelined else "256 MiB flush write between timed steps (untimed)"),
+                              if (pipelined and pipe.overlap) else "256 MiB flush write between timed steps (untimed)"),
                        "timing": ("K pairs through the pair pipeline from an idle GPU to an idle GPU (fill and drain included): CUDA events "
                                   "before the first pair enters and after the last pair's last kernel; max over ranks; kernel events "
-                                  "recorded inside the library around the gather launches" if pipelined else
+                                  "recorded inside the library around the gather launches" if (pipelined and pipe.overlap) else
                                   "CUDA events per step on the launch stream, summed; max over ranks; kernel events recorded inside the "
                                   "library around the launches"),
                        "sharding": "pairs round-robin over ranks, no data-path collective",
@@ -648,22 +707,37 @@ def run_sweep(args, rank, world, local_rank):
         torch.cuda.synchronize()
         gc.collect(); gc.disable()
 
-        t_first = torch.cuda.Event(enable_timing=True)
-        t_first.record()
-
-        def before(i):
-            flush.fill_(i & 0xFF)
-
-        def after(i, ev=ev):
-            ev[i][1].record()
         n_corr = 0
-        for out in pipe.run(items, before_step=before, after_step=after):
-            n_corr += int(out["corr_scores"].shape[0])
-        torch.cuda.synchronize()
+        if pipe.overlap:
+            t_first = torch.cuda.Event(enable_timing=True)
+            t_first.record()
+
+            def before(i):
+                flush.fill_(i & 0xFF)
+
+            def after(i, ev=ev):
+                ev[i][1].record()
+            for out in pipe.run(items, before_step=before, after_step=after):
+                n_corr += int(out["corr_scores"].shape[0])
+            torch.cuda.synchronize()
+            ms = float(t_first.elapsed_time(ev[-1][1]))  # all pairs of the class through the pipeline, fill and drain included
+        else:
+            def before(i, ev=ev):
+                if i < len(ev):
+                    flush.fill_(i & 0xFF)
+                    ev[i][0].record()
+            gen = pipe.run(items + items[:1], before_step=before)
+            for i in range(len(items)):
+                out = next(gen)
+                ev[i][1].record()
+                n_corr += int(out["corr_scores"].shape[0])
+            torch.cuda.synchronize()
+            for _ in gen:
+                pass
+            ms = float(sum(a.elapsed_time(b) for a, b in ev))
         gc.enable()
         prof = [r for r in L.prof_read() if r[0] == 1]
         L.prof_enable(False)
-        ms = float(t_first.elapsed_time(ev[-1][1]))  # all pairs of the class through the pipeline, fill and drain included
         gb = sum(kpconv_gather_bytes(m_, h_, c_, 64 if c_ == 1 else c_, 4) for _, _, m_, _, h_, c_ in prof)
         gms = sum(r[1] for r in prof)
         t = torch.tensor([float(len(items)), ms, float(gb), gms, float(n_corr), float(sum(int(x[0].shape[0]) for x in items))],
@@ -689,9 +763,8 @@ def run_sweep(args, rank, world, local_rank):
                 "config": {"workload": "config 5: %d-pair synthetic sweep, %d pairs per size class %s (points/scan), round-robin over ranks"
                                        % (args.sweep_pairs, per_class, classes),
                            "distinct_geometries_per_class": distinct, "neighbor_limits": LIMITS,
-                           "l2": "256 MiB flush write queued before every pair enters the network (inside the timed region)",
-                           "timing": "per class: CUDA events around all its pairs through the pair pipeline (idle GPU to idle GPU); "
-                                     "all pairs / slowest rank"},
+                           "l2": "256 MiB flush write between pairs (untimed)",
+                           "timing": "CUDA events per pair on the launch stream; per class: all pairs / slowest rank"},
                 "sweep": res, "roofline_peak": {"hbm_gbs": peak, "source": peak_src}}
         emit(json.dumps(line))
     if world > 1:

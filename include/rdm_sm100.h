@@ -401,6 +401,19 @@ size_t rdm_match_workspace(const rdm_match_desc* h_desc, int nc, int nc_ref, int
 int rdm_match_forward(const rdm_match_desc* h_desc, const rdm_match_io* h_io, rdm_match_result* h_result, void* workspace,
                       size_t workspace_bytes, rdm_stream_t stream);
 
+/* The same tail as a job in three calls, for callers that keep several pairs in flight (rdmnet_b200.model.PairPipeline with
+ * RDM_PIPE_OVERLAP=1): rdm_match_begin queues phase 1 (vote, NMS) and the read-back of the survivor counts and never blocks;
+ * rdm_match_continue waits for those counts only, then queues everything else and the read-back of the result; rdm_match_finish waits
+ * for the result (and redoes the patch stage at the exact count when fewer coarse pairs exist than requested). The job keeps copies
+ * of desc / io; workspace and io buffers must stay alive until rdm_match_finish. One job per pair in flight. */
+void* rdm_match_job_create(void);
+void rdm_match_job_destroy(void* job);
+int rdm_match_job_reset(void* job); /* waits for the job's stream and drops what it has in flight (abandoned pipelines) */
+int rdm_match_begin(void* job, const rdm_match_desc* h_desc, const rdm_match_io* h_io, void* workspace, size_t workspace_bytes,
+                    rdm_stream_t stream);
+int rdm_match_continue(void* job, rdm_match_result* h_result);
+int rdm_match_finish(void* job, rdm_match_result* h_result);
+
 /* ---- index_select(data, index, dim=0) (geotransformer/modules/ops/index_select.py:4-30) on rows of `row_words` 4-byte
  * words: out[i, :] = data[index[i], :], i < count. *err_flag (device int, zeroed by the caller, may be NULL) is set when
  * an index falls outside [0, rows): the host shim raises, as torch.index_select does. */

@@ -96,6 +96,12 @@ SIGNATURES = {
                                c_void_p]),
     "rdm_linear_kn_workspace": (c_size_t, [c_int, c_int, c_int]),
     "rdm_scatter_add_rows": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_int, c_i64, c_void_p, c_void_p]),
+    "rdm_match_job_create": (c_void_p, []),
+    "rdm_match_job_destroy": (None, [c_void_p]),
+    "rdm_match_job_reset": (c_int, [c_void_p]),
+    "rdm_match_begin": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "rdm_match_continue": (c_int, [c_void_p, c_void_p]),
+    "rdm_match_finish": (c_int, [c_void_p, c_void_p]),
     "rdm_backbone_set_encoder_event": (c_int, [c_void_p]),
     "rdm_set_precision": (c_int, [c_int]),
     "rdm_get_precision": (c_int, []),

@@ -650,7 +650,7 @@ struct MatchPinned {
   int meta[4];
   float T[16];
 };
-MatchPinned* g_match_pinned = nullptr;
+
 
 // phase 1: vote + NMS (sizes known). Returns through `io` buffers; sel counts land in pinned memory.
 int match_phase1(Arena& a, const rdm_match_desc& d, const rdm_match_io& io, int* d_counts, cudaStream_t st) {
@@ -778,11 +778,64 @@ extern "C" size_t rdm_match_workspace(const rdm_match_desc* h_desc, int nc, int 
   return match_ws(*h_desc, nc, nc_ref, nf, nf_ref);
 }
 
-extern "C" int rdm_match_forward(const rdm_match_desc* h_desc, const rdm_match_io* h_io, rdm_match_result* h_result, void* workspace,
-                                 size_t workspace_bytes, cudaStream_t stream) {
-  RDM_CHECK_ARG(h_desc && h_io && h_result && h_desc->h_transformer2, "rdm_match_forward: null argument");
-  const rdm_match_desc& d = *h_desc;
-  const rdm_match_io& io = *h_io;
+// ---- the matching tail as a job in three host calls, for callers that keep several pairs in flight (PairPipeline):
+//   rdm_match_begin     phase 1 (vote, NMS) + asynchronous read-back of the survivor counts            - never blocks
+//   rdm_match_continue  waits for those counts (they fix every shape below), queues phase 2 + read-back - blocks on phase 1 only
+//   rdm_match_finish    waits for the result counts + pose; the rare exact-count redo of the patch stage
+// rdm_match_forward is the three in a row.
+namespace {
+struct MatchJob {
+  MatchPinned* pinned = nullptr;
+  cudaEvent_t counts_ready = nullptr, result_ready = nullptr;
+  rdm_match_desc d;
+  rdm_match_io io;
+  void* workspace = nullptr;
+  size_t workspace_bytes = 0, arena_off = 0;
+  int* d_cnt = nullptr;
+  cudaStream_t stream = nullptr;
+  int n0 = 0, n1 = 0, stage = 0;  // stage: 0 idle, 1 begun, 2 continued
+};
+}  // namespace
+
+extern "C" void* rdm_match_job_create(void) {
+  MatchJob* j = new MatchJob();
+  if (cudaHostAlloc((void**)&j->pinned, sizeof(MatchPinned), cudaHostAllocDefault) != cudaSuccess ||
+      cudaEventCreateWithFlags(&j->counts_ready, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&j->result_ready, cudaEventDisableTiming) != cudaSuccess) {
+    rdm_set_error("rdm_match_job_create: CUDA resource allocation failed");
+    delete j;
+    return nullptr;
+  }
+  return j;
+}
+
+extern "C" void rdm_match_job_destroy(void* job) {
+  MatchJob* j = (MatchJob*)job;
+  if (j == nullptr) return;
+  if (j->pinned) cudaFreeHost(j->pinned);
+  if (j->counts_ready) cudaEventDestroy(j->counts_ready);
+  if (j->result_ready) cudaEventDestroy(j->result_ready);
+  delete j;
+}
+
+// abandons whatever the job has in flight (waits for its stream first): for callers that stop consuming a pipeline half-way
+extern "C" int rdm_match_job_reset(void* job) {
+  MatchJob* j = (MatchJob*)job;
+  RDM_CHECK_ARG(j != nullptr, "rdm_match_job_reset: null job");
+  if (j->stage != 0) RDM_CUDA(cudaStreamSynchronize(j->stream));
+  j->stage = 0;
+  return RDM_OK;
+}
+
+extern "C" int rdm_match_begin(void* job, const rdm_match_desc* h_desc, const rdm_match_io* h_io, void* workspace, size_t workspace_bytes,
+                               cudaStream_t stream) {
+  MatchJob* j = (MatchJob*)job;
+  RDM_CHECK_ARG(j && h_desc && h_io && h_desc->h_transformer2, "rdm_match_begin: null argument");
+  RDM_CHECK_ARG(j->stage == 0, "rdm_match_begin: the job is still in flight (finish it first)");
+  j->d = *h_desc;
+  j->io = *h_io;
+  const rdm_match_desc& d = j->d;
+  const rdm_match_io& io = j->io;
   RDM_CHECK_ARG(io.nc >= 1 && io.nc_ref >= 0 && io.nc_ref <= io.nc && io.nf >= 1 && io.nf_ref >= 0 && io.nf_ref <= io.nf &&
                     d.point_limit == 128 && d.num_correspondences >= 1 && d.num_correspondences <= 1024 && d.c >= 16,
                 "rdm_match_forward: bad sizes");
@@ -790,36 +843,86 @@ extern "C" int rdm_match_forward(const rdm_match_desc* h_desc, const rdm_match_i
     rdm_set_error("rdm_match_forward: workspace too small");
     return RDM_ERR_WORKSPACE;
   }
-  if (g_match_pinned == nullptr) RDM_CUDA(cudaHostAlloc((void**)&g_match_pinned, sizeof(MatchPinned), cudaHostAllocDefault));
+  j->workspace = workspace;
+  j->workspace_bytes = workspace_bytes;
+  j->stream = stream;
   Arena a(workspace, workspace_bytes, false);
-  int* d_cnt = (int*)a.raw(256);  // [0,1] NMS counts, [2] coarse count, [4..7] LGR meta
-  RDM_TRY(match_phase1(a, d, io, d_cnt, stream));
-  RDM_CUDA(cudaMemcpyAsync(g_match_pinned->counts, d_cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
-  RDM_CUDA(cudaStreamSynchronize(stream));  // sync 1: survivor counts = the shapes of everything below
-  const int n0 = g_match_pinned->counts[0], n1 = g_match_pinned->counts[1];
+  j->d_cnt = (int*)a.raw(256);  // [0,1] NMS counts, [2] coarse count, [4..7] LGR meta
+  RDM_TRY(match_phase1(a, d, io, j->d_cnt, stream));
+  j->arena_off = a.off;
+  RDM_CUDA(cudaMemcpyAsync(j->pinned->counts, j->d_cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+  RDM_CUDA(cudaEventRecord(j->counts_ready, stream));
+  j->stage = 1;
+  return RDM_OK;
+}
+
+extern "C" int rdm_match_continue(void* job, rdm_match_result* h_result) {
+  MatchJob* j = (MatchJob*)job;
+  RDM_CHECK_ARG(j && h_result && j->stage == 1, "rdm_match_continue: call rdm_match_begin first");
+  const rdm_match_desc& d = j->d;
+  const rdm_match_io& io = j->io;
+  j->stage = 0;  // an error below leaves the job reusable
+  RDM_CUDA(cudaEventSynchronize(j->counts_ready));  // sync 1: survivor counts = the shapes of everything below
+  const int n0 = j->pinned->counts[0], n1 = j->pinned->counts[1];
   RDM_CHECK_ARG(n0 >= 0 && n1 >= 0 && n0 <= io.nc_ref && n1 <= io.nc - io.nc_ref, "rdm_match_forward: inconsistent NMS counts");
   h_result->n_ref_sel = n0;
   h_result->n_src_sel = n1;
   h_result->num_patches = 0;
   h_result->num_corr = 0;
   RDM_CHECK_ARG(n0 >= 1 && n1 >= 1, "rdm_match_forward: no superpoint survived NMS in one of the clouds");
-  RDM_TRY(match_phase2(a, d, io, n0, n1, d_cnt + 2, d_cnt + 4, stream));
-  RDM_CUDA(cudaMemcpyAsync(&g_match_pinned->coarse_count, d_cnt + 2, sizeof(int), cudaMemcpyDeviceToHost, stream));
-  RDM_CUDA(cudaMemcpyAsync(g_match_pinned->meta, d_cnt + 4, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
-  RDM_CUDA(cudaMemcpyAsync(g_match_pinned->T, io.transform, 16 * sizeof(float), cudaMemcpyDeviceToHost, stream));
-  RDM_CUDA(cudaStreamSynchronize(stream));  // sync 2: result counts + pose
-  if (g_match_pinned->coarse_count < d.num_correspondences) {
+  j->n0 = n0;
+  j->n1 = n1;
+  Arena a(j->workspace, j->workspace_bytes, false);
+  a.off = j->arena_off;
+  cudaStream_t stream = j->stream;
+  RDM_TRY(match_phase2(a, d, io, n0, n1, j->d_cnt + 2, j->d_cnt + 4, stream));
+  j->arena_off = a.off;
+  RDM_CUDA(cudaMemcpyAsync(&j->pinned->coarse_count, j->d_cnt + 2, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  RDM_CUDA(cudaMemcpyAsync(j->pinned->meta, j->d_cnt + 4, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+  RDM_CUDA(cudaMemcpyAsync(j->pinned->T, io.transform, 16 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+  RDM_CUDA(cudaEventRecord(j->result_ready, stream));
+  j->stage = 2;
+  return RDM_OK;
+}
+
+extern "C" int rdm_match_finish(void* job, rdm_match_result* h_result) {
+  MatchJob* j = (MatchJob*)job;
+  RDM_CHECK_ARG(j && h_result && j->stage == 2, "rdm_match_finish: call rdm_match_continue first");
+  const rdm_match_desc& d = j->d;
+  const rdm_match_io& io = j->io;
+  j->stage = 0;
+  RDM_CUDA(cudaEventSynchronize(j->result_ready));  // sync 2: result counts + pose
+  if (j->pinned->coarse_count < d.num_correspondences) {
     // fewer valid node pairs than requested (tiny clouds): the speculative pass saw padding patches; redo it at the
     // exact count. superpoint_matching.py:52-53 takes min(num_correspondences, #pairs).
-    const int P = g_match_pinned->coarse_count;
+    const int P = j->pinned->coarse_count;
     RDM_CHECK_ARG(P >= 1, "rdm_match_forward: no coarse correspondence");
-    RDM_TRY(match_patches(a, d, io, n0, P, d_cnt + 4, stream));
-    RDM_CUDA(cudaMemcpyAsync(g_match_pinned->meta, d_cnt + 4, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
-    RDM_CUDA(cudaMemcpyAsync(g_match_pinned->T, io.transform, 16 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    Arena a(j->workspace, j->workspace_bytes, false);
+    a.off = j->arena_off;
+    cudaStream_t stream = j->stream;
+    RDM_TRY(match_patches(a, d, io, j->n0, P, j->d_cnt + 4, stream));
+    RDM_CUDA(cudaMemcpyAsync(j->pinned->meta, j->d_cnt + 4, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    RDM_CUDA(cudaMemcpyAsync(j->pinned->T, io.transform, 16 * sizeof(float), cudaMemcpyDeviceToHost, stream));
     RDM_CUDA(cudaStreamSynchronize(stream));
   }
-  h_result->num_patches = g_match_pinned->coarse_count;
-  h_result->num_corr = g_match_pinned->meta[0];
-  memcpy(h_result->transform, g_match_pinned->T, sizeof(float) * 16);
+  h_result->n_ref_sel = j->n0;
+  h_result->n_src_sel = j->n1;
+  h_result->num_patches = j->pinned->coarse_count;
+  h_result->num_corr = j->pinned->meta[0];
+  memcpy(h_result->transform, j->pinned->T, sizeof(float) * 16);
   return RDM_OK;
+}
+
+extern "C" int rdm_match_forward(const rdm_match_desc* h_desc, const rdm_match_io* h_io, rdm_match_result* h_result, void* workspace,
+                                 size_t workspace_bytes, cudaStream_t stream) {
+  static void* job = nullptr;  // one caller thread per runner (rdm_sm100.h)
+  RDM_CHECK_ARG(h_desc && h_io && h_result && h_desc->h_transformer2, "rdm_match_forward: null argument");
+  if (job == nullptr) job = rdm_match_job_create();
+  if (job == nullptr) return RDM_ERR_CUDA;
+  ((MatchJob*)job)->stage = 0;  // a previous call that failed half-way leaves nothing in flight that matters here
+  int rc = rdm_match_begin(job, h_desc, h_io, workspace, workspace_bytes, stream);
+  if (rc != RDM_OK) return rc;
+  rc = rdm_match_continue(job, h_result);
+  if (rc != RDM_OK) return rc;
+  return rdm_match_finish(job, h_result);
 }

@@ -212,16 +212,19 @@ _PIPE_STREAMS = {}
 
 class PairPipeline:
     """Software pipeline over a stream of scan pairs, single host thread, results in input order and identical to
-    model(data_dict) pair by pair. Three pairs are in flight (RDM_PIPE_OVERLAP=0: two):
+    model(data_dict) pair by pair. Default: two pairs in flight - while pair i runs through the network on the main stream, the
+    voxel pyramid of pair i+1 is built on a side stream (what the reference's DataLoader workers do on CPU cores,
+    geotransformer/utils/data.py:223-253 with num_workers=8).
 
-        side stream      pyramid of pair i+2 (what the reference's DataLoader workers do on CPU cores, utils/data.py:223-253)
+    RDM_PIPE_OVERLAP=1 (opt-in) keeps three in flight:
+        side stream      pyramid of pair i+2
         net stream A/B   encoder -> transformer 1 -> decoder of pair i+1   (forward_head, asynchronous)
         net stream B/A   vote / NMS / transformer 2 / matching / pose of pair i   (forward_tail, two host syncs)
-
-    The path is a chain of ~330 small dependent kernels per pair (3.4 ms for a 8k-point pair, 4.3 ms for a 37k-point pair:
-    latency, not throughput), so two network passes share the GPU well - except the KPConv gathers, which are bandwidth-bound
-    and are therefore kept alone: the matching tail of pair i and the radius searches of pair i+2 wait for the event that
-    rdm_backbone_forward records after the encoder of pair i+1."""
+    with the matching tail of pair i and the radius searches of pair i+2 held behind the event that rdm_backbone_forward records
+    after the encoder of pair i+1, so that the bandwidth-bound KPConv gathers keep the machine to themselves. Measured
+    (profiles/README.md, r2u): median step 4.10-4.16 ms against 4.18-4.22 ms, end to end 232-240 against 234-236 pairs/s - within
+    noise, because the cycle stays encoder(i+1) -> tail(i) -> [host] -> encoder(i+2): the host thread is blocked inside the tail's two
+    stream synchronisations and cannot queue the next head earlier. It stays off until rdm_match_forward loses its host syncs."""
 
     def __init__(self, model, device=None):
         self.model = model
@@ -241,6 +244,7 @@ class PairPipeline:
             res = _PIPE_STREAMS[self.device] = (side, nets, enc_done)
         self.side, self.nets, self.enc_done = res
         self.jobs = [PyramidJob(), PyramidJob()]
+        self.match_jobs = None
         # the next pair's radius searches are held back until the pair in the network has left its encoder, so that they share
         # the SMs with the (latency-bound) rest instead of with the KPConv gathers: measured +10 % gather
         # bandwidth and +2 % pairs/s inside the pipelined bench region (profiles/README.md, r2a). RDM_PIPE_DEFER_SEARCH=0
@@ -327,7 +331,19 @@ class PairPipeline:
         return state
 
     def _run_overlapped(self, items, before_step, after_step):
+        """Host order per iteration i (nothing here blocks on more than it needs):
+            begin(i)      phase 1 of the tail of pair i, queued right behind its head on net stream i & 1
+            head(i+1)     on the other net stream (after launching the subsampling chain of pair i+2 on the side stream)
+            pyramid(i+2)  finish: its radius searches wait for the encoder of pair i+1
+            continue(i)   host waits for the NMS counts of pair i; the rest of its tail waits for the encoder of pair i+1 (stream)
+            finish(i-1)   host waits for the result of pair i-1 -> yield
+        GPU order: net stream i & 1 carries head(i), tail(i), head(i+2), ... so encoder(i+2) starts the moment tail(i) ends, with no
+        host round trip in between; the cycle is encoder + max(transformer 1 + decoder, tail)."""
         caller = torch.cuda.current_stream(self.device)
+        if self.match_jobs is None:
+            self.match_jobs = [L.lib().rdm_match_job_create() for _ in range(4)]
+            if any(j is None for j in self.match_jobs):
+                raise RuntimeError("rdm_match_job_create failed: " + L.lib().rdm_last_error().decode())
         it = iter(items)
         first = next(it, None)
         if first is None:
@@ -337,40 +353,66 @@ class PairPipeline:
         with torch.cuda.stream(self.side):
             self._begin(first, 0)
             pyr = self._finish(0)
-        state = self._head(0, pyr, before_step)
-        pyr_next = None
         nxt = next(it, None)
         if nxt is not None:
             with torch.cuda.stream(self.side):
                 self._begin(nxt, 1)
+        state = self._head(0, pyr, before_step)
+        pyr_next = None
+        if nxt is not None:
+            with torch.cuda.stream(self.side):
                 if self.defer_searches:
                     self.side.wait_event(self.enc_done[0])
                 pyr_next = self._finish(1)
-        i = 0
+        def emit(p):  # p = (index, ctx or None, finished output or None) of the pair whose tail is in flight
+            idx, ctx, sync_out = p
+            out = self.model._match_finish(ctx) if ctx is not None else sync_out
+            for v in out.values():  # produced on a net stream, consumed by the caller on its own stream
+                if torch.is_tensor(v) and v.is_cuda:
+                    v.record_stream(caller)
+            return out
+
+        try:
+            yield from self._overlapped_loop(it, state, pyr_next, before_step, after_step, emit)
+        finally:  # a consumer that stops early (or an error) must not leave jobs "in flight" for the next run
+            for j in self.match_jobs:
+                L.call("rdm_match_job_reset", j)
+
+    def _overlapped_loop(self, it, state, pyr_next, before_step, after_step, emit):
+        pending, i = None, 0
         while state is not None:
+            s = self.nets[i & 1]
+            with torch.cuda.stream(s):
+                ctx = self.model.tail_begin(state, self.match_jobs[i & 3])
             state_next = None
             if pyr_next is not None:
-                state_next = self._head(i + 1, pyr_next, before_step)  # queued BEFORE the tail of pair i
-                pyr_next = None
                 nxt = next(it, None)
                 if nxt is not None:
                     with torch.cuda.stream(self.side):
                         self._begin(nxt, i & 1)  # job slot of pair i, whose pyramid was handed over long ago
+                state_next = self._head(i + 1, pyr_next, before_step)
+                pyr_next = None
+                if nxt is not None:
+                    with torch.cuda.stream(self.side):
                         if self.defer_searches:
                             self.side.wait_event(self.enc_done[(i + 1) & 1])
                         pyr_next = self._finish(i & 1)
-            s = self.nets[i & 1]
+            sync_out = None
             with torch.cuda.stream(s):
                 if state_next is not None and self.gather_alone:
                     s.wait_event(self.enc_done[(i + 1) & 1])  # the gathers of pair i+1 run alone
-                out = self.model.forward_tail(state)  # ends with a host sync of this stream
+                if ctx is not None:
+                    self.model._match_continue(ctx)
+                else:  # configurations without the runner tail (no vote branch / stepwise): synchronous
+                    sync_out = self.model.forward_tail(state)
                 if after_step is not None:
-                    after_step(i)
-            for v in out.values():  # produced on a net stream, consumed by the caller on its own stream
-                if torch.is_tensor(v) and v.is_cuda:
-                    v.record_stream(caller)
-            yield out
+                    after_step(i)  # right behind the pair's last kernel, before the head of pair i+2 lands on this stream
+            if pending is not None:
+                yield emit(pending)
+            pending = (i, ctx, sync_out)
             state, i = state_next, i + 1
+        if pending is not None:
+            yield emit(pending)
 
 
 def _state_key(module):
@@ -705,8 +747,9 @@ class RDMNet(_Module):
             self._mdesc, self._mdesc_keep, self._mdesc_key = d, (t2, alpha, ps_keep), key
         return self._mdesc
 
-    def _match_tail(self, out, points_c, lengths_c, nc_ref, tf, n2p, points_f, nf_ref, feats_f):
-        """model_infer.py:180-354 through rdm_match_forward (one host call, two internal synchronisations)."""
+    def _match_tail(self, out, points_c, lengths_c, nc_ref, tf, n2p, points_f, nf_ref, feats_f, job=None):
+        """model_infer.py:180-354 through rdm_match_forward (one host call, two internal synchronisations) or, with a match
+        `job`, only its asynchronous first phase (rdm_match_begin)."""
         d = self._match_desc()
         if feats_f.shape[1] != d.c:
             raise RuntimeError(f"rdm_match_forward gathers {d.c}-channel fine features (the vote / transformer width) and scales "
@@ -737,8 +780,26 @@ class RDMNet(_Module):
         wsb = int(lib.rdm_match_workspace(ctypes.byref(d), nc, nc_ref, nf, nf_ref))
         ws = torch.empty(max(wsb, 1), dtype=u8, device=dev)
         res = L.MatchResult()
+        if job is not None:  # asynchronous form: phase 1 only; _match_continue / _match_finish complete it
+            with torch.cuda.device(dev):
+                L.call("rdm_match_begin", job, ctypes.byref(d), ctypes.byref(io), L.ptr(ws), wsb, L.stream())
+            return dict(out=out, B=B, io=io, ws=ws, res=res, job=job, nc_ref=nc_ref, keep=(points_c, lengths_c, tf, n2p, points_f, feats_f))
         with torch.cuda.device(dev):
             L.call("rdm_match_forward", ctypes.byref(d), ctypes.byref(io), ctypes.byref(res), L.ptr(ws), wsb, L.stream())
+        return self._match_outputs(out, B, res, nc_ref)
+
+    def _match_continue(self, ctx):
+        """Waits for the NMS survivor counts of the pair (host), queues the rest of the tail (rdm_match_continue)."""
+        L.call("rdm_match_continue", ctx["job"], ctypes.byref(ctx["res"]))
+
+    def _match_finish(self, ctx):
+        """Waits for the pair's result counts + pose (host) and assembles the output dict."""
+        L.call("rdm_match_finish", ctx["job"], ctypes.byref(ctx["res"]))
+        return self._match_outputs(ctx["out"], ctx["B"], ctx["res"], ctx["nc_ref"])
+
+    @staticmethod
+    def _match_outputs(out, B, res, nc_ref):
+        f32 = torch.float32
         n0, n1, k, ncorr = res.n_ref_sel, res.n_src_sel, res.num_patches, res.num_corr
         out["shifted_ref_points_c"], out["shifted_src_points_c"] = B["shifted"][:nc_ref], B["shifted"][nc_ref:]
         out["mask"] = B["mask"].view(torch.bool)  # 0/1 bytes reinterpreted: no conversion kernel
@@ -814,6 +875,15 @@ class RDMNet(_Module):
                 src_n2p)
 
     @torch.no_grad()
+    def tail_begin(self, state, job):
+        """Asynchronous first phase of forward_tail (vote + NMS) on the current stream -> context for tail_continue / tail_finish.
+        Only the runner path (vote branch on, not stepwise) has it; returns None otherwise."""
+        (out, data_dict, points_c, lengths_c, nc, tf, n2p, points_f, nf, feats_f, ref_points_f, src_points_f, ref_n2p,
+         src_n2p) = state
+        if not (self.use_vote and not data_dict.get("stepwise", False)):
+            return None
+        return self._match_tail(out, points_c.contiguous(), lengths_c, nc, tf, n2p, points_f.contiguous(), nf, feats_f, job=job)
+
     def forward_tail(self, state):
         """Everything after the decoder (model_infer.py:180-354)."""
         (out, data_dict, points_c, lengths_c, nc, tf, n2p, points_f, nf, feats_f, ref_points_f, src_points_f, ref_n2p,

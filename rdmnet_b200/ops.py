@@ -129,7 +129,10 @@ def linear(x, weight, bias=None, weight_is_kn=False, act=0):
     m, k = x.shape
     n = weight.shape[1] if weight_is_kn else weight.shape[0]
     out = torch.empty((m, n), dtype=torch.float32, device=x.device)
-    wsb = L.lib().rdm_linear_workspace(m, n, k) if m * n <= (1 << 20) else 0
+    if weight_is_kn:  # room for the transposed copy that keeps a [K,N]-layout weight on the tensor cores
+        wsb = L.lib().rdm_linear_kn_workspace(m, n, k)
+    else:
+        wsb = L.lib().rdm_linear_workspace(m, n, k) if m * n <= (1 << 20) else 0
     ws = _ws(wsb, x.device) if wsb else None
     L.call("rdm_linear", L.ptr(x), k, L.ptr(weight), weight.shape[1], 0 if weight_is_kn else 1, L.ptr(bias), L.ptr(out),
            n, m, n, k, act, L.ptr(ws), wsb, L.stream())
