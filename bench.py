@@ -485,14 +485,16 @@ def run_ours(args, rank, world, local_rank):
     host_pairs = [(pairs[i % len(pairs)]["ref_points"], pairs[i % len(pairs)]["src_points"]) for i in range(max(args.steps, 3))]
     if pipelined:
         reg = PairStreamRegistrar(model, max_points=maxp, device=dev)
-        for res in reg.register_stream([host_pairs[i % len(host_pairs)] for i in range(max(args.warmup, 3) + len(pairs))]):
+        for res in reg.register_stream([host_pairs[i % len(host_pairs)] for i in range(n_lead)]):
             pass  # warm-up: every distinct pair through the host-buffer path (pinned staging + allocator blocks of its sizes)
         barrier()
         gc.collect()
         gc.disable()
+        e2e_allocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
         t0 = time.perf_counter()
+        e2e_marks = [t0]
         for res in reg.register_stream(host_pairs[:args.steps]):
-            pass
+            e2e_marks.append(time.perf_counter())
         barrier()
         e2e_s = time.perf_counter() - t0
         gc.enable()
@@ -512,6 +514,12 @@ def run_ours(args, rank, world, local_rank):
         gc.enable()
         api_name = "rdmnet_b200.api.PairRegistrar.register (host numpy in, host numpy out)"
 
+    e2e_intervals = None
+    if pipelined:
+        iv = np.diff(np.asarray(e2e_marks)) * 1e3
+        e2e_intervals = {"cudaMallocs": int(torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - e2e_allocs0),
+                         "min": float(iv.min()), "median": float(np.median(iv)), "max": float(iv.max()),
+                         "over_2x_median": [[int(i), round(float(t), 1)] for i, t in enumerate(iv) if t > 2 * np.median(iv)]}
     # ---- untimed extra pass (rank 0): the KPConv weight GEMMs bracketed with CUDA events for the tensor-pipe roofline entry
     # (the brackets break the programmatic-dependent-launch chain, which is why they are off inside the timed regions),
     # and one plain forward per distinct pair whose pose / correspondence count the cpu_baseline leg is compared with
@@ -588,6 +596,7 @@ def run_ours(args, rank, world, local_rank):
                               "outlier_steps": [int(i) for i, t in enumerate(step_ms) if t > 1.5 * float(np.median(step_ms))]},
             "e2e": {"value": world * args.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": reg.h2d_bytes,
                     "d2h_bytes_per_step": reg.d2h_bytes, "ms_per_step": e2e_ms / args.steps,
+                    "result_interval_ms": e2e_intervals,
                     "api": api_name},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "kpconv_gather_sparse_kernel (13 launches/step) + kpconv_gather_c1_kernel (1)", "bound": "hbm",
@@ -708,6 +717,7 @@ def run_sweep(args, rank, world, local_rank):
         gc.collect(); gc.disable()
 
         n_corr = 0
+        allocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
         if pipe.overlap:
             t_first = torch.cuda.Event(enable_timing=True)
             t_first.record()
@@ -753,7 +763,8 @@ def run_sweep(args, rank, world, local_rank):
                   "mean_points_per_pair": float(allt[:, 5].sum() / n_tot), "mean_corr": float(allt[:, 4].sum() / n_tot),
                   "gather_GBps": float(allt[:, 2].sum() / 1e9 / (allt[:, 3].sum() / 1e3)),
                   "gather_frac": float(allt[:, 2].sum() / 1e9 / (allt[:, 3].sum() / 1e3) / peak),
-                  "per_rank_ms": [float(x) for x in allt[:, 1]]}
+                  "per_rank_ms": [float(x) for x in allt[:, 1]],
+                  "cudaMallocs_in_timed_region_rank0": int(torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - allocs0)}
     if rank == 0:
         n_all = sum(v["pairs"] for v in res.values())
         t_all = sum(max(v["per_rank_ms"]) for v in res.values())

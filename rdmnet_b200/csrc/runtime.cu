@@ -711,8 +711,10 @@ int match_patches(Arena& a, const rdm_match_desc& d, const rdm_match_io& io, int
 }
 
 // phase 2: everything after the node selection, for n0 ref / n1 src survivors (capacities when dry)
+// fork / join (optional): the two point-to-node partitions only need the selected node coordinates, so they run on the library's
+// side stream next to transformer 2 instead of behind it (~0.2 ms of a 1.5 ms tail)
 int match_phase2(Arena& a, const rdm_match_desc& d, const rdm_match_io& io, int n0, int n1, int* d_coarse_count, int* d_meta,
-                 cudaStream_t st) {
+                 cudaStream_t st, cudaEvent_t fork = nullptr, cudaEvent_t join = nullptr) {
   const int c = d.c, K = d.point_limit, P = d.num_correspondences;
   const int ns = n0 + n1;
   size_t mark = a.off;
@@ -724,6 +726,28 @@ int match_phase2(Arena& a, const rdm_match_desc& d, const rdm_match_io& io, int 
     const int cc[4] = {3, c, 1, 1}, ld[4] = {3, c, 1, 1};
     RDM_TRY(rdm_gather_rows(src, dst, cc, ld, 4, io.selected, ns, st));
   }
+  const bool dual = !a.dry && fork != nullptr && join != nullptr && g_side.ready();
+  // point_to_node_partition x2 (model.py:267-272): needs sel_points only
+  {
+    int* p2n = (int*)a.raw(sizeof(int) * (size_t)io.nf);
+    const size_t w0 = rdm_point_to_node_workspace(io.nf_ref, n0 > 0 ? n0 : 1), w1 = rdm_point_to_node_workspace(io.nf - io.nf_ref, n1 > 0 ? n1 : 1);
+    void* ws0 = a.raw(w0);
+    void* ws1 = a.raw(w1);
+    if (!a.dry) {
+      cudaStream_t ps = st;
+      if (dual) {
+        RDM_CUDA(cudaEventRecord(fork, st));
+        RDM_CUDA(cudaStreamWaitEvent(g_side.stream, fork, 0));
+        ps = g_side.stream;
+      }
+      RDM_TRY(rdm_point_to_node(io.points_f, io.nf_ref, io.sel_points, n0, K, p2n, io.node_masks, io.knn_indices, io.knn_masks, ws0,
+                                w0, ps));
+      RDM_TRY(rdm_point_to_node(io.points_f + 3 * (size_t)io.nf_ref, io.nf - io.nf_ref, io.sel_points + 3 * (size_t)n0, n1, K,
+                                p2n + io.nf_ref, io.node_masks + n0, io.knn_indices + (size_t)n0 * K, io.knn_masks + (size_t)n0 * K,
+                                ws1, w1, ps));
+      if (dual) RDM_CUDA(cudaEventRecord(join, ps));
+    }
+  }
   {
     const size_t wsb = rdm_thdroformer_workspace(n0 > 0 ? n0 : 1, n1 > 0 ? n1 : 1, c);
     void* ws = a.raw(wsb);
@@ -732,24 +756,12 @@ int match_phase2(Arena& a, const rdm_match_desc& d, const rdm_match_io& io, int 
                                       sel_feats + (size_t)n0 * c, c, t2, t2 + (size_t)n0 * c, ws, wsb, st));
   }
   if (!a.dry) RDM_TRY(rdm_l2_normalize(t2, io.sel_feats_norm, ns, c, st));
-  // point_to_node_partition x2 (model.py:267-272)
-  {
-    int* p2n = (int*)a.raw(sizeof(int) * (size_t)io.nf);
-    const size_t w0 = rdm_point_to_node_workspace(io.nf_ref, n0 > 0 ? n0 : 1), w1 = rdm_point_to_node_workspace(io.nf - io.nf_ref, n1 > 0 ? n1 : 1);
-    void* ws = a.raw(w0 > w1 ? w0 : w1);
-    if (!a.dry) {
-      RDM_TRY(rdm_point_to_node(io.points_f, io.nf_ref, io.sel_points, n0, K, p2n, io.node_masks, io.knn_indices, io.knn_masks, ws,
-                                w0, st));
-      RDM_TRY(rdm_point_to_node(io.points_f + 3 * (size_t)io.nf_ref, io.nf - io.nf_ref, io.sel_points + 3 * (size_t)n0, n1, K,
-                                p2n + io.nf_ref, io.node_masks + n0, io.knn_indices + (size_t)n0 * K, io.knn_masks + (size_t)n0 * K,
-                                ws, w1, st));
-    }
-  }
   // SuperPointMatching (model.py:308-311)
   {
     float* xy = a.f((size_t)(n0 > 0 ? n0 : 1) * (n1 > 0 ? n1 : 1));
     float* sums = a.f((size_t)ns + 2);
     RDM_TRY(linear(a, io.sel_feats_norm, c, io.sel_feats_norm + (size_t)n0 * c, c, 1, nullptr, xy, n0, n1, c, st));
+    if (dual) RDM_CUDA(cudaStreamWaitEvent(st, join, 0));  // node masks / knn tables from the side stream
     if (!a.dry) {  // slots beyond the produced count stay at pair (0, 0): in range for the speculative patch pass below
       RDM_CUDA(cudaMemsetAsync(io.corr_ref, 0, sizeof(int64_t) * P, st));
       RDM_CUDA(cudaMemsetAsync(io.corr_src, 0, sizeof(int64_t) * P, st));
@@ -786,7 +798,7 @@ extern "C" size_t rdm_match_workspace(const rdm_match_desc* h_desc, int nc, int 
 namespace {
 struct MatchJob {
   MatchPinned* pinned = nullptr;
-  cudaEvent_t counts_ready = nullptr, result_ready = nullptr;
+  cudaEvent_t counts_ready = nullptr, result_ready = nullptr, fork = nullptr, join = nullptr;
   rdm_match_desc d;
   rdm_match_io io;
   void* workspace = nullptr;
@@ -801,7 +813,9 @@ extern "C" void* rdm_match_job_create(void) {
   MatchJob* j = new MatchJob();
   if (cudaHostAlloc((void**)&j->pinned, sizeof(MatchPinned), cudaHostAllocDefault) != cudaSuccess ||
       cudaEventCreateWithFlags(&j->counts_ready, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&j->result_ready, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&j->result_ready, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&j->fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&j->join, cudaEventDisableTiming) != cudaSuccess) {
     rdm_set_error("rdm_match_job_create: CUDA resource allocation failed");
     delete j;
     return nullptr;
@@ -815,6 +829,8 @@ extern "C" void rdm_match_job_destroy(void* job) {
   if (j->pinned) cudaFreeHost(j->pinned);
   if (j->counts_ready) cudaEventDestroy(j->counts_ready);
   if (j->result_ready) cudaEventDestroy(j->result_ready);
+  if (j->fork) cudaEventDestroy(j->fork);
+  if (j->join) cudaEventDestroy(j->join);
   delete j;
 }
 
@@ -875,7 +891,7 @@ extern "C" int rdm_match_continue(void* job, rdm_match_result* h_result) {
   Arena a(j->workspace, j->workspace_bytes, false);
   a.off = j->arena_off;
   cudaStream_t stream = j->stream;
-  RDM_TRY(match_phase2(a, d, io, n0, n1, j->d_cnt + 2, j->d_cnt + 4, stream));
+  RDM_TRY(match_phase2(a, d, io, n0, n1, j->d_cnt + 2, j->d_cnt + 4, stream, j->fork, j->join));
   j->arena_off = a.off;
   RDM_CUDA(cudaMemcpyAsync(&j->pinned->coarse_count, j->d_cnt + 2, sizeof(int), cudaMemcpyDeviceToHost, stream));
   RDM_CUDA(cudaMemcpyAsync(j->pinned->meta, j->d_cnt + 4, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));

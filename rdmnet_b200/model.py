@@ -706,7 +706,14 @@ class RDMNet(_Module):
         wsb = int(lib.rdm_backbone_workspace(ctypes.byref(d), ctypes.byref(desc), nc_ref))
         if wsb == 0:
             raise RuntimeError("rdm_backbone_workspace failed: " + lib.rdm_last_error().decode())
-        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        # the backbone's scratch (~330 MB of transient activations for a 30k-point pair) is kept per stream and only ever grows:
+        # the next use on the same stream is ordered behind this one, and its size varies from pair to pair by a few per cent,
+        # which made the caching allocator fall back to cudaMalloc (a 10-20 ms stall) every now and then
+        key = ("backbone", torch.cuda.current_stream(dev).cuda_stream)
+        cache = self.__dict__.setdefault("_ws_cache", {})
+        ws = cache.get(key)
+        if ws is None or ws.numel() < wsb:
+            ws = cache[key] = torch.empty(int(wsb * 1.25) + (1 << 20), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             L.call("rdm_backbone_forward", ctypes.byref(d), ctypes.byref(desc), nc_ref, L.ptr(feats.contiguous()), ctypes.byref(o),
                    L.ptr(ws), wsb, L.stream())
@@ -884,6 +891,7 @@ class RDMNet(_Module):
             return None
         return self._match_tail(out, points_c.contiguous(), lengths_c, nc, tf, n2p, points_f.contiguous(), nf, feats_f, job=job)
 
+    @torch.no_grad()
     def forward_tail(self, state):
         """Everything after the decoder (model_infer.py:180-354)."""
         (out, data_dict, points_c, lengths_c, nc, tf, n2p, points_f, nf, feats_f, ref_points_f, src_points_f, ref_n2p,
