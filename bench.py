@@ -412,6 +412,8 @@ def run_ours(args, rank, world, local_rank):
     gc.collect()
     gc.disable()
     clocks.mark_begin()
+    if pipelined and pipe.overlap:
+        clocks.sample_now()  # edge sample (see `before` below)
     t_wall0 = time.perf_counter()
     if pipelined and pipe.overlap:
         # (opt-in RDM_PIPE_OVERLAP=1) K pairs through the pair pipeline, from an idle GPU to an idle GPU (pipeline fill and drain included). Three pairs are in
@@ -422,8 +424,11 @@ def run_ours(args, rank, world, local_rank):
         t_first.record()
 
         def before(i):
-            if i % 6 == 3:
-                clocks.sample_now()  # under load, between the queueing of two pairs
+            # ONE clock / throttle query under load, in the middle of the region: with three pairs in flight there is no idle moment
+            # to hide an NVML query in, and each one stalls the launch stream for 5-40 ms (steps 3 and 9 were the outliers of every
+            # run when the region was sampled every 6 steps); two more samples sit right at the region's edges (below)
+            if i == args.steps // 2:
+                clocks.sample_now()
             if not no_flush:
                 flush.fill_(i & 0xFF)
             ev[i][0].record()
@@ -437,6 +442,7 @@ def run_ours(args, rank, world, local_rank):
             pass
         barrier()
         t_wall = time.perf_counter() - t_wall0
+        clocks.sample_now()
         launches = L.launch_count() - launches0
     elif pipelined:
         def before(i):
