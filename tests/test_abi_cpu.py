@@ -105,12 +105,14 @@ def test_bench_reference_arm_emits_contract_line():
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
-def test_bench_gpu_arm_fails_loudly_without_gpu():
-    """The product arm of bench.py has no CPU path: without a CUDA device it must exit non-zero with a clear message and
-    print no JSON line (a silent fallback would void the measurement)."""
+@pytest.mark.parametrize("mode", [[], ["--sweep"], ["--train"], ["--precision", "tf32"]])
+def test_bench_gpu_arm_fails_loudly_without_gpu(mode):
+    """The product arm of bench.py - the default run, the config-5 sweep, the config-4 training steps and the config-3 precision
+    mode - has no CPU path: without a CUDA device it must exit non-zero with a clear message and print no JSON line (a silent
+    fallback would void the measurement)."""
     import subprocess
     import sys
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True,
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"] + mode, capture_output=True,
                          text=True, timeout=300)
     assert out.returncode != 0
     assert "CUDA device" in out.stderr and "no CPU path" in out.stderr
