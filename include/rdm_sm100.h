@@ -408,6 +408,10 @@ int rdm_match_forward(const rdm_match_desc* h_desc, const rdm_match_io* h_io, rd
  * of desc / io; workspace and io buffers must stay alive until rdm_match_finish. One job per pair in flight. */
 void* rdm_match_job_create(void);
 void rdm_match_job_destroy(void* job);
+/* Optional: a cudaEvent_t that the patch stage (patch scores, Sinkhorn, pose) of the NEXT rdm_match_continue / rdm_match_forward calls
+ * waits for on its stream (NULL = off): lets the small-grid front of the tail overlap another pair's encoder while the large-grid
+ * patch stage stays behind it. */
+int rdm_match_set_patch_wait_event(void* cuda_event);
 int rdm_match_job_reset(void* job); /* waits for the job's stream and drops what it has in flight (abandoned pipelines) */
 int rdm_match_begin(void* job, const rdm_match_desc* h_desc, const rdm_match_io* h_io, void* workspace, size_t workspace_bytes,
                     rdm_stream_t stream);

@@ -99,6 +99,7 @@ SIGNATURES = {
     "rdm_match_job_create": (c_void_p, []),
     "rdm_match_job_destroy": (None, [c_void_p]),
     "rdm_match_job_reset": (c_int, [c_void_p]),
+    "rdm_match_set_patch_wait_event": (c_int, [c_void_p]),
     "rdm_match_begin": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "rdm_match_continue": (c_int, [c_void_p, c_void_p]),
     "rdm_match_finish": (c_int, [c_void_p, c_void_p]),

@@ -711,6 +711,7 @@ int match_patches(Arena& a, const rdm_match_desc& d, const rdm_match_io& io, int
 }
 
 // phase 2: everything after the node selection, for n0 ref / n1 src survivors (capacities when dry)
+cudaEvent_t g_patch_wait = nullptr;
 // fork / join (optional): the two point-to-node partitions only need the selected node coordinates, so they run on the library's
 // side stream next to transformer 2 instead of behind it (~0.2 ms of a 1.5 ms tail)
 int match_phase2(Arena& a, const rdm_match_desc& d, const rdm_match_io& io, int n0, int n1, int* d_coarse_count, int* d_meta,
@@ -770,6 +771,10 @@ int match_phase2(Arena& a, const rdm_match_desc& d, const rdm_match_io& io, int 
       RDM_TRY(rdm_coarse_matching(xy, n0, n1, io.node_masks, io.node_masks + n0, P, d.dual_normalization, io.corr_ref, io.corr_src,
                                   io.corr_node_scores, d_coarse_count, sums, st));
   }
+  // optional (rdm_match_set_patch_wait_event): only the patch stage - patch scores, Sinkhorn, pose: the kernels with real
+  // grids - is held behind the caller's event; what precedes it (transformer 2, partitions, coarse matching: <= 108 CTAs at a
+  // time) may share the machine with the next pair's encoder
+  if (!a.dry && g_patch_wait != nullptr) RDM_CUDA(cudaStreamWaitEvent(st, g_patch_wait, 0));
   RDM_TRY(match_patches(a, d, io, n0, P, d_meta, st));
   a.off = mark;
   return RDM_OK;
@@ -832,6 +837,11 @@ extern "C" void rdm_match_job_destroy(void* job) {
   if (j->fork) cudaEventDestroy(j->fork);
   if (j->join) cudaEventDestroy(j->join);
   delete j;
+}
+
+extern "C" int rdm_match_set_patch_wait_event(void* cuda_event) {
+  g_patch_wait = (cudaEvent_t)cuda_event;
+  return RDM_OK;
 }
 
 // abandons whatever the job has in flight (waits for its stream first): for callers that stop consuming a pipeline half-way

@@ -253,6 +253,9 @@ class PairPipeline:
         self.overlap = os.environ.get("RDM_PIPE_OVERLAP", "1") == "1"
         # RDM_PIPE_GATHER_ALONE=0 lets the matching tail of pair i start at once, on top of the encoder of pair i+1 (A/B knob)
         self.gather_alone = os.environ.get("RDM_PIPE_GATHER_ALONE", "1") == "1"
+        # RDM_PIPE_TAIL_EARLY=1: the small-grid front of the tail (transformer 2, partitions, coarse matching) may overlap the next
+        # pair's encoder; only the patch stage (patch scores, Sinkhorn, pose) waits for it
+        self.tail_early = os.environ.get("RDM_PIPE_TAIL_EARLY", "0") == "1"
 
     def _begin(self, item, slot):
         points, lengths = item() if callable(item) else item  # a callable may stage host data (runs on the side stream)
@@ -399,10 +402,17 @@ class PairPipeline:
                         pyr_next = self._finish(i & 1)
             sync_out = None
             with torch.cuda.stream(s):
-                if state_next is not None and self.gather_alone:
+                early = self.tail_early and ctx is not None and state_next is not None and self.gather_alone
+                if state_next is not None and self.gather_alone and not early:
                     s.wait_event(self.enc_done[(i + 1) & 1])  # the gathers of pair i+1 run alone
                 if ctx is not None:
-                    self.model._match_continue(ctx)
+                    if early:  # only the patch stage waits for the encoder of pair i+1 (inside rdm_match_continue)
+                        L.call("rdm_match_set_patch_wait_event", self.enc_done[(i + 1) & 1].cuda_event)
+                    try:
+                        self.model._match_continue(ctx)
+                    finally:
+                        if early:
+                            L.call("rdm_match_set_patch_wait_event", None)
                 else:  # configurations without the runner tail (no vote branch / stepwise): synchronous
                     sync_out = self.model.forward_tail(state)
                 if after_step is not None:
