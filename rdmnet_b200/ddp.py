@@ -41,12 +41,13 @@ class BucketedGradAllReduce:
             self.buckets.append(cur)
         self.flat = [torch.zeros(sum(p.numel() for p in b), dtype=torch.float32, device=b[0].device) for b in self.buckets]
         self.wire = [f if comm_dtype == torch.float32 else torch.zeros_like(f, dtype=comm_dtype) for f in self.flat]
-        self.where = {}
+        self.where, self.views = {}, {}
         for bi, b in enumerate(self.buckets):
             off = 0
             for p in b:
                 self.where[p] = bi
-                p.grad = self.flat[bi][off:off + p.numel()].view_as(p)
+                self.views[p] = self.flat[bi][off:off + p.numel()].view_as(p)
+                p.grad = self.views[p]
                 off += p.numel()
         self.pending = [0] * len(self.buckets)
         self.handles = [None] * len(self.buckets)
@@ -61,6 +62,9 @@ class BucketedGradAllReduce:
     def zero_grad(self):
         for f in self.flat:
             f.zero_()
+        for p, view in self.views.items():  # re-attach views that were dropped with set_to_none
+            if p.grad is None:
+                p.grad = view
 
     def _launch(self, bi):
         if self.world > 1:
@@ -70,6 +74,12 @@ class BucketedGradAllReduce:
 
     def _on_grad(self, p):
         bi = self.where[p]
+        view = self.views[p]
+        if p.grad is not view and p.grad.data_ptr() != view.data_ptr():
+            # somebody replaced the gradient tensor (optimizer.zero_grad(set_to_none=True), a manual `p.grad = None`): adopt the
+            # freshly accumulated values and re-attach the view, instead of reducing a stale bucket slice
+            view.copy_(p.grad)
+            p.grad = view
         self.pending[bi] -= 1
         if self.pending[bi] == 0:
             self._launch(bi)
@@ -78,8 +88,12 @@ class BucketedGradAllReduce:
         """Waits for the bucket collectives and leaves the averaged gradients in place. A bucket whose countdown did not reach zero
         (a parameter received no gradient in this step: its slice is still zero) is reduced here, so that all ranks stay in lock
         step."""
-        for bi in range(len(self.buckets)):
+        for bi, b in enumerate(self.buckets):
             if self.pending[bi] != 0:
+                for p in b:  # no gradient this step and the old tensor dropped (set_to_none): contribute zeros, re-attach the view
+                    if p.grad is None:
+                        self.views[p].zero_()
+                        p.grad = self.views[p]
                 self._launch(bi)
         for bi in range(len(self.buckets)):
             if self.handles[bi] is not None:

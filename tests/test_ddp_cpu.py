@@ -42,7 +42,10 @@ def _worker(rank, world, port, comm_dtype, q):
         grads = []
         for step in range(2):  # two steps: the reducer must re-arm
             x, y = _data(rank + 10 * step)
-            red.zero_grad()
+            if step == 0:
+                red.zero_grad()
+            else:
+                model.zero_grad(set_to_none=True)  # the habit the reducer must survive: gradient tensors are re-created by autograd
             out = model(x)
             if rank == 1 and step == 1:
                 loss = ((out[:, :2] - y[:, :2]) ** 2).mean() * 0.5  # rank-dependent graph: still no dead-lock
