@@ -800,7 +800,10 @@ class RDMNet(_Module):
         if job is not None:  # asynchronous form: phase 1 only; _match_continue / _match_finish complete it
             with torch.cuda.device(dev):
                 L.call("rdm_match_begin", job, ctypes.byref(d), ctypes.byref(io), L.ptr(ws), wsb, L.stream())
-            return dict(out=out, B=B, io=io, ws=ws, res=res, job=job, nc_ref=nc_ref, keep=(points_c, lengths_c, tf, n2p, points_f, feats_f))
+            # everything the job still points at until rdm_match_finish: the buffers, and the descriptor structs (the job keeps a
+            # COPY of `d`, but `d` itself points at the transformer-2 descriptor and the weight tensors of this weights epoch)
+            return dict(out=out, B=B, io=io, ws=ws, res=res, job=job, nc_ref=nc_ref,
+                        keep=(points_c, lengths_c, tf, n2p, points_f, feats_f, d, self._mdesc_keep))
         with torch.cuda.device(dev):
             L.call("rdm_match_forward", ctypes.byref(d), ctypes.byref(io), ctypes.byref(res), L.ptr(ws), wsb, L.stream())
         return self._match_outputs(out, B, res, nc_ref)
